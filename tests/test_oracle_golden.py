@@ -1,0 +1,106 @@
+"""CPU: the NumPy oracle reproduces the golden vectors generated from the live reference
+(oracle/make_golden.py).  This is what pins the oracle."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, relerr
+from oracle import nbody_oracle as O
+
+
+def test_pair_kernels():
+    g = load_golden("pair_kernels.npz")
+    for c in range(int(g["n_cases"])):
+        k = f"c{c:02d}_"
+        q, m, eps, G, dr = g[k + "q"], g[k + "m"], float(g[k + "eps"]), float(g[k + "G"]), g[k + "dr"]
+        assert relerr(O.gravitational_force(q, m, eps, G), g[k + "F"]) < 1e-14
+        assert relerr(O.accelerations(q, m, eps, G), g[k + "acc"]) < 1e-14
+        assert abs(O.dV_d_epsilon(q, m, eps, G) - float(g[k + "dV"])) <= 1e-14 * abs(float(g[k + "dV"]))
+        assert abs(O.softened_potential(q, m, G, eps) - float(g[k + "U"])) <= 1e-14 * abs(float(g[k + "U"]))
+        assert relerr(O.variational_accel(q, m, eps * eps, dr, G), g[k + "da"]) < 1e-14
+
+
+def test_kepler_bug_compatible():
+    g = load_golden("kepler.npz")
+    for row in g["cfunc"]:
+        c = O.kepler_cfunc(row[0])
+        assert np.allclose(c, row[1:], rtol=1e-15, atol=0)
+    for r, v, mu, dt, ro, vo in zip(g["r"], g["v"], g["mu"], g["dt"], g["r_out"], g["v_out"]):
+        r1, v1 = O.kepler_propagate(r, v, mu, dt)
+        assert np.array_equal(r1, ro) and np.array_equal(v1, vo)   # same arithmetic -> same bits
+
+
+@pytest.mark.parametrize("horizon,tol", [(1, 1e-14), (10, 1e-13), (100, 1e-12), (1000, 1e-9)])
+def test_classic_trajectories(horizon, tol):
+    g = load_golden("trajectories.npz")
+    for key in g["names"]:
+        key = str(key)
+        mode = key.split("_")[1]
+        sim = O.OracleSim(g[key + "m"], g[key + "q_in"], g[key + "v_in"], softening=float(g[key + "soft"]),
+                          integrator_mode=mode)
+        assert relerr(sim.v, g[key + "v0"]) < 1e-15                 # COM removal + ctor half kick
+        assert sim.h_sub_ref == pytest.approx(float(g[key + "h_sub_ref"]), rel=1e-15)
+        assert sim.n_sub_for(0.01) == int(g[key + "n_sub"])
+        for _ in range(horizon):
+            sim.step(0.01)
+        assert relerr(sim.q, g[key + f"q{horizon}"]) < tol, key
+        assert relerr(sim.v, g[key + f"v{horizon}"]) < tol * 10, key
+        if horizon == 1000:
+            sim.commit_state()
+            assert relerr(sim.v, g[key + "v_snap"]) < tol * 10
+
+
+def test_whfast_trajectories():
+    g = load_golden("whfast.npz")
+    dt = float(g["dt"])
+    for key in g["names"]:
+        key = str(key)
+        sim = O.OracleSim(g[key + "m"], g[key + "q_in"], g[key + "v_in"], softening=0.0,
+                          integrator_mode="whfast")
+        assert sim.mode == "whfast"
+        assert relerr(sim.v, g[key + "v0"]) < 1e-15
+        done = 0
+        for target, tol in ((1, 1e-14), (10, 1e-13), (100, 1e-11), (500, 1e-9)):
+            for _ in range(target - done):
+                sim.step(dt)
+            done = target
+            assert relerr(sim.q, g[key + f"q{target}"]) < tol, (key, target)
+            assert relerr(sim.v, g[key + f"v{target}"]) < tol * 10, (key, target)
+
+
+# columns whose value is set by chaotic amplification over >1000 steps get a looser gate
+_LOOSE = {"MEGNO": 1e-6, "lyapunov_time": 1e-6, "energy_drift": 1e-5, "angular_momentum_drift": 1e-2}
+
+
+@pytest.mark.parametrize("mode", ["verlet", "yoshida4"])
+def test_feature_rows(mode):
+    g = load_golden(f"features_{mode}.npz")
+    n_steps, dt = int(g["n_steps"]), float(g["dt"])
+    cols = [str(c) for c in g["columns"]]
+    for name in g["names"]:
+        name = str(name)
+        sim = O.OracleSim(g[f"{name}_m"], g[f"{name}_q"], g[f"{name}_v"], softening=float(g[f"{name}_soft"]),
+                          integrator_mode=mode)
+        row = O.run_stability_analysis(sim, n_steps, dt, "full", g[f"{name}_raw_r"], g[f"{name}_raw_v"])
+        for c in cols:
+            if c in ("simulation_id",):
+                continue
+            ref = g[f"{name}__{c}"]
+            if ref.dtype.kind in "US":
+                assert str(row[c]) == str(ref), (name, c)
+                continue
+            ref = float(ref)
+            got = float(row[c])
+            if math.isnan(ref):
+                assert math.isnan(got), (name, c)
+                continue
+            if math.isinf(ref):
+                assert got == ref, (name, c)
+                continue
+            if c in ("energy_drift", "angular_momentum_drift"):
+                # drifts are differences of O(1) numbers: absolute gate at a few ulps of the invariant
+                assert abs(got - ref) <= 1e-13 + _LOOSE[c] * abs(ref), (name, c, got, ref)
+                continue
+            tol = _LOOSE.get(c, 1e-9)
+            assert abs(got - ref) <= tol * max(abs(ref), 1e-12) + 1e-15, (name, c, got, ref)
