@@ -1,0 +1,147 @@
+/* nbody_b200.h -- C ABI of the B200-native NBodySimProject hot path.
+ *
+ * The reference (calkan27/NBodySimProject, pure Python/NumPy) has no FFI of its own: its boundary
+ * is the Python call surface.  Each entry point below replaces the reference
+ * function(s) cited next to it; `nbodysimproject_b200/` binds them with ctypes and INTEGRATION.md
+ * shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types.  `*_f64` / `*_f32` entry points take DEVICE pointers
+ *     (caller-owned, e.g. torch tensors) and a cudaStream_t passed as `void*`; they never allocate,
+ *     never synchronise and are safe to call concurrently on distinct streams.
+ *   - `*_host` entry points take HOST pointers and do H2D -> kernels -> D2H themselves (they own a
+ *     cached per-device workspace); they return after the result is in the host buffers.
+ *   - arrays use the reference's own layouts: m[B][N], q[B][N][2], v[B][N][2] row-major fp64
+ *     (simulation_state.py:28-31), one batch = B systems with the same body count N (2..NB_MAX_N).
+ *   - every function returns NB_OK (0) or a negative error code and never throws.  Numerical failure
+ *     of one system is reported per system in `status[B]`, never as a hang or exception.
+ */
+#ifndef NBODY_B200_H
+#define NBODY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB_OK 0
+#define NB_ERR_ARG (-1)        /* bad argument (null pointer, N out of range, ...) */
+#define NB_ERR_CUDA (-2)       /* a CUDA runtime call failed; see nb_last_error() */
+#define NB_ERR_UNSUPPORTED (-3)
+
+#define NB_MIN_N 2
+#define NB_MAX_N 8             /* ensemble kernels are templated on N = 2..8 */
+
+/* integrator_mode (sim_config.py:19-24) */
+#define NB_MODE_VERLET 0
+#define NB_MODE_YOSHIDA4 1
+#define NB_MODE_WHFAST 2
+#define NB_MODE_HAMSOFT 3
+
+/* per-system status word written by the ensemble kernels */
+#define NB_STATUS_OK 0
+#define NB_STATUS_NONFINITE 1      /* state became non-finite (reference: inf/NaN features, OverflowError) */
+#define NB_STATUS_EPS_OOB 2        /* ham_soft: epsilon left [eps_min, eps_max] by more than their span */
+#define NB_STATUS_KEPLER_NOCONV 4  /* whfast: Newton loop hit the 64-iteration cap */
+
+/* flags for nb_ensemble_prepare_f64 */
+#define NB_PREP_REMOVE_COM 1u      /* v -= sum(m v)/sum(m)            simulation.py:85-86, physics_utils.py:16-26 */
+#define NB_PREP_CTOR_KICK 2u       /* v += 0.5*kick_dt*a(q)           simulation.py:150-157, integration_scheme_base.py:154-192 */
+#define NB_PREP_SNAPSHOT_KICK 4u   /* a second, identical half kick   simulation.py:319-326 (snapshot()/copy()) */
+#define NB_PREP_STATIC_FEATURES 8u /* fill static_features[B][NB_N_STATIC] from the (kicked) state */
+
+/* flags for nb_ensemble_run_f64 */
+#define NB_RUN_ENERGY 1u           /* E0/E1, L0/L1 + drifts           stability_analyzer.py:106-131 */
+#define NB_RUN_WRITE_STATE 2u      /* write final q, v (and eps, pi) back */
+#define NB_RUN_KEPLER_EXACT 4u     /* whfast: physically correct Kepler solver instead of the bug-compatible one */
+
+/* columns of dyn_features[B][NB_N_DYN] (stability_analyzer.py:226-252, in the reference's order) */
+enum {
+  NB_F_IS_STABLE = 0, NB_F_ENERGY_DRIFT, NB_F_ANGMOM_DRIFT, NB_F_COM_MEAN, NB_F_COM_MAX,
+  NB_F_JEPS_MEAN, NB_F_JEPS_STD, NB_F_THETA_MEAN, NB_F_THETA_STD, NB_F_COS_MEAN, NB_F_COS_MIN,
+  NB_F_VARL_MEAN, NB_F_VARL_MAX, NB_F_TIDAL_MEAN, NB_F_TIDAL_MAX, NB_F_MEGNO, NB_F_LYAP_TIME,
+  NB_F_E0, NB_F_E1, NB_F_L0, NB_F_L1, NB_F_T_END, NB_N_DYN
+};
+
+/* columns of static_features[B][NB_N_STATIC] (dynamical_features.py:27-155, in the reference's order) */
+enum {
+  NB_S_TOTAL_MASS = 0, NB_S_MASS_VAR, NB_S_MASS_RATIO_MAX, NB_S_MASS_CENTER_OFFSET,
+  NB_S_MEAN_SEP, NB_S_STD_SEP, NB_S_MIN_SEP, NB_S_MAX_SEP, NB_S_SEP_RATIO,
+  NB_S_MEAN_SPEED, NB_S_STD_SPEED, NB_S_MAX_SPEED, NB_S_MEAN_RELVEL, NB_S_MAX_RELVEL,
+  NB_S_KINETIC, NB_S_POTENTIAL, NB_S_TOTAL_ENERGY, NB_S_VIRIAL, NB_S_ENERGY_PER_MASS, NB_S_IS_BOUND,
+  NB_S_TOTAL_ANGMOM, NB_S_MEAN_SPEC_ANGMOM, NB_S_ANGMOM_VAR, NB_S_SOFT_MEAN, NB_S_SOFT_STD,
+  NB_N_STATIC
+};
+
+/* ham_soft per-system parameters (hamiltonian_softening_integrator.py:47-141, hamsoft_params.py:31-76);
+ * one row of hs_params[B][NB_HS_NPARAM] */
+enum {
+  NB_HS_K_SOFT = 0, NB_HS_MU_SOFT, NB_HS_EPS_MIN, NB_HS_EPS_MAX, NB_HS_ALPHA_RUN, NB_HS_K_WALL,
+  NB_HS_BARRIER_N, NB_HS_ETA, NB_HS_J_MAX_CAP, NB_HS_LAMBDA, NB_HS_POLICY /*0 soft, 1 reflection, 2 none*/,
+  NB_HS_NPARAM
+};
+
+const char* nb_last_error(void);
+int nb_version(void);
+
+/* ---- a1-a5: forces.py:63-75 gravitational_force (+ simulation.py:551-552 division by m_i),
+ *      forces.py:77-112 dV_d_epsilon, potential.py:23-64 softened_potential, geometry_cache.py:24-39.
+ *      acc[B][N][2], U[B], dVdeps[B]; any output pointer may be NULL.  eps[B], G scalar. */
+int nb_pair_batched_f64(const double* q, const double* m, const double* eps, double G, int B, int N,
+                        double* acc, double* U, double* dVdeps, void* stream);
+
+/* ---- a6: tangent_map.py:21-59 TangentMap.variational_accel; s2[B] = manager.step_s2 */
+int nb_variational_batched_f64(const double* q, const double* m, const double* s2, const double* dr,
+                               double G, int B, int N, double* da, void* stream);
+
+/* ---- a3/a8/a9 construction-time work, one thread per system:
+ *      COM removal, corrector half kicks (ctor and snapshot), the frozen sub-step schedule
+ *      h_sub_ref (timestep_manager.py:139-253) and the 25 static features.
+ *      v is updated in place; h_sub_ref[B] and n_sub[B] (for step size dt) are outputs. */
+int nb_ensemble_prepare_f64(const double* m, const double* q, double* v, const double* eps, double G,
+                            int B, int N, int mode, unsigned flags, double kick_dt, double sched_dt,
+                            double dt, int split_n_max, double* h_sub_ref, int32_t* n_sub,
+                            double* static_features, void* stream);
+
+/* ---- a7/a8/a10/a17: the persistent ensemble integrator, one thread per system, state in registers.
+ *      Runs n_steps macro steps of size dt (each n_sub[s] sub-steps; integrator.py:78-104), sampling
+ *      step_metrics every sample_interval steps (0 = never; stability_analyzer.py:115-127), then n_megno
+ *      further steps with the tangent map (evolution_features.py:34-66; raw_dr/raw_dv are the two
+ *      randn(N,2) draws per system).  perm[B] (optional) maps thread -> system so that callers can sort
+ *      by n_sub.  ham_soft additionally takes eps_pi[B][2] (epsilon, pi; in/out) and hs_params. */
+int nb_ensemble_run_f64(const double* m, double* q, double* v, const double* eps, double G, int B, int N,
+                        int mode, unsigned flags, double dt, int n_steps, int sample_interval, int n_megno,
+                        const int32_t* n_sub, const int32_t* perm, const double* raw_dr, const double* raw_dv,
+                        double* eps_pi, const double* hs_params,
+                        double* dyn_features, int32_t* status, void* stream);
+
+/* counting sort of systems by n_sub (descending) -> perm[B]; workspace: 64 int32 on the device */
+int nb_sort_by_nsub(const int32_t* n_sub, int B, int32_t* perm, int32_t* workspace64, void* stream);
+
+/* ---- the same path end to end with HOST buffers (BatchStabilityAnalyzer.analyze_batch,
+ *      batch_stability_analyzer.py:62-80): prepare(flags) -> sort -> run -> features.
+ *      v_host is updated with the kicked velocities (the reference mutates the caller's sims). */
+int nb_ensemble_analyze_host(const double* m, const double* q, double* v, const double* eps, double G,
+                             int B, int N, int mode, unsigned prep_flags, double kick_dt, double sched_dt,
+                             double dt, int n_steps, int n_megno, int split_n_max, const double* raw_dr,
+                             const double* raw_dv, double* dyn_features, double* static_features,
+                             int32_t* n_sub_out, int32_t* status, int device);
+
+/* ---- large-N direct sum (new capability, same formula as forces.py:63-75 / 77-112 / potential.py:23-64),
+ *      fp32 pair arithmetic, fp64 accumulation across j-tiles.  xym[n_total] = (x, y, m, 0) packed float4.
+ *      Rank-local i-range [i0, i0+ni).  acc[ni] float2; sums[2] += {sum_{i in range, j} m_i m_j/rho, sum m_i m_j/rho^3}
+ *      (ordered pairs; halve for i<j). */
+int nb_largeN_accel_f32(const float* xym, int n_total, int i0, int ni, float eps, float G, float* acc,
+                        double* sums, void* stream);
+/* kick/drift on the rank-local block and re-pack into the gather buffer (fused pack for the all-gather) */
+int nb_largeN_kick_drift_f32(float* xym_local, float* vel, const float* acc, int ni, float kick_h, float drift_h,
+                             void* stream);
+
+/* ---- register-resident FMA micro-benchmarks used for the roofline denominators (TFLOP/s) */
+int nb_peak_flops(int which /*0 fp64 DFMA, 1 fp32 FFMA, 2 fp32x2 FFMA2*/, int device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,45 @@
+// args.cuh -- launch-argument structs shared by the translation units.
+#pragma once
+#include <stdint.h>
+
+namespace nb {
+
+struct RunArgs {
+  const double* m;
+  double* q;
+  double* v;
+  const double* eps;
+  double G;
+  int B;
+  unsigned flags;
+  double dt;
+  int n_steps;
+  int sample_interval;
+  int n_megno;
+  const int32_t* n_sub;
+  const int32_t* perm;
+  const double* raw_dr;
+  const double* raw_dv;
+  double* dyn;
+  int32_t* status;
+};
+
+struct PrepArgs {
+  const double* m;
+  const double* q;
+  double* v;
+  const double* eps;
+  double G;
+  int B;
+  int mode;
+  unsigned flags;
+  double kick_dt;
+  double sched_dt;
+  double dt;
+  int split_n_max;
+  double* h_sub_ref;
+  int32_t* n_sub;
+  double* stat;
+};
+
+}  // namespace nb

@@ -1,0 +1,313 @@
+// capi.cu -- the extern "C" boundary declared in include/nbody_b200.h.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include "common.cuh"
+#include "args.cuh"
+
+namespace nb {
+
+// ---- error plumbing -----------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* msg) {
+  std::snprintf(g_err, sizeof(g_err), "%s", msg ? msg : "");
+}
+int cuda_fail(cudaError_t e, const char* where) {
+  std::snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), where);
+  return NB_ERR_CUDA;
+}
+
+// ---- declarations of the launchers in the other translation units -------------------------------------
+int ensemble_run_classic(const RunArgs& a, int N, int mode, cudaStream_t st);
+int ensemble_prepare(const PrepArgs& a, int N, cudaStream_t st);
+int pair_batched(const double* q, const double* m, const double* eps, double G, int B, int N, double* acc, double* U,
+                 double* dV, cudaStream_t st);
+int variational_batched(const double* q, const double* m, const double* s2, const double* dr, double G, int B, int N,
+                        double* da, cudaStream_t st);
+int sort_by_nsub(const int32_t* n_sub, int B, int32_t* perm, int32_t* ws, cudaStream_t st);
+int largeN_accel(const float* xym, int n_total, int i0, int ni, float eps, float G, float* acc, double* sums,
+                 cudaStream_t st);
+int largeN_kick_drift(float* xym_local, float* vel, const float* acc, int ni, float kick_h, float drift_h,
+                      cudaStream_t st);
+int hamsoft_run(const double* m, double* q, double* v, double G, int B, int N, unsigned flags, double dt, int n_steps,
+                int sample_interval, int n_megno, const int32_t* n_sub, const int32_t* perm, const double* raw_dr,
+                const double* raw_dv, double* eps_pi, const double* hs, double* dyn, int32_t* status, cudaStream_t st);
+
+// ---- peak micro-benchmarks ------------------------------------------------------------------------------
+template <int WHICH>
+__global__ void __launch_bounds__(256) peak_kernel(int iters, float seed, float* out) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (WHICH == 0) {
+    double a[8];
+    const double b = 1.0000001 + seed, c = 1e-9 * tid;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = k + seed;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = fma(a[k], b, c);
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == 123.456) out[0] = (float)s;
+  } else if (WHICH == 1) {
+    float a[16];
+    const float b = 1.0000001f + seed, c = 1e-9f * tid;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = k + seed;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) a[k] = fmaf(a[k], b, c);
+    }
+    float s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += a[k];
+    if (s == 123.456f) out[0] = s;
+  } else if (WHICH == 2) {
+    unsigned long long a[16];
+    unsigned long long b, c;
+    {
+      float2 fb = make_float2(1.0000001f + seed, 0.9999999f + seed), fc = make_float2(1e-9f * tid, 2e-9f * tid);
+      b = *reinterpret_cast<unsigned long long*>(&fb);
+      c = *reinterpret_cast<unsigned long long*>(&fc);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        float2 fa = make_float2(k + seed, k - seed);
+        a[k] = *reinterpret_cast<unsigned long long*>(&fa);
+      }
+    }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[k]) : "l"(b), "l"(c));
+    }
+    float s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float2 fa = *reinterpret_cast<float2*>(&a[k]);
+      s += fa.x + fa.y;
+    }
+    if (s == 123.456f) out[0] = s;
+  } else if (WHICH == 3) {
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 1.5f + k + seed + 1e-3f * tid;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(a[k]));
+    }
+    float s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == 123.456f) out[0] = s;
+  } else {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 1.5 + k + seed + 1e-3 * tid;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) asm volatile("rsqrt.approx.ftz.f64 %0, %0;" : "+d"(a[k]));
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == 123.456) out[0] = (float)s;
+  }
+}
+
+static int peak_flops(int which, int device, double* tflops) {
+  if (!tflops || which < 0 || which > 4) { set_error("nb_peak_flops: bad arguments"); return NB_ERR_ARG; }
+  NB_CUDA_CHECK(cudaSetDevice(device));
+  int sms = 0;
+  NB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  float* out = nullptr;
+  NB_CUDA_CHECK(cudaMalloc(&out, 4));
+  const int blocks = sms * 8, threads = 256;
+  const int iters = 4096;
+  cudaEvent_t e0, e1;
+  NB_CUDA_CHECK(cudaEventCreate(&e0));
+  NB_CUDA_CHECK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    NB_CUDA_CHECK(cudaEventRecord(e0));
+    switch (which) {
+      case 0: peak_kernel<0><<<blocks, threads>>>(iters, 0.f, out); break;
+      case 1: peak_kernel<1><<<blocks, threads>>>(iters, 0.f, out); break;
+      case 2: peak_kernel<2><<<blocks, threads>>>(iters, 0.f, out); break;
+      case 3: peak_kernel<3><<<blocks, threads>>>(iters, 0.f, out); break;
+      default: peak_kernel<4><<<blocks, threads>>>(iters, 0.f, out); break;
+    }
+    NB_CUDA_CHECK(cudaEventRecord(e1));
+    NB_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    NB_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    const double per_thread = which == 0 ? 8.0 * 2 : which == 1 ? 16.0 * 2 : which == 2 ? 16.0 * 4 : 8.0;
+    const double ops = per_thread * iters * (double)blocks * threads;
+    const double t = ops / (ms * 1e-3) * 1e-12;
+    if (rep > 0 && t > best) best = t;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return NB_OK;
+}
+
+// ---- cached workspace for the *_host entry points ----------------------------------------------------------
+struct HostWs {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  void* buf = nullptr;
+  size_t cap = 0;
+};
+static HostWs g_ws;
+static std::mutex g_ws_mu;
+
+static int ws_reserve(int device, size_t bytes) {
+  if (g_ws.device != device) {
+    if (g_ws.buf) { cudaSetDevice(g_ws.device); cudaFree(g_ws.buf); cudaStreamDestroy(g_ws.stream); }
+    g_ws = HostWs();
+    NB_CUDA_CHECK(cudaSetDevice(device));
+    NB_CUDA_CHECK(cudaStreamCreateWithFlags(&g_ws.stream, cudaStreamNonBlocking));
+    g_ws.device = device;
+  }
+  NB_CUDA_CHECK(cudaSetDevice(device));
+  if (g_ws.cap < bytes) {
+    if (g_ws.buf) cudaFree(g_ws.buf);
+    g_ws.buf = nullptr;
+    g_ws.cap = 0;
+    NB_CUDA_CHECK(cudaMalloc(&g_ws.buf, bytes));
+    g_ws.cap = bytes;
+  }
+  return NB_OK;
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace nb
+
+using namespace nb;
+
+extern "C" {
+
+const char* nb_last_error(void) { return g_err; }
+int nb_version(void) { return 100; }
+
+int nb_pair_batched_f64(const double* q, const double* m, const double* eps, double G, int B, int N, double* acc,
+                        double* U, double* dVdeps, void* stream) {
+  if (!q || !m || !eps || B < 0 || N < NB_MIN_N || N > NB_MAX_N) { set_error("nb_pair_batched_f64: bad arguments"); return NB_ERR_ARG; }
+  if (B == 0) return NB_OK;
+  return pair_batched(q, m, eps, G, B, N, acc, U, dVdeps, (cudaStream_t)stream);
+}
+
+int nb_variational_batched_f64(const double* q, const double* m, const double* s2, const double* dr, double G, int B,
+                               int N, double* da, void* stream) {
+  if (!q || !m || !s2 || !dr || !da || B < 0 || N < NB_MIN_N || N > NB_MAX_N) { set_error("nb_variational_batched_f64: bad arguments"); return NB_ERR_ARG; }
+  if (B == 0) return NB_OK;
+  return variational_batched(q, m, s2, dr, G, B, N, da, (cudaStream_t)stream);
+}
+
+int nb_ensemble_prepare_f64(const double* m, const double* q, double* v, const double* eps, double G, int B, int N,
+                            int mode, unsigned flags, double kick_dt, double sched_dt, double dt, int split_n_max,
+                            double* h_sub_ref, int32_t* n_sub, double* static_features, void* stream) {
+  if (!m || !q || !v || !eps || B < 0 || N < NB_MIN_N || N > NB_MAX_N) { set_error("nb_ensemble_prepare_f64: bad arguments"); return NB_ERR_ARG; }
+  if (B == 0) return NB_OK;
+  PrepArgs a{m, q, v, eps, G, B, mode, flags, kick_dt, sched_dt, dt, split_n_max, h_sub_ref, n_sub, static_features};
+  return ensemble_prepare(a, N, (cudaStream_t)stream);
+}
+
+int nb_ensemble_run_f64(const double* m, double* q, double* v, const double* eps, double G, int B, int N, int mode,
+                        unsigned flags, double dt, int n_steps, int sample_interval, int n_megno, const int32_t* n_sub,
+                        const int32_t* perm, const double* raw_dr, const double* raw_dv, double* eps_pi,
+                        const double* hs_params, double* dyn_features, int32_t* status, void* stream) {
+  if (!m || !q || !v || B < 0 || N < NB_MIN_N || N > NB_MAX_N || n_steps < 0 || n_megno < 0) { set_error("nb_ensemble_run_f64: bad arguments"); return NB_ERR_ARG; }
+  if (n_megno > 0 && (!raw_dr || !raw_dv)) { set_error("nb_ensemble_run_f64: n_megno > 0 needs raw_dr/raw_dv"); return NB_ERR_ARG; }
+  if (B == 0) return NB_OK;
+  if (mode == NB_MODE_HAMSOFT) {
+    if (!eps_pi || !hs_params) { set_error("nb_ensemble_run_f64: ham_soft needs eps_pi and hs_params"); return NB_ERR_ARG; }
+    return hamsoft_run(m, q, v, G, B, N, flags, dt, n_steps, sample_interval, n_megno, n_sub, perm, raw_dr, raw_dv,
+                       eps_pi, hs_params, dyn_features, status, (cudaStream_t)stream);
+  }
+  if (!eps) { set_error("nb_ensemble_run_f64: eps is required"); return NB_ERR_ARG; }
+  RunArgs a{m, q, v, eps, G, B, flags, dt, n_steps, sample_interval, n_megno, n_sub, perm, raw_dr, raw_dv, dyn_features, status};
+  return ensemble_run_classic(a, N, mode, (cudaStream_t)stream);
+}
+
+int nb_sort_by_nsub(const int32_t* n_sub, int B, int32_t* perm, int32_t* workspace64, void* stream) {
+  if (!n_sub || !perm || !workspace64 || B < 0) { set_error("nb_sort_by_nsub: bad arguments"); return NB_ERR_ARG; }
+  if (B == 0) return NB_OK;
+  return sort_by_nsub(n_sub, B, perm, workspace64, (cudaStream_t)stream);
+}
+
+int nb_ensemble_analyze_host(const double* m, const double* q, double* v, const double* eps, double G, int B, int N,
+                             int mode, unsigned prep_flags, double kick_dt, double sched_dt, double dt, int n_steps,
+                             int n_megno, int split_n_max, const double* raw_dr, const double* raw_dv, double* dyn_features,
+                             double* static_features, int32_t* n_sub_out, int32_t* status, int device) {
+  if (!m || !q || !v || !eps || !dyn_features || B < 0 || N < NB_MIN_N || N > NB_MAX_N) { set_error("nb_ensemble_analyze_host: bad arguments"); return NB_ERR_ARG; }
+  if (mode == NB_MODE_HAMSOFT) { set_error("nb_ensemble_analyze_host: ham_soft goes through nb_ensemble_run_f64"); return NB_ERR_UNSUPPORTED; }
+  if (n_megno > 0 && (!raw_dr || !raw_dv)) { set_error("nb_ensemble_analyze_host: n_megno > 0 needs raw_dr/raw_dv"); return NB_ERR_ARG; }
+  if (B == 0) return NB_OK;
+  std::lock_guard<std::mutex> lock(g_ws_mu);
+  const size_t bn = (size_t)B * N;
+  const size_t sz_m = align256(bn * 8), sz_q = align256(bn * 16), sz_b = align256((size_t)B * 8);
+  const size_t sz_dyn = align256((size_t)B * NB_N_DYN * 8), sz_stat = align256((size_t)B * NB_N_STATIC * 8);
+  const size_t sz_i = align256((size_t)B * 4);
+  const size_t total = sz_m + 4 * sz_q + sz_b + sz_dyn + sz_stat + 3 * sz_i + 256;
+  int rc = ws_reserve(device, total);
+  if (rc != NB_OK) return rc;
+  cudaStream_t st = g_ws.stream;
+  char* p = (char*)g_ws.buf;
+  double* d_m = (double*)p; p += sz_m;
+  double* d_q = (double*)p; p += sz_q;
+  double* d_v = (double*)p; p += sz_q;
+  double* d_dr = (double*)p; p += sz_q;
+  double* d_dv = (double*)p; p += sz_q;
+  double* d_eps = (double*)p; p += sz_b;
+  double* d_dyn = (double*)p; p += sz_dyn;
+  double* d_stat = (double*)p; p += sz_stat;
+  int32_t* d_nsub = (int32_t*)p; p += sz_i;
+  int32_t* d_perm = (int32_t*)p; p += sz_i;
+  int32_t* d_status = (int32_t*)p; p += sz_i;
+  int32_t* d_bins = (int32_t*)p;
+  NB_CUDA_CHECK(cudaMemcpyAsync(d_m, m, bn * 8, cudaMemcpyHostToDevice, st));
+  NB_CUDA_CHECK(cudaMemcpyAsync(d_q, q, bn * 16, cudaMemcpyHostToDevice, st));
+  NB_CUDA_CHECK(cudaMemcpyAsync(d_v, v, bn * 16, cudaMemcpyHostToDevice, st));
+  NB_CUDA_CHECK(cudaMemcpyAsync(d_eps, eps, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+  if (n_megno > 0) {
+    NB_CUDA_CHECK(cudaMemcpyAsync(d_dr, raw_dr, bn * 16, cudaMemcpyHostToDevice, st));
+    NB_CUDA_CHECK(cudaMemcpyAsync(d_dv, raw_dv, bn * 16, cudaMemcpyHostToDevice, st));
+  }
+  unsigned pf = prep_flags;
+  if (static_features) pf |= NB_PREP_STATIC_FEATURES; else pf &= ~NB_PREP_STATIC_FEATURES;
+  PrepArgs pa{d_m, d_q, d_v, d_eps, G, B, mode, pf, kick_dt, sched_dt, dt, split_n_max, nullptr, d_nsub, d_stat};
+  rc = ensemble_prepare(pa, N, st);
+  if (rc != NB_OK) return rc;
+  if (pf & (NB_PREP_REMOVE_COM | NB_PREP_CTOR_KICK | NB_PREP_SNAPSHOT_KICK))
+    NB_CUDA_CHECK(cudaMemcpyAsync(v, d_v, bn * 16, cudaMemcpyDeviceToHost, st));   // the reference mutates the caller's sims
+  rc = sort_by_nsub(d_nsub, B, d_perm, d_bins, st);
+  if (rc != NB_OK) return rc;
+  const int interval = n_steps / 100 > 1 ? n_steps / 100 : 1;
+  RunArgs ra{d_m, d_q, d_v, d_eps, G, B, NB_RUN_ENERGY, dt, n_steps, interval, n_megno, d_nsub, d_perm, d_dr, d_dv, d_dyn, d_status};
+  rc = ensemble_run_classic(ra, N, mode, st);
+  if (rc != NB_OK) return rc;
+  NB_CUDA_CHECK(cudaMemcpyAsync(dyn_features, d_dyn, (size_t)B * NB_N_DYN * 8, cudaMemcpyDeviceToHost, st));
+  if (static_features) NB_CUDA_CHECK(cudaMemcpyAsync(static_features, d_stat, (size_t)B * NB_N_STATIC * 8, cudaMemcpyDeviceToHost, st));
+  if (n_sub_out) NB_CUDA_CHECK(cudaMemcpyAsync(n_sub_out, d_nsub, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  if (status) NB_CUDA_CHECK(cudaMemcpyAsync(status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  NB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return NB_OK;
+}
+
+int nb_largeN_accel_f32(const float* xym, int n_total, int i0, int ni, float eps, float G, float* acc, double* sums,
+                        void* stream) {
+  return largeN_accel(xym, n_total, i0, ni, eps, G, acc, sums, (cudaStream_t)stream);
+}
+
+int nb_largeN_kick_drift_f32(float* xym_local, float* vel, const float* acc, int ni, float kick_h, float drift_h,
+                             void* stream) {
+  return largeN_kick_drift(xym_local, vel, acc, ni, kick_h, drift_h, (cudaStream_t)stream);
+}
+
+int nb_peak_flops(int which, int device, double* tflops) { return peak_flops(which, device, tflops); }
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// common.cuh -- shared device helpers for the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/nbody_b200.h"
+
+namespace nb {
+
+void set_error(const char* msg);
+int cuda_fail(cudaError_t e, const char* where);
+
+#define NB_CUDA_CHECK(expr)                                   \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return nb::cuda_fail(_e, #expr);   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// fp64 reciprocal square root: MUFU.RSQ64H seed (rel. err ~2^-22) + one cubic (Halley) correction
+//   e = 1 - x y0^2 ;  y = y0 (1 + e/2 + 3 e^2/8)      -> rel. err ~ (5/16) e^3 < 2^-60
+// 4 DP-pipe ops + 1 MUFU.  x <= 0 / denormal -> 0, matching the reference's masked inv_r3
+// (geometry_cache.py:33-36); NaN propagates.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rsqrt_seed(double x) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  return y0;
+}
+
+template <bool GUARD>
+__device__ __forceinline__ double rsqrt_f64(double x) {
+  double y0 = rsqrt_seed(x);
+  double t = x * y0;
+  double e = fma(-t, y0, 1.0);
+  double p = fma(0.375, e, 0.5);
+  double y = fma(y0 * e, p, y0);
+  if (GUARD) {
+    // x < 2^-1022 (zero, denormal or negative): the reference leaves inv_r3 = 0 there
+    if (__double2hiint(x) < 0x00100000) y = 0.0;
+  }
+  return y;
+}
+
+// ------------------------------------------------------------------------------------------------
+// double-double arithmetic (only used for the E0/E1 energy reductions that the reference does in
+// long double + Kahan, diagnostics.py:457-549)
+// ------------------------------------------------------------------------------------------------
+struct dd {
+  double hi, lo;
+};
+__device__ __forceinline__ dd dd_make(double a) { return dd{a, 0.0}; }
+__device__ __forceinline__ dd two_sum(double a, double b) {
+  double s = __dadd_rn(a, b);
+  double bb = __dadd_rn(s, -a);
+  double e = __dadd_rn(__dadd_rn(a, -__dadd_rn(s, -bb)), __dadd_rn(b, -bb));
+  return dd{s, e};
+}
+__device__ __forceinline__ dd quick_two_sum(double a, double b) {
+  double s = __dadd_rn(a, b);
+  double e = __dadd_rn(b, -__dadd_rn(s, -a));
+  return dd{s, e};
+}
+__device__ __forceinline__ dd two_prod(double a, double b) {
+  double p = __dmul_rn(a, b);
+  double e = __fma_rn(a, b, -p);
+  return dd{p, e};
+}
+__device__ __forceinline__ dd dd_add(dd a, dd b) {
+  dd s = two_sum(a.hi, b.hi);
+  dd t = two_sum(a.lo, b.lo);
+  s.lo = __dadd_rn(s.lo, t.hi);
+  s = quick_two_sum(s.hi, s.lo);
+  s.lo = __dadd_rn(s.lo, t.lo);
+  return quick_two_sum(s.hi, s.lo);
+}
+__device__ __forceinline__ dd dd_neg(dd a) { return dd{-a.hi, -a.lo}; }
+__device__ __forceinline__ dd dd_sub(dd a, dd b) { return dd_add(a, dd_neg(b)); }
+__device__ __forceinline__ dd dd_add_d(dd a, double b) { return dd_add(a, dd_make(b)); }
+__device__ __forceinline__ dd dd_mul(dd a, dd b) {
+  dd p = two_prod(a.hi, b.hi);
+  p.lo = __fma_rn(a.hi, b.lo, p.lo);
+  p.lo = __fma_rn(a.lo, b.hi, p.lo);
+  return quick_two_sum(p.hi, p.lo);
+}
+__device__ __forceinline__ dd dd_mul_d(dd a, double b) {
+  dd p = two_prod(a.hi, b);
+  p.lo = __fma_rn(a.lo, b, p.lo);
+  return quick_two_sum(p.hi, p.lo);
+}
+__device__ __forceinline__ dd dd_div(dd a, dd b) {
+  double q1 = __ddiv_rn(a.hi, b.hi);
+  dd r = dd_sub(a, dd_mul_d(b, q1));
+  double q2 = __ddiv_rn(r.hi, b.hi);
+  r = dd_sub(r, dd_mul_d(b, q2));
+  double q3 = __ddiv_rn(r.hi, b.hi);
+  dd q = quick_two_sum(q1, q2);
+  return dd_add_d(q, q3);
+}
+__device__ __forceinline__ dd dd_sqrt(dd a) {
+  if (!(a.hi > 0.0)) return dd_make(0.0);
+  double x = 1.0 / sqrt(a.hi);
+  double ax = __dmul_rn(a.hi, x);
+  dd err = dd_sub(a, two_prod(ax, ax));
+  return quick_two_sum(ax, __dmul_rn(err.hi, __dmul_rn(x, 0.5)));
+}
+__device__ __forceinline__ double dd_to_double(dd a) { return __dadd_rn(a.hi, a.lo); }
+
+__device__ __forceinline__ bool is_finite(double x) { return (__double2hiint(x) & 0x7ff00000) != 0x7ff00000; }
+
+}  // namespace nb

@@ -1,0 +1,328 @@
+// ensemble_misc.cu -- construction-time kernel, stand-alone pair kernels and the n_sub counting sort.
+#include "ensemble_run.cuh"
+
+namespace nb {
+
+int ensemble_run_verlet(const RunArgs& a, int N, cudaStream_t st);
+int ensemble_run_yoshida4(const RunArgs& a, int N, cudaStream_t st);
+int ensemble_run_whfast(const RunArgs& a, int N, cudaStream_t st);
+
+int ensemble_run_classic(const RunArgs& a, int N, int mode, cudaStream_t st) {
+  switch (mode) {
+    case NB_MODE_VERLET: return ensemble_run_verlet(a, N, st);
+    case NB_MODE_YOSHIDA4: return ensemble_run_yoshida4(a, N, st);
+    case NB_MODE_WHFAST: return ensemble_run_whfast(a, N, st);
+    default: set_error("nb_ensemble_run_f64: unsupported mode"); return NB_ERR_UNSUPPORTED;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// prepare kernel
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128) ensemble_prepare_kernel(PrepArgs a) {
+  const int sys = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sys >= a.B) return;
+  SysState<N> s;
+  double m[N];
+  const double G = a.G;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    m[i] = a.m[(size_t)sys * N + i];
+    s.gm[i] = G * m[i];
+    s.x[i] = a.q[((size_t)sys * N + i) * 2 + 0];
+    s.y[i] = a.q[((size_t)sys * N + i) * 2 + 1];
+    s.vx[i] = a.v[((size_t)sys * N + i) * 2 + 0];
+    s.vy[i] = a.v[((size_t)sys * N + i) * 2 + 1];
+  }
+  const double eps = a.eps[sys];
+  s.eps2 = eps * eps;
+  bool touched = false;
+  if (a.flags & NB_PREP_REMOVE_COM) {   // physics_utils.py:16-26
+    double M = 0.0, px = 0.0, py = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { M += m[i]; px += m[i] * s.vx[i]; py += m[i] * s.vy[i]; }
+    if (M != 0.0) {
+      px /= M; py /= M;
+#pragma unroll
+      for (int i = 0; i < N; ++i) { s.vx[i] -= px; s.vy[i] -= py; }
+    }
+    touched = true;
+  }
+  const int n_kicks = ((a.flags & NB_PREP_CTOR_KICK) ? 1 : 0) + ((a.flags & NB_PREP_SNAPSHOT_KICK) ? 1 : 0);
+  if (n_kicks > 0 && G != 0.0) {        // integration_scheme_base.py:154-192 / whfast_scheme.py:95-123
+    if (a.mode == NB_MODE_WHFAST) {
+      double ax[N], ay[N];
+      wh_interaction_accel<N>(s, m, G, ax, ay);
+#pragma unroll
+      for (int i = 0; i < N; ++i) { s.ax[i] = ax[i]; s.ay[i] = ay[i]; }
+    } else {
+      pair_pass<N, false, true>(s, nullptr, nullptr, nullptr, nullptr);
+    }
+    for (int k = 0; k < n_kicks; ++k) kick<N>(s, 0.5 * a.kick_dt);
+    touched = true;
+  }
+  if (touched) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      a.v[((size_t)sys * N + i) * 2 + 0] = s.vx[i];
+      a.v[((size_t)sys * N + i) * 2 + 1] = s.vy[i];
+    }
+  }
+  // ---- frozen sub-step schedule (timestep_manager.py:139-253, classic branch)
+  if (a.h_sub_ref || a.n_sub) {
+    double tau = __longlong_as_double(0x7ff0000000000000LL);
+    if (G != 0.0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = i + 1; j < N; ++j) {
+          const double dx = s.x[i] - s.x[j], dy = s.y[i] - s.y[j];
+          const double r = sqrt(dx * dx + dy * dy);
+          const double r3 = r * r * r;
+          const double den = G * (m[i] + m[j]);
+          if (is_finite(r3) && is_finite(den) && den > 0.0) tau = fmin(tau, sqrt(r3 / den));
+        }
+    }
+    const double dt_user = fabs(a.sched_dt);
+    double hs = 0.9 * tau;
+    if (!is_finite(hs) || hs <= 0.0) hs = dt_user > 0.0 ? dt_user : 1.0;
+    if (a.split_n_max > 0) {
+      if (ceil(dt_user / fmax(hs, 1e-30)) > (double)a.split_n_max) hs = dt_user / (double)a.split_n_max;
+    }
+    if (a.h_sub_ref) a.h_sub_ref[sys] = hs;
+    if (a.n_sub) {
+      double need = ceil(fabs(a.dt) / hs);
+      int ns = need > (double)a.split_n_max ? a.split_n_max : (int)need;
+      a.n_sub[sys] = max(1, ns);
+    }
+  }
+  // ---- static features (dynamical_features.py:27-155)
+  if ((a.flags & NB_PREP_STATIC_FEATURES) && a.stat) {
+    double* f = a.stat + (size_t)sys * NB_N_STATIC;
+    double M = 0.0, mmin = m[0], mmax = m[0], xs = 0.0, ys = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      M += m[i]; mmin = fmin(mmin, m[i]); mmax = fmax(mmax, m[i]);
+      xs += m[i] * s.x[i]; ys += m[i] * s.y[i];
+    }
+    double mvar = 0.0;
+    { const double mu = M / N;
+#pragma unroll
+      for (int i = 0; i < N; ++i) mvar += (m[i] - mu) * (m[i] - mu);
+      mvar /= N; }
+    f[NB_S_TOTAL_MASS] = M;
+    f[NB_S_MASS_VAR] = mvar;
+    f[NB_S_MASS_RATIO_MAX] = mmin > 0.0 ? mmax / mmin : 1.0;
+    f[NB_S_MASS_CENTER_OFFSET] = (M != 0.0) ? sqrt((xs / M) * (xs / M) + (ys / M) * (ys / M)) : 0.0;
+    constexpr int NP = N * (N - 1) / 2;
+    double dsum = 0.0, dmin = __longlong_as_double(0x7ff0000000000000LL), dmax = 0.0, rsum = 0.0, rmax = 0.0;
+    double dist[NP];
+    double PE = 0.0;
+    { int p = 0;
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = i + 1; j < N; ++j) {
+          const double dx = s.x[j] - s.x[i], dy = s.y[j] - s.y[i];
+          const double r = sqrt(dx * dx + dy * dy);
+          dist[p++] = r; dsum += r; dmin = fmin(dmin, r); dmax = fmax(dmax, r);
+          const double ux = s.vx[j] - s.vx[i], uy = s.vy[j] - s.vy[i];
+          const double dv = sqrt(ux * ux + uy * uy);
+          rsum += dv; rmax = fmax(rmax, dv);
+          PE -= G * m[i] * m[j] / sqrt(dx * dx + dy * dy + s.eps2);
+        } }
+    const double dmean = dsum / NP;
+    double dvar = 0.0;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) dvar += (dist[p] - dmean) * (dist[p] - dmean);
+    f[NB_S_MEAN_SEP] = dmean;
+    f[NB_S_STD_SEP] = sqrt(dvar / NP);
+    f[NB_S_MIN_SEP] = dmin;
+    f[NB_S_MAX_SEP] = dmax;
+    f[NB_S_SEP_RATIO] = dmin > 0.0 ? dmax / dmin : 1.0;
+    double sp[N], ssum = 0.0, smax = 0.0, KE = 0.0, L = 0.0, spec[N], spsum = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double v2 = s.vx[i] * s.vx[i] + s.vy[i] * s.vy[i];
+      sp[i] = sqrt(v2); ssum += sp[i]; smax = fmax(smax, sp[i]);
+      KE += 0.5 * m[i] * v2;
+      const double li = m[i] * (s.x[i] * s.vy[i] - s.y[i] * s.vx[i]);
+      L += li;
+      spec[i] = fabs(li) / m[i]; spsum += spec[i];
+    }
+    const double smean = ssum / N, spmean = spsum / N;
+    double svar = 0.0, spvar = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { svar += (sp[i] - smean) * (sp[i] - smean); spvar += (spec[i] - spmean) * (spec[i] - spmean); }
+    f[NB_S_MEAN_SPEED] = smean;
+    f[NB_S_STD_SPEED] = sqrt(svar / N);
+    f[NB_S_MAX_SPEED] = smax;
+    f[NB_S_MEAN_RELVEL] = rsum / NP;
+    f[NB_S_MAX_RELVEL] = rmax;
+    const double E = KE + PE;
+    f[NB_S_KINETIC] = KE;
+    f[NB_S_POTENTIAL] = PE;
+    f[NB_S_TOTAL_ENERGY] = E;
+    f[NB_S_VIRIAL] = PE != 0.0 ? 2.0 * KE / fabs(PE) : 0.0;
+    f[NB_S_ENERGY_PER_MASS] = E / M;
+    f[NB_S_IS_BOUND] = E < 0.0 ? 1.0 : 0.0;
+    f[NB_S_TOTAL_ANGMOM] = fabs(L);
+    f[NB_S_MEAN_SPEC_ANGMOM] = spmean;
+    f[NB_S_ANGMOM_VAR] = spvar / N;
+    f[NB_S_SOFT_MEAN] = eps;     // history == [s] for a sim that has not been stepped; the host overrides otherwise
+    f[NB_S_SOFT_STD] = 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pair / variational batched kernels (a1-a6 as stand-alone calls)
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128) pair_batched_kernel(const double* __restrict__ q, const double* __restrict__ m,
+                                                           const double* __restrict__ eps, double G, int B,
+                                                           double* acc, double* U, double* dV) {
+  const int sys = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sys >= B) return;
+  SysState<N> s;
+  double mm[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    mm[i] = m[(size_t)sys * N + i];
+    s.gm[i] = G * mm[i];
+    s.x[i] = q[((size_t)sys * N + i) * 2 + 0];
+    s.y[i] = q[((size_t)sys * N + i) * 2 + 1];
+  }
+  const double e = eps[sys];
+  s.eps2 = e * e;
+  if (acc) {
+    pair_pass<N, false, true>(s, nullptr, nullptr, nullptr, nullptr);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      acc[((size_t)sys * N + i) * 2 + 0] = s.ax[i];
+      acc[((size_t)sys * N + i) * 2 + 1] = s.ay[i];
+    }
+  }
+  if (U || dV) {
+    double u, s3;
+    pair_scalars<N, true>(s.gm, mm, s.x, s.y, s.eps2, u, s3);
+    if (U) U[sys] = (G == 0.0) ? 0.0 : u;
+    if (dV) dV[sys] = (e == 0.0 || G == 0.0) ? 0.0 : e * s3;   // forces.py:96-98
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) variational_batched_kernel(const double* __restrict__ q, const double* __restrict__ m,
+                                                                  const double* __restrict__ s2, const double* __restrict__ dr,
+                                                                  double G, int B, double* da) {
+  const int sys = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sys >= B) return;
+  SysState<N> s;
+  double drx[N], dry[N], dax[N], day[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    s.gm[i] = G * m[(size_t)sys * N + i];
+    s.x[i] = q[((size_t)sys * N + i) * 2 + 0];
+    s.y[i] = q[((size_t)sys * N + i) * 2 + 1];
+    drx[i] = dr[((size_t)sys * N + i) * 2 + 0];
+    dry[i] = dr[((size_t)sys * N + i) * 2 + 1];
+  }
+  s.eps2 = s2[sys];
+  pair_pass<N, true, true>(s, drx, dry, dax, day);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    da[((size_t)sys * N + i) * 2 + 0] = dax[i];
+    da[((size_t)sys * N + i) * 2 + 1] = day[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// counting sort by n_sub (descending): histogram -> exclusive scan (65 bins) -> scatter
+// ---------------------------------------------------------------------------------------------
+__global__ void sort_hist_kernel(const int32_t* __restrict__ n_sub, int B, int32_t* bins) {
+  __shared__ int sh[64];
+  if (threadIdx.x < 64) sh[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x)
+    atomicAdd(&sh[min(max(n_sub[i], 0), 63)], 1);
+  __syncthreads();
+  if (threadIdx.x < 64 && sh[threadIdx.x]) atomicAdd(&bins[threadIdx.x], sh[threadIdx.x]);
+}
+__global__ void sort_scan_kernel(int32_t* bins) {  // descending: bin 63 first
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int b = 63; b >= 0; --b) { int c = bins[b]; bins[b] = run; run += c; }
+  }
+}
+__global__ void sort_scatter_kernel(const int32_t* __restrict__ n_sub, int B, int32_t* bins, int32_t* perm) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+    const int b = min(max(n_sub[i], 0), 63);
+    perm[atomicAdd(&bins[b], 1)] = i;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+int ensemble_prepare(const PrepArgs& a, int N, cudaStream_t st) {
+  const int threads = 128, blocks = (a.B + threads - 1) / threads;
+  switch (N) {
+    case 2: ensemble_prepare_kernel<2><<<blocks, threads, 0, st>>>(a); break;
+    case 3: ensemble_prepare_kernel<3><<<blocks, threads, 0, st>>>(a); break;
+    case 4: ensemble_prepare_kernel<4><<<blocks, threads, 0, st>>>(a); break;
+    case 5: ensemble_prepare_kernel<5><<<blocks, threads, 0, st>>>(a); break;
+    case 6: ensemble_prepare_kernel<6><<<blocks, threads, 0, st>>>(a); break;
+    case 7: ensemble_prepare_kernel<7><<<blocks, threads, 0, st>>>(a); break;
+    case 8: ensemble_prepare_kernel<8><<<blocks, threads, 0, st>>>(a); break;
+    default: set_error("N must be in 2..8"); return NB_ERR_ARG;
+  }
+  NB_CUDA_CHECK(cudaGetLastError());
+  return NB_OK;
+}
+
+int pair_batched(const double* q, const double* m, const double* eps, double G, int B, int N, double* acc, double* U,
+                 double* dV, cudaStream_t st) {
+  const int threads = 128, blocks = (B + threads - 1) / threads;
+  switch (N) {
+    case 2: pair_batched_kernel<2><<<blocks, threads, 0, st>>>(q, m, eps, G, B, acc, U, dV); break;
+    case 3: pair_batched_kernel<3><<<blocks, threads, 0, st>>>(q, m, eps, G, B, acc, U, dV); break;
+    case 4: pair_batched_kernel<4><<<blocks, threads, 0, st>>>(q, m, eps, G, B, acc, U, dV); break;
+    case 5: pair_batched_kernel<5><<<blocks, threads, 0, st>>>(q, m, eps, G, B, acc, U, dV); break;
+    case 6: pair_batched_kernel<6><<<blocks, threads, 0, st>>>(q, m, eps, G, B, acc, U, dV); break;
+    case 7: pair_batched_kernel<7><<<blocks, threads, 0, st>>>(q, m, eps, G, B, acc, U, dV); break;
+    case 8: pair_batched_kernel<8><<<blocks, threads, 0, st>>>(q, m, eps, G, B, acc, U, dV); break;
+    default: set_error("N must be in 2..8"); return NB_ERR_ARG;
+  }
+  NB_CUDA_CHECK(cudaGetLastError());
+  return NB_OK;
+}
+
+int variational_batched(const double* q, const double* m, const double* s2, const double* dr, double G, int B, int N,
+                        double* da, cudaStream_t st) {
+  const int threads = 128, blocks = (B + threads - 1) / threads;
+  switch (N) {
+    case 2: variational_batched_kernel<2><<<blocks, threads, 0, st>>>(q, m, s2, dr, G, B, da); break;
+    case 3: variational_batched_kernel<3><<<blocks, threads, 0, st>>>(q, m, s2, dr, G, B, da); break;
+    case 4: variational_batched_kernel<4><<<blocks, threads, 0, st>>>(q, m, s2, dr, G, B, da); break;
+    case 5: variational_batched_kernel<5><<<blocks, threads, 0, st>>>(q, m, s2, dr, G, B, da); break;
+    case 6: variational_batched_kernel<6><<<blocks, threads, 0, st>>>(q, m, s2, dr, G, B, da); break;
+    case 7: variational_batched_kernel<7><<<blocks, threads, 0, st>>>(q, m, s2, dr, G, B, da); break;
+    case 8: variational_batched_kernel<8><<<blocks, threads, 0, st>>>(q, m, s2, dr, G, B, da); break;
+    default: set_error("N must be in 2..8"); return NB_ERR_ARG;
+  }
+  NB_CUDA_CHECK(cudaGetLastError());
+  return NB_OK;
+}
+
+int sort_by_nsub(const int32_t* n_sub, int B, int32_t* perm, int32_t* ws, cudaStream_t st) {
+  NB_CUDA_CHECK(cudaMemsetAsync(ws, 0, 64 * sizeof(int32_t), st));
+  const int threads = 256;
+  const int blocks = min((B + threads - 1) / threads, 148 * 8);
+  sort_hist_kernel<<<blocks, threads, 0, st>>>(n_sub, B, ws);
+  sort_scan_kernel<<<1, 32, 0, st>>>(ws);
+  sort_scatter_kernel<<<blocks, threads, 0, st>>>(n_sub, B, ws, perm);
+  NB_CUDA_CHECK(cudaGetLastError());
+  return NB_OK;
+}
+
+}  // namespace nb

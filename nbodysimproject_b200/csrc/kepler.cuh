@@ -1,0 +1,172 @@
+// kepler.cuh -- universal-variable Kepler propagation for the "whfast" kick-drift scheme.
+//
+// Two solvers:
+//   * kepler_reference<>  restates kepler_solver.py:25-91 INCLUDING its quirks (Stumpff c1,c2 where
+//     c2,c3 belong at :69-70 and the argument-doubling recurrence at :36-45), because parity with the
+//     reference means bug-compatibility.  It is evaluated with strictly
+//     rounded, non-contracted fp64 operations (sd type below) so the Newton iteration follows the
+//     same path as the NumPy/CPython arithmetic.
+//   * kepler_exact<>      a physically correct universal-variable solver (NB_RUN_KEPLER_EXACT), checked
+//     against the analytic two-body solution.
+#pragma once
+#include "common.cuh"
+
+namespace nb {
+
+// strictly-rounded double: every operator is one IEEE operation, never contracted into an FMA
+struct sd {
+  double v;
+  __device__ __forceinline__ sd() {}
+  __device__ __forceinline__ sd(double a) : v(a) {}
+};
+__device__ __forceinline__ sd operator+(sd a, sd b) { return sd(__dadd_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator-(sd a, sd b) { return sd(__dadd_rn(a.v, -b.v)); }
+__device__ __forceinline__ sd operator*(sd a, sd b) { return sd(__dmul_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator/(sd a, sd b) { return sd(__ddiv_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator-(sd a) { return sd(-a.v); }
+
+// kepler_solver.py:25-46
+__device__ __forceinline__ void cfunc_reference(double z_in, sd& c0, sd& c1, sd& c2, sd& c3) {
+  sd z(z_in);
+  int n = 0;
+  while (fabs(z.v) > 0.1 && n < 600) {
+    z = z * sd(0.25);
+    ++n;
+  }
+  const sd z2 = z * z;
+  c0 = sd(1.0) - z * sd(0.5) + z2 / sd(24.0) - z * z2 / sd(720.0) + z2 * z2 / sd(40320.0);
+  c1 = sd(1.0) - z / sd(6.0) + z2 / sd(120.0) - z * z2 / sd(5040.0) + z2 * z2 / sd(362880.0);
+  c2 = sd(0.5) - z / sd(24.0) + z2 / sd(720.0) - z * z2 / sd(40320.0);
+  c3 = sd(1.0 / 6.0) - z / sd(120.0) + z2 / sd(5040.0) - z * z2 / sd(362880.0);
+  while (n) {
+    z = z * sd(4.0);
+    --n;
+    const sd c3o = c3, c1o = c1, c2o = c2;
+    c0 = sd(1.0) - z * c2o;
+    c1 = sd(1.0) - z * c3o;
+    c2 = sd(0.5) - z * (c3o * (sd(1.0) + c1o)) * sd(0.125);
+    c3 = (c1o - sd(1.0)) / z;
+  }
+}
+
+// kepler_solver.py:48-91.  Returns the Newton iteration count (64 = cap reached).
+__device__ __forceinline__ int kepler_reference(double& rx, double& ry, double& vx, double& vy, double mu_in,
+                                                double dt_in) {
+  const sd r_x(rx), r_y(ry), v_x(vx), v_y(vy), mu(mu_in), dt(dt_in);
+  const sd r0(hypot(rx, ry));
+  if (r0.v < 1e-14) {
+    rx = (r_x + v_x * dt).v;
+    ry = (r_y + v_y * dt).v;
+    return 0;
+  }
+  const sd vr0 = (r_x * v_x + r_y * v_y) / r0;
+  const sd v2 = v_x * v_x + v_y * v_y;
+  const sd alpha = sd(2.0) / r0 - v2 / mu;
+  const sd sqrt_mu(sqrt(mu.v));
+  sd chi;
+  if (fabs(alpha.v) > 1e-12)
+    chi = sqrt_mu * sd(fabs(alpha.v)) * dt;
+  else
+    chi = sqrt_mu * dt / r0;
+  double prev1 = __longlong_as_double(0x7ff8000000000000LL), prev2 = prev1;
+  sd c0, c1, c2, c3;
+  int it = 0;
+  for (; it < 64;) {
+    ++it;
+    const sd z = alpha * chi * chi;
+    cfunc_reference(z.v, c0, c1, c2, c3);
+    const sd f = r0 * vr0 / sqrt_mu * chi * chi * c1 + (sd(1.0) - alpha * r0) * chi * chi * chi * c2 + r0 * chi -
+                 sqrt_mu * dt;
+    const sd fp = r0 * vr0 / sqrt_mu * chi * (sd(1.0) - alpha * chi * chi * c2) +
+                  (sd(1.0) - alpha * r0) * chi * chi * c1 + r0;
+    if (fp.v == 0.0) break;
+    const sd chi_new = chi - f / fp;
+    prev2 = prev1;
+    prev1 = chi_new.v;
+    if (chi_new.v == chi.v || chi_new.v == prev2) {
+      chi = chi_new;
+      break;
+    }
+    chi = chi_new;
+  }
+  const sd z = alpha * chi * chi;
+  cfunc_reference(z.v, c0, c1, c2, c3);
+  const sd f = sd(1.0) - chi * chi * c2 / r0;
+  const sd g = dt - chi * chi * chi * c3 / sqrt_mu;
+  const sd nx = f * r_x + g * v_x;
+  const sd ny = f * r_y + g * v_y;
+  const sd rn(hypot(nx.v, ny.v));
+  rx = nx.v;
+  ry = ny.v;
+  if (rn.v == 0.0) return it;
+  const sd fdot = sqrt_mu / (rn * r0) * (alpha * chi * chi * c3 - chi);
+  const sd gdot = sd(1.0) - chi * chi * c2 / rn;
+  const sd wx = fdot * r_x + gdot * v_x;
+  const sd wy = fdot * r_y + gdot * v_y;
+  vx = wx.v;
+  vy = wy.v;
+  return it;
+}
+
+// ---- physically correct solver -----------------------------------------------------------------
+// Stumpff functions c2(psi) = (1-cos sqrt psi)/psi, c3(psi) = (sqrt psi - sin sqrt psi)/psi^1.5
+__device__ __forceinline__ void stumpff(double psi, double& c2, double& c3) {
+  if (psi > 1e-6) {
+    const double s = sqrt(psi);
+    double sn, cs;
+    sincos(s, &sn, &cs);
+    c2 = (1.0 - cs) / psi;
+    c3 = (s - sn) / (psi * s);
+  } else if (psi < -1e-6) {
+    const double s = sqrt(-psi);
+    c2 = (1.0 - cosh(s)) / psi;
+    c3 = (sinh(s) - s) / (-psi * s);
+  } else {
+    c2 = 0.5 - psi / 24.0 + psi * psi / 720.0;
+    c3 = 1.0 / 6.0 - psi / 120.0 + psi * psi / 5040.0;
+  }
+}
+
+__device__ __forceinline__ int kepler_exact(double& rx, double& ry, double& vx, double& vy, double mu, double dt) {
+  const double r0 = hypot(rx, ry);
+  if (r0 < 1e-14) {
+    rx += vx * dt;
+    ry += vy * dt;
+    return 0;
+  }
+  const double sm = sqrt(mu);
+  const double rv = rx * vx + ry * vy;
+  const double alpha = 2.0 / r0 - (vx * vx + vy * vy) / mu;
+  double chi = sm * dt / r0;                 // good for small steps
+  if (alpha > 1e-12) chi = sm * dt * alpha;
+  double c2 = 0.5, c3 = 1.0 / 6.0;
+  int it = 0;
+  for (; it < 64; ++it) {
+    const double chi2 = chi * chi;
+    stumpff(alpha * chi2, c2, c3);
+    const double f = rv / sm * chi2 * c2 + (1.0 - alpha * r0) * chi2 * chi * c3 + r0 * chi - sm * dt;
+    const double fp = rv / sm * chi * (1.0 - alpha * chi2 * c3) + (1.0 - alpha * r0) * chi2 * c2 + r0;
+    const double d = f / fp;
+    chi -= d;
+    if (fabs(d) <= 4e-16 * fabs(chi)) {
+      ++it;
+      break;
+    }
+  }
+  const double chi2 = chi * chi;
+  stumpff(alpha * chi2, c2, c3);
+  const double f = 1.0 - chi2 * c2 / r0;
+  const double g = dt - chi2 * chi * c3 / sm;
+  const double nx = f * rx + g * vx, ny = f * ry + g * vy;
+  const double rn = hypot(nx, ny);
+  const double fdot = sm / (rn * r0) * (alpha * chi2 * chi * c3 - chi);
+  const double gdot = 1.0 - chi2 * c2 / rn;
+  const double wx = fdot * rx + gdot * vx, wy = fdot * ry + gdot * vy;
+  rx = nx;
+  ry = ny;
+  vx = wx;
+  vy = wy;
+  return it;
+}
+
+}  // namespace nb
