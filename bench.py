@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native NBodySimProject hot path.
+
+Workload (BASELINE.json configs[2], "C3"): a batch stability ensemble of hierarchical / polygon / random /
+close-encounter systems with N = 3..8 bodies, integrator yoshida4, dt = 0.01, n_steps = 1000 main steps +
+50 tangent-map (MEGNO) steps, analysis mode 'full' -- i.e. BatchStabilityAnalyzer.analyze_batch
+(batch_stability_analyzer.py:62-80) for `--systems` systems per GPU.  One bench "step" = one full pass of that
+analysis over the batch.  Systems are sharded by system over ranks, no data-path collective (weak scaling).
+
+  value : system-steps/s with the inputs already resident in HBM (CUDA events, max over ranks)
+  e2e   : the same metric through the C-ABI host entry point nb_ensemble_analyze_host_async with pinned HOST
+          buffers: H2D of every input and D2H of the feature tables inside the timed region
+  roofline : FP64-pipe roofline of the dominant kernel (ensemble_main_kernel<N, yoshida4>), algorithmic flops
+          from SURVEY.md section 8d, peak = DFMA micro-benchmark measured live on the same GPU
+  cpu_baseline : the NumPy oracle (a restatement of the reference's Python path) on the host cores
+
+`--impl reference` times that CPU path alone (the reference is pure Python and cannot travel to the GPU box;
+the oracle port is pinned against the reference's outputs by tests/test_oracle_golden.py).
+`--workload largen` reports the large-N direct-sum kernel (pair-interactions/s) instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DT = 0.01
+N_STEPS = 1000
+N_MEGNO = 50
+MODE = "yoshida4"
+STEPS_PER_SYSTEM = N_STEPS + N_MEGNO
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = upper half of the samples
+        s = sorted(sm)
+        return {"sm_mhz": float(np.median(s[len(s) // 2:])), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(n_systems: int, seed: int):
+    """Diverse cohort (ml_training_pipeline.py:44-122 extended to N <= 8) + per-system tangent draws."""
+    from nbodysimproject_b200.generators import EnsembleInputs
+    rng = np.random.default_rng(seed)
+    buckets = EnsembleInputs.diverse(rng, n_systems, n_max=8)
+    out = {}
+    for N, (m, q, v, soft, cohort) in sorted(buckets.items()):
+        B = m.shape[0]
+        out[N] = dict(m=m, q=q, v=v, eps=soft, raw_dr=rng.standard_normal((B, N, 2)),
+                      raw_dv=rng.standard_normal((B, N, 2)), cohort=cohort)
+    return out
+
+
+def flops_main(N, n_sub_sum, n_steps):
+    """yoshida4 sub-step = 3 force evaluations (14 flop / ordered pair) + 36 N kick/drift flops."""
+    return float(n_sub_sum) * n_steps * (3 * 14.0 * N * (N - 1) + 36.0 * N)
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference's Python path)
+# ---------------------------------------------------------------------------------------------
+
+def _cpu_worker(job):
+    from oracle import nbody_oracle as O
+    m, q, v, eps, rr, rv = job
+    sim = O.OracleSim(m, q, v, softening=float(eps), integrator_mode=MODE)
+    O.run_stability_analysis(sim, N_STEPS, DT, "full", rr, rv)
+    return STEPS_PER_SYSTEM
+
+
+def cpu_sample_jobs(n_jobs: int, seed: int):
+    inp = make_inputs(max(64, n_jobs * 4), seed)
+    jobs = []
+    # round-robin over the N buckets so the sample has the workload's mix
+    keys = sorted(inp)
+    idx = {k: 0 for k in keys}
+    while len(jobs) < n_jobs:
+        for k in keys:
+            d = inp[k]
+            i = idx[k]
+            if i < d["m"].shape[0] and len(jobs) < n_jobs:
+                jobs.append((d["m"][i], d["q"][i], d["v"][i], d["eps"][i], d["raw_dr"][i], d["raw_dv"][i]))
+                idx[k] += 1
+    return jobs
+
+
+def run_cpu(n_jobs: int, cores: int, seed: int = 777):
+    import multiprocessing as mp
+    jobs = cpu_sample_jobs(n_jobs, seed)
+    t0 = time.perf_counter()
+    if cores > 1:
+        with mp.get_context("fork").Pool(cores) as pool:
+            done = sum(pool.map(_cpu_worker, jobs, chunksize=1))
+    else:
+        done = sum(_cpu_worker(j) for j in jobs)
+    dt = time.perf_counter() - t0
+    return done / dt, dt
+
+
+def impl_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_jobs = max(cores, 8) * 4
+    times, done = [], 0
+    for it in range(args.warmup + args.steps):
+        rate, dt = run_cpu(n_jobs, cores, seed=1000 + it)
+        if it >= args.warmup:
+            times.append(dt)
+            done += n_jobs * STEPS_PER_SYSTEM
+        if sum(times) > 150:          # keep the whole arm within a few minutes
+            break
+    total = sum(times)
+    value = done / total
+    k = len(times)
+    line = {
+        "impl": "reference", "metric": "system-steps/s (N=3-8 ensembles, MEGNO on)", "value": value,
+        "unit": "system-steps/s", "n_gpus": args.gpus, "steps": k, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / max(k, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3 batch stability ensemble: diverse N=3-8 cohort, yoshida4, 1000+50 MEGNO steps, "
+                               "mode full (bounded CPU sample of the same generator)",
+                   "systems_per_step": n_jobs, "integrator": MODE, "dt": DT},
+        "cpu_baseline": {"value": value, "unit": "system-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_jobs} systems x {STEPS_PER_SYSTEM} steps per bench step, NumPy oracle "
+                                   f"(oracle/nbody_oracle.py) in {cores} worker processes"},
+        "e2e": {"value": value, "unit": "system-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+
+def impl_b200(args):
+    import torch
+    import torch.distributed as dist
+    from nbodysimproject_b200 import _lib as L
+    from nbodysimproject_b200 import ensemble as E
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()
+
+    if args.workload == "largen":
+        return bench_largen(args, torch, dist, world, rank, local, dev)
+
+    B_total = args.systems
+    inp = make_inputs(B_total, seed=42 + rank)
+    Ns = sorted(inp)
+    # pinned host buffers (e2e) and device-resident copies (value)
+    host, devb = {}, {}
+    h2d = d2h = 0
+    for N in Ns:
+        d = inp[N]
+        B = d["m"].shape[0]
+        hb = {}
+        for k in ("m", "q", "v", "eps", "raw_dr", "raw_dv"):
+            t = torch.from_numpy(np.ascontiguousarray(d[k], dtype=np.float64)).pin_memory()
+            hb[k] = t
+            h2d += t.numel() * 8
+        hb["v_work"] = torch.empty_like(hb["v"]).pin_memory()
+        hb["dyn"] = torch.empty((B, L.N_DYN), dtype=torch.float64).pin_memory()
+        hb["stat"] = torch.empty((B, L.N_STATIC), dtype=torch.float64).pin_memory()
+        hb["nsub"] = torch.empty((B,), dtype=torch.int32).pin_memory()
+        hb["status"] = torch.empty((B,), dtype=torch.int32).pin_memory()
+        d2h += hb["dyn"].numel() * 8 + hb["stat"].numel() * 8 + B * 8 + hb["v"].numel() * 8
+        host[N] = hb
+        bk = E.DeviceBucket(hb["m"], hb["q"], hb["v"], hb["eps"], 1.0, MODE, dev)
+        bk.v0 = bk.v.clone()
+        bk.q0 = bk.q.clone()
+        bk.rdr = hb["raw_dr"].to(dev)
+        bk.rdv = hb["raw_dv"].to(dev)
+        bk.stream = torch.cuda.Stream(device=dev)
+        devb[N] = bk
+    prep_flags = L.PREP_REMOVE_COM | L.PREP_CTOR_KICK | L.PREP_SNAPSHOT_KICK
+    interval = max(1, N_STEPS // 100)
+    launches_per_step = 0
+
+    def step_device():
+        nonlocal launches_per_step
+        cur = torch.cuda.current_stream()
+        n = 0
+        for N in Ns:
+            bk = devb[N]
+            bk.stream.wait_stream(cur)
+            with torch.cuda.stream(bk.stream):
+                bk.q.copy_(bk.q0)
+                bk.v.copy_(bk.v0)
+                bk.prepare(prep_flags, 0.01, 0.01, DT, 50, want_static=True)     # 1 kernel
+                bk.sort()                                                        # 3 kernels
+                bk.dyn = bk.run(DT, N_STEPS, interval, N_MEGNO, bk.rdr, bk.rdv, flags=L.RUN_ENERGY)  # 2+1+1+1
+                n += 9
+        for N in Ns:
+            cur.wait_stream(devb[N].stream)
+        launches_per_step = n
+
+    def step_e2e():
+        for slot, N in enumerate(Ns):
+            hb = host[N]
+            hb["v_work"].copy_(hb["v"])
+            B = hb["m"].shape[0]
+            L.check(lib.nb_ensemble_analyze_host_async(
+                L.ptr(hb["m"]), L.ptr(hb["q"]), L.ptr(hb["v_work"]), L.ptr(hb["eps"]), 1.0, B, N, L.MODES[MODE],
+                prep_flags, 0.01, 0.01, DT, N_STEPS, N_MEGNO, 50, L.ptr(hb["raw_dr"]), L.ptr(hb["raw_dv"]),
+                L.ptr(hb["dyn"]), L.ptr(hb["stat"]), L.ptr(hb["nsub"]), L.ptr(hb["status"]), local, slot % 8),
+                "nb_ensemble_analyze_host_async")
+        for slot in range(min(len(Ns), 8)):
+            L.check(lib.nb_host_sync(slot), "nb_host_sync")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- value: device-resident
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    # ---- e2e: host buffers through the C ABI
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(tt[0]), float(tt[1])
+    sys_steps = float(B_total) * world * STEPS_PER_SYSTEM * args.steps
+
+    # ---- cross-check: e2e and device paths give identical feature tables; count statuses
+    same = all(np.array_equal(host[N]["dyn"].numpy(), devb[N].dyn.cpu().numpy(), equal_nan=True) for N in Ns)
+    n_bad = int(sum(int((host[N]["status"].numpy() != 0).sum()) for N in Ns))
+
+    # ---- roofline of the dominant kernel: ensemble_main_kernel<N, yoshida4> timed alone on the current stream
+    roof = None
+    if rank == 0:
+        peak = L.peak_flops(0, local)
+        per = []
+        for N in Ns:
+            bk = devb[N]
+            bk.q.copy_(bk.q0); bk.v.copy_(bk.v0)
+            bk.prepare(prep_flags, 0.01, 0.01, DT, 50)
+            bk.sort()
+            nsub_sum = int(bk.n_sub.sum().item())
+            best = 1e30
+            for rep in range(3):
+                bk.q.copy_(bk.q0)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                bk.run(DT, N_STEPS, interval, 0, flags=0, want_dyn=False)
+                b.record()
+                torch.cuda.synchronize()
+                best = min(best, a.elapsed_time(b) * 1e-3)
+            fl = flops_main(N, nsub_sum, N_STEPS)
+            per.append(dict(N=N, B=bk.B, mean_n_sub=nsub_sum / bk.B, ms=best * 1e3, tflops=fl / best * 1e-12))
+        dom = max(per, key=lambda r: r["ms"])
+        tot_fl = sum(r["tflops"] * r["ms"] for r in per)
+        tot_ms = sum(r["ms"] for r in per)
+        roof = {"bound": "fp64", "kernel": f"ensemble_main_kernel<N={dom['N']}, yoshida4>",
+                "achieved": dom["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": dom["tflops"] / peak,
+                "traffic": None, "peak_source": "nb_peak_flops(0): register-resident DFMA micro-benchmark, same GPU, "
+                                                "same run (MEASURED_PEAKS.json has no FP64 figure)",
+                "all_buckets": per, "aggregate_tflops": tot_fl / tot_ms, "aggregate_frac": tot_fl / tot_ms / peak,
+                "share_of_step_ms": tot_ms / (t_dev / args.steps * 1e3)}
+
+    # ---- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        n_jobs = max(cores, 8) * 24
+        rate, dt_cpu = run_cpu(n_jobs, cores)
+        cpu = {"value": rate, "unit": "system-steps/s", "cores": cores, "kind": "port",
+               "sample": f"{n_jobs} systems x {STEPS_PER_SYSTEM} steps of the same generator, NumPy oracle in "
+                         f"{cores} processes, {dt_cpu:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "system-steps/s (N=3-8 ensembles, MEGNO on)", "value": sys_steps / t_dev,
+            "unit": "system-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3 batch stability ensemble (BASELINE.json configs[2]): diverse cohort "
+                                   "40% random N=3-8 / 30% hierarchical triples / 20% polygons / 10% close encounters, "
+                                   "yoshida4 dt=0.01, 1000 steps + 50 tangent-map MEGNO steps, mode full",
+                       "systems_per_gpu": B_total, "buckets": {str(N): int(devb[N].B) for N in Ns},
+                       "sharding": "by system, no collective", "l2_note": "inputs re-read from HBM each step "
+                       f"({h2d / 1e6:.0f} MB per GPU > 126 MB L2)"},
+            "e2e": {"value": sys_steps / t_e2e, "unit": "system-steps/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "api": "nb_ensemble_analyze_host_async (C ABI, pinned host buffers)"},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "checks": {"e2e_equals_device_path": bool(same), "systems_with_nonzero_status": n_bad},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_largen(args, torch, dist, world, rank, local, dev):
+    from nbodysimproject_b200.largen import bench_largen as run
+    line = run(args, world, rank, local, dev)
+    if rank == 0 and line is not None:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ensemble", choices=["ensemble", "largen"])
+    ap.add_argument("--systems", type=int, default=1 << 20, help="systems per GPU (weak scaling)")
+    ap.add_argument("--n", type=int, default=1 << 20, help="particles for --workload largen")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        impl_reference(args)
+    else:
+        impl_b200(args)
+
+
+if __name__ == "__main__":
+    main()

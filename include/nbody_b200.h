@@ -128,6 +128,16 @@ int nb_ensemble_analyze_host(const double* m, const double* q, double* v, const 
                              const double* raw_dv, double* dyn_features, double* static_features,
                              int32_t* n_sub_out, int32_t* status, int device);
 
+/* asynchronous form: enqueues everything on workspace slot `slot` (0..7, each with its own stream and
+ * device buffers) and returns; host buffers must stay alive (and should be pinned) until nb_host_sync(slot).
+ * Several buckets in flight on different slots overlap their copies and kernels. */
+int nb_ensemble_analyze_host_async(const double* m, const double* q, double* v, const double* eps, double G,
+                             int B, int N, int mode, unsigned prep_flags, double kick_dt, double sched_dt,
+                             double dt, int n_steps, int n_megno, int split_n_max, const double* raw_dr,
+                             const double* raw_dv, double* dyn_features, double* static_features,
+                             int32_t* n_sub_out, int32_t* status, int device, int slot);
+int nb_host_sync(int slot);
+
 /* ---- large-N direct sum (new capability, same formula as forces.py:63-75 / 77-112 / potential.py:23-64),
  *      fp32 pair arithmetic, fp64 accumulation across j-tiles.  xym[n_total] = (x, y, m, 0) packed float4.
  *      Rank-local i-range [i0, i0+ni).  acc[ni] float2; sums[2] += {sum_{i in range, j} m_i m_j/rho, sum m_i m_j/rho^3}

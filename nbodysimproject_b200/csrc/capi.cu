@@ -153,31 +153,35 @@ static int peak_flops(int which, int device, double* tflops) {
   return NB_OK;
 }
 
-// ---- cached workspace for the *_host entry points ----------------------------------------------------------
+// ---- cached workspaces for the *_host entry points: NB_HOST_SLOTS independent (stream, buffer) pairs so that
+// callers can keep several buckets in flight (H2D of one overlapping the kernels of another) -----------------
+constexpr int NB_HOST_SLOTS = 8;
 struct HostWs {
   int device = -1;
   cudaStream_t stream = nullptr;
   void* buf = nullptr;
   size_t cap = 0;
 };
-static HostWs g_ws;
+static HostWs g_ws[NB_HOST_SLOTS];
 static std::mutex g_ws_mu;
 
-static int ws_reserve(int device, size_t bytes) {
-  if (g_ws.device != device) {
-    if (g_ws.buf) { cudaSetDevice(g_ws.device); cudaFree(g_ws.buf); cudaStreamDestroy(g_ws.stream); }
-    g_ws = HostWs();
+static int ws_reserve(int slot, int device, size_t bytes) {
+  HostWs& w = g_ws[slot];
+  if (w.device != device) {
+    if (w.device >= 0) { cudaSetDevice(w.device); if (w.buf) cudaFree(w.buf); if (w.stream) cudaStreamDestroy(w.stream); }
+    w = HostWs();
     NB_CUDA_CHECK(cudaSetDevice(device));
-    NB_CUDA_CHECK(cudaStreamCreateWithFlags(&g_ws.stream, cudaStreamNonBlocking));
-    g_ws.device = device;
+    NB_CUDA_CHECK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    w.device = device;
   }
   NB_CUDA_CHECK(cudaSetDevice(device));
-  if (g_ws.cap < bytes) {
-    if (g_ws.buf) cudaFree(g_ws.buf);
-    g_ws.buf = nullptr;
-    g_ws.cap = 0;
-    NB_CUDA_CHECK(cudaMalloc(&g_ws.buf, bytes));
-    g_ws.cap = bytes;
+  if (w.cap < bytes) {
+    NB_CUDA_CHECK(cudaStreamSynchronize(w.stream));
+    if (w.buf) cudaFree(w.buf);
+    w.buf = nullptr;
+    w.cap = 0;
+    NB_CUDA_CHECK(cudaMalloc(&w.buf, bytes));
+    w.cap = bytes;
   }
   return NB_OK;
 }
@@ -239,10 +243,11 @@ int nb_sort_by_nsub(const int32_t* n_sub, int B, int32_t* perm, int32_t* workspa
   return sort_by_nsub(n_sub, B, perm, workspace64, (cudaStream_t)stream);
 }
 
-int nb_ensemble_analyze_host(const double* m, const double* q, double* v, const double* eps, double G, int B, int N,
+int nb_ensemble_analyze_host_async(const double* m, const double* q, double* v, const double* eps, double G, int B, int N,
                              int mode, unsigned prep_flags, double kick_dt, double sched_dt, double dt, int n_steps,
                              int n_megno, int split_n_max, const double* raw_dr, const double* raw_dv, double* dyn_features,
-                             double* static_features, int32_t* n_sub_out, int32_t* status, int device) {
+                             double* static_features, int32_t* n_sub_out, int32_t* status, int device, int slot) {
+  if (slot < 0 || slot >= NB_HOST_SLOTS) { set_error("nb_ensemble_analyze_host_async: slot out of range"); return NB_ERR_ARG; }
   if (!m || !q || !v || !eps || !dyn_features || B < 0 || N < NB_MIN_N || N > NB_MAX_N) { set_error("nb_ensemble_analyze_host: bad arguments"); return NB_ERR_ARG; }
   if (mode == NB_MODE_HAMSOFT) { set_error("nb_ensemble_analyze_host: ham_soft goes through nb_ensemble_run_f64"); return NB_ERR_UNSUPPORTED; }
   if (n_megno > 0 && (!raw_dr || !raw_dv)) { set_error("nb_ensemble_analyze_host: n_megno > 0 needs raw_dr/raw_dv"); return NB_ERR_ARG; }
@@ -253,10 +258,10 @@ int nb_ensemble_analyze_host(const double* m, const double* q, double* v, const 
   const size_t sz_dyn = align256((size_t)B * NB_N_DYN * 8), sz_stat = align256((size_t)B * NB_N_STATIC * 8);
   const size_t sz_i = align256((size_t)B * 4);
   const size_t total = sz_m + 4 * sz_q + sz_b + sz_dyn + sz_stat + 3 * sz_i + 256;
-  int rc = ws_reserve(device, total);
+  int rc = ws_reserve(slot, device, total);
   if (rc != NB_OK) return rc;
-  cudaStream_t st = g_ws.stream;
-  char* p = (char*)g_ws.buf;
+  cudaStream_t st = g_ws[slot].stream;
+  char* p = (char*)g_ws[slot].buf;
   double* d_m = (double*)p; p += sz_m;
   double* d_q = (double*)p; p += sz_q;
   double* d_v = (double*)p; p += sz_q;
@@ -294,8 +299,26 @@ int nb_ensemble_analyze_host(const double* m, const double* q, double* v, const 
   if (static_features) NB_CUDA_CHECK(cudaMemcpyAsync(static_features, d_stat, (size_t)B * NB_N_STATIC * 8, cudaMemcpyDeviceToHost, st));
   if (n_sub_out) NB_CUDA_CHECK(cudaMemcpyAsync(n_sub_out, d_nsub, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   if (status) NB_CUDA_CHECK(cudaMemcpyAsync(status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-  NB_CUDA_CHECK(cudaStreamSynchronize(st));
   return NB_OK;
+}
+
+int nb_host_sync(int slot) {
+  if (slot < 0 || slot >= NB_HOST_SLOTS) { set_error("nb_host_sync: slot out of range"); return NB_ERR_ARG; }
+  if (g_ws[slot].device < 0) return NB_OK;
+  NB_CUDA_CHECK(cudaSetDevice(g_ws[slot].device));
+  NB_CUDA_CHECK(cudaStreamSynchronize(g_ws[slot].stream));
+  return NB_OK;
+}
+
+int nb_ensemble_analyze_host(const double* m, const double* q, double* v, const double* eps, double G, int B, int N,
+                             int mode, unsigned prep_flags, double kick_dt, double sched_dt, double dt, int n_steps,
+                             int n_megno, int split_n_max, const double* raw_dr, const double* raw_dv, double* dyn_features,
+                             double* static_features, int32_t* n_sub_out, int32_t* status, int device) {
+  int rc = nb_ensemble_analyze_host_async(m, q, v, eps, G, B, N, mode, prep_flags, kick_dt, sched_dt, dt, n_steps, n_megno,
+                                          split_n_max, raw_dr, raw_dv, dyn_features, static_features, n_sub_out, status,
+                                          device, 0);
+  if (rc != NB_OK) return rc;
+  return nb_host_sync(0);
 }
 
 int nb_largeN_accel_f32(const float* xym, int n_total, int i0, int ni, float eps, float G, float* acc, double* sums,

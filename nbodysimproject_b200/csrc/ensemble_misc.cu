@@ -3,17 +3,98 @@
 
 namespace nb {
 
-int ensemble_run_verlet(const RunArgs& a, int N, cudaStream_t st);
-int ensemble_run_yoshida4(const RunArgs& a, int N, cudaStream_t st);
-int ensemble_run_whfast(const RunArgs& a, int N, cudaStream_t st);
+int ensemble_run_verlet(const RunArgs& a, int N, int phase, int write_state, cudaStream_t st);
+int ensemble_run_yoshida4(const RunArgs& a, int N, int phase, int write_state, cudaStream_t st);
+int ensemble_run_whfast(const RunArgs& a, int N, int phase, int write_state, cudaStream_t st);
+
+// T + U with double-double accumulation; each part rounded to fp64 and then added, like
+// diagnostics.py:543-549 does with its long-double Kahan sums.  One thread per system, straight from
+// global memory (runs twice per analysis, so it is kept out of the register-resident hot kernels).
+__global__ void __launch_bounds__(128) energy_kernel(const double* __restrict__ m, const double* __restrict__ q,
+                                                     const double* __restrict__ v, const double* __restrict__ eps_arr,
+                                                     double G, int B, int N, double* dyn, int slot) {
+  const int sys = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sys >= B) return;
+  const double* mm = m + (size_t)sys * N;
+  const double* qq = q + (size_t)sys * N * 2;
+  const double* vv = v + (size_t)sys * N * 2;
+  const double eps = eps_arr[sys];
+  dd T = dd_make(0.0);
+  double L = 0.0;
+  for (int i = 0; i < N; ++i) {
+    const double vx = vv[2 * i], vy = vv[2 * i + 1];
+    dd v2 = dd_add(two_prod(vx, vx), two_prod(vy, vy));
+    T = dd_add(T, dd_mul_d(dd_mul_d(v2, mm[i]), 0.5));
+    L += mm[i] * __dadd_rn(__dmul_rn(qq[2 * i], vy), -__dmul_rn(qq[2 * i + 1], vx));   // diagnostics.py:553-557
+  }
+  dd S = dd_make(0.0);
+  const dd e2 = two_prod(eps, eps);
+  if (G != 0.0) {
+    for (int i = 0; i < N; ++i)
+      for (int j = i + 1; j < N; ++j) {
+        dd dx = two_sum(qq[2 * i], -qq[2 * j]);
+        dd dy = two_sum(qq[2 * i + 1], -qq[2 * j + 1]);
+        dd r2 = dd_add(dd_add(dd_mul(dx, dx), dd_mul(dy, dy)), e2);
+        if (!(r2.hi > 0.0)) r2 = dd_make(1e-300);
+        dd inv = dd_div(dd_make(1.0), dd_sqrt(r2));
+        S = dd_add(S, dd_mul(two_prod(mm[i], mm[j]), inv));
+      }
+  }
+  const double Tf = dd_to_double(T);
+  const double Vf = dd_to_double(dd_mul_d(S, -G));
+  double* f = dyn + (size_t)sys * NB_N_DYN;
+  f[NB_F_E0 + slot] = Tf + Vf;
+  f[NB_F_L0 + slot] = L;
+}
+
+// drifts + the is_stable predicate (stability_analyzer.py:147-231)
+__global__ void __launch_bounds__(128) finalize_kernel(double* dyn, int B, int have_energy, int have_megno) {
+  const int sys = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sys >= B) return;
+  double* f = dyn + (size_t)sys * NB_N_DYN;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  if (!have_megno) {
+    f[NB_F_MEGNO] = 2.0;
+    f[NB_F_LYAP_TIME] = __longlong_as_double(0x7ff0000000000000LL);
+    f[NB_F_T_END] = 0.0;
+  }
+  double ed = nan, ld = nan;
+  if (have_energy) {
+    ed = drift_of(f[NB_F_E0], f[NB_F_E1]);
+    ld = drift_of(f[NB_F_L0], f[NB_F_L1]);
+  } else {
+    f[NB_F_E0] = nan; f[NB_F_E1] = nan; f[NB_F_L0] = nan; f[NB_F_L1] = nan;
+  }
+  f[NB_F_ENERGY_DRIFT] = ed;
+  f[NB_F_ANGMOM_DRIFT] = ld;
+  f[NB_F_IS_STABLE] = ((ed < 0.01) && (ld < 0.01) && (f[NB_F_COM_MEAN] < 1.0) && (f[NB_F_MEGNO] < 10.0)) ? 1.0 : 0.0;
+}
 
 int ensemble_run_classic(const RunArgs& a, int N, int mode, cudaStream_t st) {
-  switch (mode) {
-    case NB_MODE_VERLET: return ensemble_run_verlet(a, N, st);
-    case NB_MODE_YOSHIDA4: return ensemble_run_yoshida4(a, N, st);
-    case NB_MODE_WHFAST: return ensemble_run_whfast(a, N, st);
-    default: set_error("nb_ensemble_run_f64: unsupported mode"); return NB_ERR_UNSUPPORTED;
+  if (N < NB_MIN_N || N > NB_MAX_N) { set_error("N must be in 2..8"); return NB_ERR_ARG; }
+  auto phase = [&](int ph, int write_state) -> int {
+    switch (mode) {
+      case NB_MODE_VERLET: return ensemble_run_verlet(a, N, ph, write_state, st);
+      case NB_MODE_YOSHIDA4: return ensemble_run_yoshida4(a, N, ph, write_state, st);
+      case NB_MODE_WHFAST: return ensemble_run_whfast(a, N, ph, write_state, st);
+      default: set_error("nb_ensemble_run_f64: unsupported mode"); return NB_ERR_UNSUPPORTED;
+    }
+  };
+  const int threads = 128, blocks = (a.B + threads - 1) / threads;
+  const bool energy = (a.flags & NB_RUN_ENERGY) != 0 && a.dyn != nullptr;
+  const bool megno = a.n_megno > 0;
+  const int write = ((a.flags & NB_RUN_WRITE_STATE) || energy || megno) ? 1 : 0;
+  if (energy) energy_kernel<<<blocks, threads, 0, st>>>(a.m, a.q, a.v, a.eps, a.G, a.B, N, a.dyn, 0);
+  int rc = phase(0, write);
+  if (rc != NB_OK) return rc;
+  if (energy) energy_kernel<<<blocks, threads, 0, st>>>(a.m, a.q, a.v, a.eps, a.G, a.B, N, a.dyn, 1);
+  if (megno) {
+    rc = phase(1, (a.flags & NB_RUN_WRITE_STATE) ? 1 : 0);
+    if (rc != NB_OK) return rc;
   }
+  if (a.dyn) finalize_kernel<<<blocks, threads, 0, st>>>(a.dyn, a.B, energy ? 1 : 0, megno ? 1 : 0);
+  NB_CUDA_CHECK(cudaGetLastError());
+  return NB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

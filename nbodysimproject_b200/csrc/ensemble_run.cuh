@@ -188,32 +188,6 @@ __device__ __forceinline__ int substep(SysState<N>& s, const double* m, double G
   return kep;
 }
 
-// T + U with double-double accumulation; each part rounded to fp64 and then added, like
-// diagnostics.py:543-549 does with its long-double Kahan sums.
-template <int N>
-__device__ __noinline__ double energy_dd(const double* m, const double* x, const double* y, const double* vx,
-                                         const double* vy, double eps, double G) {
-  dd T = dd_make(0.0);
-  for (int i = 0; i < N; ++i) {
-    dd v2 = dd_add(two_prod(vx[i], vx[i]), two_prod(vy[i], vy[i]));
-    T = dd_add(T, dd_mul_d(dd_mul_d(v2, m[i]), 0.5));
-  }
-  dd S = dd_make(0.0);
-  const dd e2 = two_prod(eps, eps);
-  for (int i = 0; i < N; ++i)
-    for (int j = i + 1; j < N; ++j) {
-      dd dx = two_sum(x[i], -x[j]);
-      dd dy = two_sum(y[i], -y[j]);
-      dd r2 = dd_add(dd_add(dd_mul(dx, dx), dd_mul(dy, dy)), e2);
-      if (!(r2.hi > 0.0)) r2 = dd_make(1e-300);
-      dd inv = dd_div(dd_make(1.0), dd_sqrt(r2));
-      S = dd_add(S, dd_mul(two_prod(m[i], m[j]), inv));
-    }
-  const double Tf = dd_to_double(T);
-  const double Vf = dd_to_double(dd_mul_d(S, -G));
-  return Tf + Vf;
-}
-
 __device__ __forceinline__ double drift_of(double a0, double a1) {  // stability_analyzer.py:147-170
   if (is_finite(a0) && fabs(a0) > 0.0 && is_finite(a1)) return fabs((a1 - a0) / a0);
   if (is_finite(a0) && is_finite(a1)) return fabs(a1 - a0);
@@ -221,28 +195,11 @@ __device__ __forceinline__ double drift_of(double a0, double a1) {  // stability
 }
 
 template <int N>
-__device__ __forceinline__ double angmom(const double* m, const SysState<N>& s) {  // diagnostics.py:553-557
-  double L = 0.0;
-#pragma unroll
-  for (int i = 0; i < N; ++i) L += m[i] * (s.x[i] * s.vy[i] - s.y[i] * s.vx[i]);
-  return L;
-}
-
-// ---------------------------------------------------------------------------------------------
-// run kernel
-// ---------------------------------------------------------------------------------------------
-template <int N, int MODE, bool GUARD, bool EXACT>
-__global__ void __launch_bounds__(128) ensemble_run_kernel(RunArgs a) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= a.B) return;
-  const int sys = a.perm ? a.perm[t] : t;
-  SysState<N> s;
-  double m[N];
-  const double G = a.G;
+__device__ __forceinline__ void load_state(const RunArgs& a, int sys, SysState<N>& s, double* m) {
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     m[i] = a.m[(size_t)sys * N + i];
-    s.gm[i] = G * m[i];
+    s.gm[i] = a.G * m[i];
     s.x[i] = a.q[((size_t)sys * N + i) * 2 + 0];
     s.y[i] = a.q[((size_t)sys * N + i) * 2 + 1];
     s.vx[i] = a.v[((size_t)sys * N + i) * 2 + 0];
@@ -250,33 +207,55 @@ __global__ void __launch_bounds__(128) ensemble_run_kernel(RunArgs a) {
   }
   const double eps = a.eps[sys];
   s.eps2 = eps * eps;
+}
+
+template <int N>
+__device__ __forceinline__ int store_state(const RunArgs& a, int sys, const SysState<N>& s, bool write) {
+  bool finite = true;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    finite = finite && is_finite(s.x[i]) && is_finite(s.y[i]) && is_finite(s.vx[i]) && is_finite(s.vy[i]);
+  if (write) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      a.q[((size_t)sys * N + i) * 2 + 0] = s.x[i];
+      a.q[((size_t)sys * N + i) * 2 + 1] = s.y[i];
+      a.v[((size_t)sys * N + i) * 2 + 0] = s.vx[i];
+      a.v[((size_t)sys * N + i) * 2 + 1] = s.vy[i];
+    }
+  }
+  return finite ? 0 : NB_STATUS_NONFINITE;
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 1: the main loop, n_steps macro steps with step_metrics sampling (stability_analyzer.py:113-128).
+// Nothing in here takes the address of the state, so it stays in registers for the whole run.
+// ---------------------------------------------------------------------------------------------
+template <int N, int MODE, bool GUARD, bool EXACT>
+__global__ void __launch_bounds__(128) ensemble_main_kernel(RunArgs a, int write_state) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.B) return;
+  const int sys = a.perm ? a.perm[t] : t;
+  SysState<N> s;
+  double m[N];
+  load_state<N>(a, sys, s, m);
+  const double G = a.G;
+  const double eps = a.eps[sys];
   const int n_sub = a.n_sub ? max(1, a.n_sub[sys]) : 1;
   const double h = a.dt / (double)n_sub;
-  const bool want_energy = (a.flags & NB_RUN_ENERGY) != 0;
-  int st = 0;
   int kep_worst = 0;
+  if (MODE != NB_MODE_WHFAST) pair_pass<N, false, GUARD>(s, nullptr, nullptr, nullptr, nullptr);   // FSAL start
 
-  double E0 = 0.0, L0 = 0.0;
-  if (want_energy) {
-    E0 = energy_dd<N>(m, s.x, s.y, s.vx, s.vy, eps, G);
-    L0 = angmom<N>(m, s);
-  }
-  // FSAL start acceleration
-  if (MODE != NB_MODE_WHFAST) pair_pass<N, false, GUARD>(s, nullptr, nullptr, nullptr, nullptr);
-
-  // ---- main loop with step_metrics sampling (stability_analyzer.py:113-128)
-  double com_sum = 0.0, com_max = -1.0, var_sum = 0.0, var_max = -1.0, cos_sum = 0.0, cos_min = 2.0;
-  double th_sum = 0.0;
+  double com_sum = 0.0, com_max = -1.0, var_sum = 0.0, var_max = -1.0, cos_sum = 0.0, cos_min = 2.0, th_sum = 0.0;
   double Lfirst = 0.0;
   bool have_first = false, cos_nan = false;
-  int n_samp = 0;
-  int next_sample = 0;
+  int n_samp = 0, next_sample = 0;
   const int interval = a.sample_interval;
   for (int step = 0; step < a.n_steps; ++step) {
 #pragma unroll 1
     for (int k = 0; k < n_sub; ++k)
       kep_worst = max(kep_worst, substep<N, MODE, GUARD, EXACT, false>(s, m, G, h, nullptr, nullptr, nullptr, nullptr));
-    if (interval > 0 && step == next_sample) {
+    if (interval > 0 && step == next_sample) {       // diagnostics.py:241-285
       next_sample += interval;
       double cx = 0.0, cy = 0.0, Lt = 0.0, Li[N];
 #pragma unroll
@@ -303,103 +282,14 @@ __global__ void __launch_bounds__(128) ensemble_run_kernel(RunArgs a) {
       ++n_samp;
     }
   }
-
-  double E1 = 0.0, L1 = 0.0;
-  if (want_energy) {
-    E1 = energy_dd<N>(m, s.x, s.y, s.vx, s.vy, eps, G);
-    L1 = angmom<N>(m, s);
-  }
-
-  // ---- MEGNO (evolution_features.py:34-66)
-  double megno = 2.0, lyap = __longlong_as_double(0x7ff0000000000000LL), t_end = 0.0;
-  if (a.n_megno > 0) {
-    double drx[N], dry[N], dvx[N], dvy[N], dax[N], day[N];
-    {
-      double M = 0.0, cx = 0.0, cy = 0.0, ux = 0.0, uy = 0.0;
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        drx[i] = a.raw_dr[((size_t)sys * N + i) * 2 + 0];
-        dry[i] = a.raw_dr[((size_t)sys * N + i) * 2 + 1];
-        dvx[i] = a.raw_dv[((size_t)sys * N + i) * 2 + 0];
-        dvy[i] = a.raw_dv[((size_t)sys * N + i) * 2 + 1];
-        M += m[i];
-        cx += m[i] * drx[i]; cy += m[i] * dry[i];
-        ux += m[i] * dvx[i]; uy += m[i] * dvy[i];
-      }
-      cx /= M; cy /= M; ux /= M; uy /= M;
-      double nr = 0.0, nv = 0.0;
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        drx[i] -= cx; dry[i] -= cy; dvx[i] -= ux; dvy[i] -= uy;
-        nr += drx[i] * drx[i] + dry[i] * dry[i];
-        nv += dvx[i] * dvx[i] + dvy[i] * dvy[i];
-      }
-      nr = sqrt(nr); nv = sqrt(nv);
-#pragma unroll
-      for (int i = 0; i < N; ++i) { drx[i] /= nr; dry[i] /= nr; dvx[i] /= nv; dvy[i] /= nv; }
-    }
-    double tt = 0.0, accum = 0.0;
-    const double dt = a.dt;
-    for (int step = 0; step < a.n_megno; ++step) {
-#pragma unroll 1
-      for (int k = 0; k < n_sub - 1; ++k)
-        kep_worst = max(kep_worst, substep<N, MODE, GUARD, EXACT, false>(s, m, G, h, nullptr, nullptr, nullptr, nullptr));
-      // delta_r += delta_v dt does not depend on the step, so it can precede the fused last evaluation
-#pragma unroll
-      for (int i = 0; i < N; ++i) { drx[i] = fma(dvx[i], dt, drx[i]); dry[i] = fma(dvy[i], dt, dry[i]); }
-      kep_worst = max(kep_worst, substep<N, MODE, GUARD, EXACT, true>(s, m, G, h, drx, dry, dax, day));
-      double nr = 0.0, nv = 0.0;
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        dvx[i] = fma(dax[i], dt, dvx[i]);
-        dvy[i] = fma(day[i], dt, dvy[i]);
-        nr += drx[i] * drx[i] + dry[i] * dry[i];
-      }
-      tt += dt;
-      nr = sqrt(nr);
-      if (nr < 1e-12) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) { drx[i] /= nr; dry[i] /= nr; dvx[i] /= nr; dvy[i] /= nr; }
-        nr = 1.0;
-      }
-#pragma unroll
-      for (int i = 0; i < N; ++i) nv += dvx[i] * dvx[i] + dvy[i] * dvy[i];
-      nv = sqrt(nv);
-      accum += (nv / nr) * tt * dt;
-    }
-    megno = 2.0 * accum / tt;
-    lyap = (megno == 0.0) ? __longlong_as_double(0x7ff0000000000000LL) : tt / fabs(megno);
-    t_end = tt;
-  }
-
-  // ---- outputs
-  bool finite = true;
-#pragma unroll
-  for (int i = 0; i < N; ++i)
-    finite = finite && is_finite(s.x[i]) && is_finite(s.y[i]) && is_finite(s.vx[i]) && is_finite(s.vy[i]);
-  if (!finite) st |= NB_STATUS_NONFINITE;
+  int st = store_state<N>(a, sys, s, write_state != 0);
   if (MODE == NB_MODE_WHFAST && kep_worst >= 64) st |= NB_STATUS_KEPLER_NOCONV;
   if (a.status) a.status[sys] = st;
-
-  if (a.flags & NB_RUN_WRITE_STATE) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      a.q[((size_t)sys * N + i) * 2 + 0] = s.x[i];
-      a.q[((size_t)sys * N + i) * 2 + 1] = s.y[i];
-      a.v[((size_t)sys * N + i) * 2 + 0] = s.vx[i];
-      a.v[((size_t)sys * N + i) * 2 + 1] = s.vy[i];
-    }
-  }
   if (a.dyn) {
     double* f = a.dyn + (size_t)sys * NB_N_DYN;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    const double ed = want_energy ? drift_of(E0, E1) : nan;
-    const double ld = want_energy ? drift_of(L0, L1) : nan;
     const double inv = n_samp > 0 ? 1.0 / (double)n_samp : nan;
-    const double com_mean = n_samp > 0 ? com_sum * inv : nan;
-    f[NB_F_ENERGY_DRIFT] = ed;
-    f[NB_F_ANGMOM_DRIFT] = ld;
-    f[NB_F_COM_MEAN] = com_mean;
+    f[NB_F_COM_MEAN] = n_samp > 0 ? com_sum * inv : nan;
     f[NB_F_COM_MAX] = n_samp > 0 ? com_max : nan;
     f[NB_F_JEPS_MEAN] = n_samp > 0 ? 0.0 : nan;   // classic: pi = 0, mu_soft = 1 (diagnostics.py:246-249)
     f[NB_F_JEPS_STD] = n_samp > 0 ? 0.0 : nan;
@@ -411,41 +301,119 @@ __global__ void __launch_bounds__(128) ensemble_run_kernel(RunArgs a) {
     f[NB_F_VARL_MAX] = n_samp > 0 ? var_max : nan;
     f[NB_F_TIDAL_MEAN] = n_samp > 0 ? 0.0 : nan;  // integrator.py:48 -- _last_tr_hessian is never updated
     f[NB_F_TIDAL_MAX] = n_samp > 0 ? 0.0 : nan;
-    f[NB_F_MEGNO] = megno;
-    f[NB_F_LYAP_TIME] = lyap;
-    f[NB_F_IS_STABLE] = ((ed < 0.01) && (ld < 0.01) && (com_mean < 1.0) && (megno < 10.0)) ? 1.0 : 0.0;
-    f[NB_F_E0] = E0;
-    f[NB_F_E1] = E1;
-    f[NB_F_L0] = L0;
-    f[NB_F_L1] = L1;
-    f[NB_F_T_END] = t_end;
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// phase 2: MEGNO (evolution_features.py:34-66): n_megno further steps with the tangent map
+// ---------------------------------------------------------------------------------------------
+template <int N, int MODE, bool GUARD, bool EXACT>
+__global__ void __launch_bounds__(128) ensemble_megno_kernel(RunArgs a, int write_state) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.B) return;
+  const int sys = a.perm ? a.perm[t] : t;
+  SysState<N> s;
+  double m[N];
+  load_state<N>(a, sys, s, m);
+  const double G = a.G;
+  const int n_sub = a.n_sub ? max(1, a.n_sub[sys]) : 1;
+  const double h = a.dt / (double)n_sub;
+  int kep_worst = 0;
+  if (MODE != NB_MODE_WHFAST) pair_pass<N, false, GUARD>(s, nullptr, nullptr, nullptr, nullptr);
+
+  double drx[N], dry[N], dvx[N], dvy[N], dax[N], day[N];
+  {
+    double M = 0.0, cx = 0.0, cy = 0.0, ux = 0.0, uy = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      drx[i] = a.raw_dr[((size_t)sys * N + i) * 2 + 0];
+      dry[i] = a.raw_dr[((size_t)sys * N + i) * 2 + 1];
+      dvx[i] = a.raw_dv[((size_t)sys * N + i) * 2 + 0];
+      dvy[i] = a.raw_dv[((size_t)sys * N + i) * 2 + 1];
+      M += m[i];
+      cx += m[i] * drx[i]; cy += m[i] * dry[i];
+      ux += m[i] * dvx[i]; uy += m[i] * dvy[i];
+    }
+    cx /= M; cy /= M; ux /= M; uy /= M;
+    double nr = 0.0, nv = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      drx[i] -= cx; dry[i] -= cy; dvx[i] -= ux; dvy[i] -= uy;
+      nr += drx[i] * drx[i] + dry[i] * dry[i];
+      nv += dvx[i] * dvx[i] + dvy[i] * dvy[i];
+    }
+    nr = sqrt(nr); nv = sqrt(nv);
+#pragma unroll
+    for (int i = 0; i < N; ++i) { drx[i] /= nr; dry[i] /= nr; dvx[i] /= nv; dvy[i] /= nv; }
+  }
+  double tt = 0.0, accum = 0.0;
+  const double dt = a.dt;
+  for (int step = 0; step < a.n_megno; ++step) {
+#pragma unroll 1
+    for (int k = 0; k < n_sub - 1; ++k)
+      kep_worst = max(kep_worst, substep<N, MODE, GUARD, EXACT, false>(s, m, G, h, nullptr, nullptr, nullptr, nullptr));
+    // delta_r += delta_v dt does not depend on the step, so it can precede the fused last evaluation
+#pragma unroll
+    for (int i = 0; i < N; ++i) { drx[i] = fma(dvx[i], dt, drx[i]); dry[i] = fma(dvy[i], dt, dry[i]); }
+    kep_worst = max(kep_worst, substep<N, MODE, GUARD, EXACT, true>(s, m, G, h, drx, dry, dax, day));
+    double nr = 0.0, nv = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      dvx[i] = fma(dax[i], dt, dvx[i]);
+      dvy[i] = fma(day[i], dt, dvy[i]);
+      nr += drx[i] * drx[i] + dry[i] * dry[i];
+    }
+    tt += dt;
+    nr = sqrt(nr);
+    if (nr < 1e-12) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) { drx[i] /= nr; dry[i] /= nr; dvx[i] /= nr; dvy[i] /= nr; }
+      nr = 1.0;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) nv += dvx[i] * dvx[i] + dvy[i] * dvy[i];
+    nv = sqrt(nv);
+    accum += (nv / nr) * tt * dt;
+  }
+  const double megno = 2.0 * accum / tt;
+  const double lyap = (megno == 0.0) ? __longlong_as_double(0x7ff0000000000000LL) : tt / fabs(megno);
+  int st = store_state<N>(a, sys, s, write_state != 0);
+  if (MODE == NB_MODE_WHFAST && kep_worst >= 64) st |= NB_STATUS_KEPLER_NOCONV;
+  if (a.status) a.status[sys] |= st;
+  if (a.dyn) {
+    double* f = a.dyn + (size_t)sys * NB_N_DYN;
+    f[NB_F_MEGNO] = megno;
+    f[NB_F_LYAP_TIME] = lyap;
+    f[NB_F_T_END] = tt;
+  }
+}
 
 template <int N, int MODE>
-static int launch_run_mode(const RunArgs& a, cudaStream_t st) {
+static int launch_run_mode(const RunArgs& a, int phase, int write_state, cudaStream_t st) {
   const int threads = 128;
   const int blocks = (a.B + threads - 1) / threads;
-  const bool exact = (a.flags & NB_RUN_KEPLER_EXACT) != 0;
-  if (MODE == NB_MODE_WHFAST && exact)
-    ensemble_run_kernel<N, MODE, true, true><<<blocks, threads, 0, st>>>(a);
-  else
-    ensemble_run_kernel<N, MODE, true, false><<<blocks, threads, 0, st>>>(a);
+  const bool exact = MODE == NB_MODE_WHFAST && (a.flags & NB_RUN_KEPLER_EXACT) != 0;
+  if (phase == 0) {
+    if (exact) ensemble_main_kernel<N, MODE, true, MODE == NB_MODE_WHFAST><<<blocks, threads, 0, st>>>(a, write_state);
+    else ensemble_main_kernel<N, MODE, true, false><<<blocks, threads, 0, st>>>(a, write_state);
+  } else {
+    if (exact) ensemble_megno_kernel<N, MODE, true, MODE == NB_MODE_WHFAST><<<blocks, threads, 0, st>>>(a, write_state);
+    else ensemble_megno_kernel<N, MODE, true, false><<<blocks, threads, 0, st>>>(a, write_state);
+  }
   NB_CUDA_CHECK(cudaGetLastError());
   return NB_OK;
 }
 
 template <int MODE>
-static int launch_run_n(const RunArgs& a, int N, cudaStream_t st) {
+static int launch_run_n(const RunArgs& a, int N, int phase, int write_state, cudaStream_t st) {
   switch (N) {
-    case 2: return launch_run_mode<2, MODE>(a, st);
-    case 3: return launch_run_mode<3, MODE>(a, st);
-    case 4: return launch_run_mode<4, MODE>(a, st);
-    case 5: return launch_run_mode<5, MODE>(a, st);
-    case 6: return launch_run_mode<6, MODE>(a, st);
-    case 7: return launch_run_mode<7, MODE>(a, st);
-    case 8: return launch_run_mode<8, MODE>(a, st);
+    case 2: return launch_run_mode<2, MODE>(a, phase, write_state, st);
+    case 3: return launch_run_mode<3, MODE>(a, phase, write_state, st);
+    case 4: return launch_run_mode<4, MODE>(a, phase, write_state, st);
+    case 5: return launch_run_mode<5, MODE>(a, phase, write_state, st);
+    case 6: return launch_run_mode<6, MODE>(a, phase, write_state, st);
+    case 7: return launch_run_mode<7, MODE>(a, phase, write_state, st);
+    case 8: return launch_run_mode<8, MODE>(a, phase, write_state, st);
     default: set_error("N must be in 2..8"); return NB_ERR_ARG;
   }
 }

@@ -127,6 +127,53 @@ def gen_kepler(mb):
     print("kepler: 200 cases")
 
 
+def _alt_force(q, m, eps=0.0, G=1.0):
+    """Mathematically identical to forces.py:63-75 with different rounding (sequential pair loop,
+    (1/sqrt)^3, no m_i multiply/divide) -- what any re-implementation, CPU or GPU, looks like."""
+    q = np.asarray(q, dtype=float)
+    m = np.asarray(m, dtype=float)
+    n = len(m)
+    F = np.zeros_like(q)
+    if n < 2 or G == 0.0:
+        return F
+    for i in range(n):
+        for j in range(i + 1, n):
+            d = q[i] - q[j]
+            r2 = d[0] * d[0] + d[1] * d[1] + eps * eps
+            if r2 > 0.0:
+                w = 1.0 / np.sqrt(r2)
+                f = G * m[i] * m[j] * w * w * w * d
+                F[i] -= f
+                F[j] += f
+    return F
+
+
+def _sensitivity(mb, m, p, v, soft, mode, dt, targets):
+    """Divergence of the REFERENCE from itself when its force routine is replaced by _alt_force:
+    the chaotic amplification of last-bit rounding, i.e. the horizon beyond which no tolerance is meaningful."""
+    import minbody.simulation as simmod
+    with quiet():
+        a = mb.NBodySimulation(masses=m, positions=p, velocities=v, softening=soft, integrator_mode=mode)
+    orig = simmod.gravitational_force
+    simmod.gravitational_force = _alt_force
+    try:
+        with quiet():
+            b = mb.NBodySimulation(masses=m, positions=p, velocities=v, softening=soft, integrator_mode=mode)
+        out = {}
+        done = 0
+        for t in targets:
+            for _ in range(t - done):
+                simmod.gravitational_force = orig
+                a.step(dt)
+                simmod.gravitational_force = _alt_force
+                b.step(dt)
+            done = t
+            out[t] = float(np.max(np.abs(a._pos - b._pos)) / np.max(np.abs(a._pos)))
+    finally:
+        simmod.gravitational_force = orig
+    return out
+
+
 def gen_traj(mb):
     S = named_systems(mb)
     out = {}
@@ -159,6 +206,8 @@ def gen_traj(mb):
             with quiet():
                 snap = sim.snapshot()
             out[key + "v_snap"] = sim._vel.copy()         # snapshot half kick applied
+            for t, val in _sensitivity(mb, m, p, v, soft, mode, dt, (1, 10, 100, 1000)).items():
+                out[key + f"sens{t}"] = val
     out["names"] = np.array(names)
     np.savez_compressed(os.path.join(OUT, "trajectories.npz"), **out)
     print("trajectories:", len(names))

@@ -85,6 +85,8 @@ def test_classic_trajectories_vs_golden(E, horizon, tol):
         assert float(bk.h_sub_ref[0]) == pytest.approx(float(g[key + "h_sub_ref"]), rel=1e-14)
         assert int(bk.n_sub[0]) == int(g[key + "n_sub"])
         bk.run(0.01, horizon, flags=L.RUN_WRITE_STATE, want_dyn=False)
+        # tolerance "before chaotic divergence": see tests/test_oracle_golden.py
+        tol = max(tol, 30.0 * float(g[key + f"sens{horizon}"]))
         assert relerr(bk.q.cpu().numpy()[0], g[key + f"q{horizon}"]) < tol, key
         assert relerr(bk.v.cpu().numpy()[0], g[key + f"v{horizon}"]) < tol * 10, key
         assert int(bk.status[0]) == 0

@@ -44,6 +44,10 @@ def test_classic_trajectories(horizon, tol):
         assert sim.n_sub_for(0.01) == int(g[key + "n_sub"])
         for _ in range(horizon):
             sim.step(0.01)
+        # tolerance "before chaotic divergence": the golden file records how far the reference drifts from
+        # itself under an equivalent-arithmetic force routine (sens*); systems with a close encounter
+        # amplify last-bit differences by many orders of magnitude
+        tol = max(tol, 30.0 * float(g[key + f"sens{horizon}"]))
         assert relerr(sim.q, g[key + f"q{horizon}"]) < tol, key
         assert relerr(sim.v, g[key + f"v{horizon}"]) < tol * 10, key
         if horizon == 1000:
