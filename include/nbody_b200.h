@@ -109,15 +109,20 @@ int nb_ensemble_prepare_f64(const double* m, const double* q, double* v, const d
  *      step_metrics every sample_interval steps (0 = never; stability_analyzer.py:115-127), then n_megno
  *      further steps with the tangent map (evolution_features.py:34-66; raw_dr/raw_dv are the two
  *      randn(N,2) draws per system).  perm[B] (optional) maps thread -> system so that callers can sort
- *      by n_sub.  ham_soft additionally takes eps_pi[B][2] (epsilon, pi; in/out) and hs_params. */
+ *      by n_sub; n_heavy (optional, device int32 = workspace[64] of nb_sort_by_nsub) says how many leading
+ *      entries of perm have n_sub > 4: those run on the latency-optimised lane-per-body mapping.
+ *      q, v are advanced in place when NB_RUN_WRITE_STATE, NB_RUN_ENERGY or n_megno > 0 is requested.
+ *      ham_soft additionally takes eps_pi[B][2] (epsilon, pi; in/out) and hs_params. */
 int nb_ensemble_run_f64(const double* m, double* q, double* v, const double* eps, double G, int B, int N,
                         int mode, unsigned flags, double dt, int n_steps, int sample_interval, int n_megno,
-                        const int32_t* n_sub, const int32_t* perm, const double* raw_dr, const double* raw_dv,
+                        const int32_t* n_sub, const int32_t* perm, const int32_t* n_heavy,
+                        const double* raw_dr, const double* raw_dv,
                         double* eps_pi, const double* hs_params,
                         double* dyn_features, int32_t* status, void* stream);
 
-/* counting sort of systems by n_sub (descending) -> perm[B]; workspace: 64 int32 on the device */
-int nb_sort_by_nsub(const int32_t* n_sub, int B, int32_t* perm, int32_t* workspace64, void* stream);
+/* counting sort of systems by n_sub (descending) -> perm[B]; workspace: 128 int32 on the device;
+ * on return workspace[64] = number of systems with n_sub > 4 (the "heavy" head of perm) */
+int nb_sort_by_nsub(const int32_t* n_sub, int B, int32_t* perm, int32_t* workspace, void* stream);
 
 /* ---- the same path end to end with HOST buffers (BatchStabilityAnalyzer.analyze_batch,
  *      batch_stability_analyzer.py:62-80): prepare(flags) -> sort -> run -> features.

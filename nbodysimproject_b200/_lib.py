@@ -71,7 +71,7 @@ def load():
     lib.nb_pair_batched_f64.argtypes = [p, p, p, d, i, i, p, p, p, p]
     lib.nb_variational_batched_f64.argtypes = [p, p, p, p, d, i, i, p, p]
     lib.nb_ensemble_prepare_f64.argtypes = [p, p, p, p, d, i, i, i, u, d, d, d, i, p, p, p, p]
-    lib.nb_ensemble_run_f64.argtypes = [p, p, p, p, d, i, i, i, u, d, i, i, i, p, p, p, p, p, p, p, p, p]
+    lib.nb_ensemble_run_f64.argtypes = [p, p, p, p, d, i, i, i, u, d, i, i, i, p, p, p, p, p, p, p, p, p, p]
     lib.nb_sort_by_nsub.argtypes = [p, i, p, p, p]
     lib.nb_ensemble_analyze_host.argtypes = [p, p, p, p, d, i, i, i, u, d, d, d, i, i, i, p, p, p, p, p, p, i]
     lib.nb_ensemble_analyze_host_async.argtypes = lib.nb_ensemble_analyze_host.argtypes + [i]

@@ -18,6 +18,8 @@ struct RunArgs {
   int n_megno;
   const int32_t* n_sub;
   const int32_t* perm;
+  const int32_t* n_heavy;   // device int: the first *n_heavy entries of perm go to the lane-per-body mapping
+  int group_blocks;         // CTAs [0, group_blocks) of the main/megno kernels run that mapping
   const double* raw_dr;
   const double* raw_dv;
   double* dyn;

@@ -222,8 +222,8 @@ int nb_ensemble_prepare_f64(const double* m, const double* q, double* v, const d
 
 int nb_ensemble_run_f64(const double* m, double* q, double* v, const double* eps, double G, int B, int N, int mode,
                         unsigned flags, double dt, int n_steps, int sample_interval, int n_megno, const int32_t* n_sub,
-                        const int32_t* perm, const double* raw_dr, const double* raw_dv, double* eps_pi,
-                        const double* hs_params, double* dyn_features, int32_t* status, void* stream) {
+                        const int32_t* perm, const int32_t* n_heavy, const double* raw_dr, const double* raw_dv,
+                        double* eps_pi, const double* hs_params, double* dyn_features, int32_t* status, void* stream) {
   if (!m || !q || !v || B < 0 || N < NB_MIN_N || N > NB_MAX_N || n_steps < 0 || n_megno < 0) { set_error("nb_ensemble_run_f64: bad arguments"); return NB_ERR_ARG; }
   if (n_megno > 0 && (!raw_dr || !raw_dv)) { set_error("nb_ensemble_run_f64: n_megno > 0 needs raw_dr/raw_dv"); return NB_ERR_ARG; }
   if (B == 0) return NB_OK;
@@ -233,14 +233,14 @@ int nb_ensemble_run_f64(const double* m, double* q, double* v, const double* eps
                        eps_pi, hs_params, dyn_features, status, (cudaStream_t)stream);
   }
   if (!eps) { set_error("nb_ensemble_run_f64: eps is required"); return NB_ERR_ARG; }
-  RunArgs a{m, q, v, eps, G, B, flags, dt, n_steps, sample_interval, n_megno, n_sub, perm, raw_dr, raw_dv, dyn_features, status};
+  RunArgs a{m, q, v, eps, G, B, flags, dt, n_steps, sample_interval, n_megno, n_sub, perm, perm ? n_heavy : nullptr, 0, raw_dr, raw_dv, dyn_features, status};
   return ensemble_run_classic(a, N, mode, (cudaStream_t)stream);
 }
 
-int nb_sort_by_nsub(const int32_t* n_sub, int B, int32_t* perm, int32_t* workspace64, void* stream) {
-  if (!n_sub || !perm || !workspace64 || B < 0) { set_error("nb_sort_by_nsub: bad arguments"); return NB_ERR_ARG; }
+int nb_sort_by_nsub(const int32_t* n_sub, int B, int32_t* perm, int32_t* workspace, void* stream) {
+  if (!n_sub || !perm || !workspace || B < 0) { set_error("nb_sort_by_nsub: bad arguments"); return NB_ERR_ARG; }
   if (B == 0) return NB_OK;
-  return sort_by_nsub(n_sub, B, perm, workspace64, (cudaStream_t)stream);
+  return sort_by_nsub(n_sub, B, perm, workspace, (cudaStream_t)stream);
 }
 
 int nb_ensemble_analyze_host_async(const double* m, const double* q, double* v, const double* eps, double G, int B, int N,
@@ -257,7 +257,7 @@ int nb_ensemble_analyze_host_async(const double* m, const double* q, double* v, 
   const size_t sz_m = align256(bn * 8), sz_q = align256(bn * 16), sz_b = align256((size_t)B * 8);
   const size_t sz_dyn = align256((size_t)B * NB_N_DYN * 8), sz_stat = align256((size_t)B * NB_N_STATIC * 8);
   const size_t sz_i = align256((size_t)B * 4);
-  const size_t total = sz_m + 4 * sz_q + sz_b + sz_dyn + sz_stat + 3 * sz_i + 256;
+  const size_t total = sz_m + 4 * sz_q + sz_b + sz_dyn + sz_stat + 3 * sz_i + 512;
   int rc = ws_reserve(slot, device, total);
   if (rc != NB_OK) return rc;
   cudaStream_t st = g_ws[slot].stream;
@@ -292,7 +292,7 @@ int nb_ensemble_analyze_host_async(const double* m, const double* q, double* v, 
   rc = sort_by_nsub(d_nsub, B, d_perm, d_bins, st);
   if (rc != NB_OK) return rc;
   const int interval = n_steps / 100 > 1 ? n_steps / 100 : 1;
-  RunArgs ra{d_m, d_q, d_v, d_eps, G, B, NB_RUN_ENERGY, dt, n_steps, interval, n_megno, d_nsub, d_perm, d_dr, d_dv, d_dyn, d_status};
+  RunArgs ra{d_m, d_q, d_v, d_eps, G, B, NB_RUN_ENERGY, dt, n_steps, interval, n_megno, d_nsub, d_perm, d_bins + 64, 0, d_dr, d_dv, d_dyn, d_status};
   rc = ensemble_run_classic(ra, N, mode, st);
   if (rc != NB_OK) return rc;
   NB_CUDA_CHECK(cudaMemcpyAsync(dyn_features, d_dyn, (size_t)B * NB_N_DYN * 8, cudaMemcpyDeviceToHost, st));

@@ -332,7 +332,10 @@ __global__ void sort_hist_kernel(const int32_t* __restrict__ n_sub, int B, int32
 __global__ void sort_scan_kernel(int32_t* bins) {  // descending: bin 63 first
   if (threadIdx.x == 0) {
     int run = 0;
-    for (int b = 63; b >= 0; --b) { int c = bins[b]; bins[b] = run; run += c; }
+    for (int b = 63; b >= 0; --b) {
+      if (b == NB_HEAVY_NSUB) bins[64] = run;      // number of systems with n_sub > NB_HEAVY_NSUB
+      int c = bins[b]; bins[b] = run; run += c;
+    }
   }
 }
 __global__ void sort_scatter_kernel(const int32_t* __restrict__ n_sub, int B, int32_t* bins, int32_t* perm) {
@@ -396,7 +399,7 @@ int variational_batched(const double* q, const double* m, const double* s2, cons
 }
 
 int sort_by_nsub(const int32_t* n_sub, int B, int32_t* perm, int32_t* ws, cudaStream_t st) {
-  NB_CUDA_CHECK(cudaMemsetAsync(ws, 0, 64 * sizeof(int32_t), st));
+  NB_CUDA_CHECK(cudaMemsetAsync(ws, 0, 65 * sizeof(int32_t), st));
   const int threads = 256;
   const int blocks = min((B + threads - 1) / threads, 148 * 8);
   sort_hist_kernel<<<blocks, threads, 0, st>>>(n_sub, B, ws);

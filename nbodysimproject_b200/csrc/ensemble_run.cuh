@@ -18,6 +18,7 @@
 #include "pair_small.cuh"
 #include "kepler.cuh"
 #include "args.cuh"
+#include "ensemble_group.cuh"
 
 namespace nb {
 
@@ -233,9 +234,14 @@ __device__ __forceinline__ int store_state(const RunArgs& a, int sys, const SysS
 // ---------------------------------------------------------------------------------------------
 template <int N, int MODE, bool GUARD, bool EXACT>
 __global__ void __launch_bounds__(128) ensemble_main_kernel(RunArgs a, int write_state) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= a.B) return;
-  const int sys = a.perm ? a.perm[t] : t;
+  if (MODE != NB_MODE_WHFAST && (int)blockIdx.x < a.group_blocks) {   // lane-per-body mapping for the n_sub-heavy head
+    group_body<N, MODE == NB_MODE_WHFAST ? NB_MODE_VERLET : MODE, GUARD>(a, 0, write_state);
+    return;
+  }
+  const int nh = (a.group_blocks > 0) ? min(*a.n_heavy, a.B) : 0;
+  const int t = ((int)blockIdx.x - a.group_blocks) * blockDim.x + threadIdx.x;
+  if (t >= a.B - nh) return;
+  const int sys = a.perm ? a.perm[t + nh] : t;
   SysState<N> s;
   double m[N];
   load_state<N>(a, sys, s, m);
@@ -283,7 +289,7 @@ __global__ void __launch_bounds__(128) ensemble_main_kernel(RunArgs a, int write
     }
   }
   int st = store_state<N>(a, sys, s, write_state != 0);
-  if (MODE == NB_MODE_WHFAST && kep_worst >= 64) st |= NB_STATUS_KEPLER_NOCONV;
+  if (MODE == NB_MODE_WHFAST && kep_worst > 64) st |= NB_STATUS_KEPLER_NOCONV;
   if (a.status) a.status[sys] = st;
   if (a.dyn) {
     double* f = a.dyn + (size_t)sys * NB_N_DYN;
@@ -309,9 +315,14 @@ __global__ void __launch_bounds__(128) ensemble_main_kernel(RunArgs a, int write
 // ---------------------------------------------------------------------------------------------
 template <int N, int MODE, bool GUARD, bool EXACT>
 __global__ void __launch_bounds__(128) ensemble_megno_kernel(RunArgs a, int write_state) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= a.B) return;
-  const int sys = a.perm ? a.perm[t] : t;
+  if (MODE != NB_MODE_WHFAST && (int)blockIdx.x < a.group_blocks) {   // lane-per-body mapping for the n_sub-heavy head
+    group_body<N, MODE == NB_MODE_WHFAST ? NB_MODE_VERLET : MODE, GUARD>(a, 1, write_state);
+    return;
+  }
+  const int nh = (a.group_blocks > 0) ? min(*a.n_heavy, a.B) : 0;
+  const int t = ((int)blockIdx.x - a.group_blocks) * blockDim.x + threadIdx.x;
+  if (t >= a.B - nh) return;
+  const int sys = a.perm ? a.perm[t + nh] : t;
   SysState<N> s;
   double m[N];
   load_state<N>(a, sys, s, m);
@@ -378,7 +389,7 @@ __global__ void __launch_bounds__(128) ensemble_megno_kernel(RunArgs a, int writ
   const double megno = 2.0 * accum / tt;
   const double lyap = (megno == 0.0) ? __longlong_as_double(0x7ff0000000000000LL) : tt / fabs(megno);
   int st = store_state<N>(a, sys, s, write_state != 0);
-  if (MODE == NB_MODE_WHFAST && kep_worst >= 64) st |= NB_STATUS_KEPLER_NOCONV;
+  if (MODE == NB_MODE_WHFAST && kep_worst > 64) st |= NB_STATUS_KEPLER_NOCONV;
   if (a.status) a.status[sys] |= st;
   if (a.dyn) {
     double* f = a.dyn + (size_t)sys * NB_N_DYN;
@@ -389,9 +400,11 @@ __global__ void __launch_bounds__(128) ensemble_megno_kernel(RunArgs a, int writ
 }
 
 template <int N, int MODE>
-static int launch_run_mode(const RunArgs& a, int phase, int write_state, cudaStream_t st) {
+static int launch_run_mode(const RunArgs& a_in, int phase, int write_state, cudaStream_t st) {
+  RunArgs a = a_in;
   const int threads = 128;
-  const int blocks = (a.B + threads - 1) / threads;
+  a.group_blocks = (MODE != NB_MODE_WHFAST && a.n_heavy && a.perm) ? group_blocks_for<N>(a.B) : 0;
+  const int blocks = a.group_blocks + (a.B + threads - 1) / threads;
   const bool exact = MODE == NB_MODE_WHFAST && (a.flags & NB_RUN_KEPLER_EXACT) != 0;
   if (phase == 0) {
     if (exact) ensemble_main_kernel<N, MODE, true, MODE == NB_MODE_WHFAST><<<blocks, threads, 0, st>>>(a, write_state);

@@ -107,7 +107,7 @@ class DeviceBucket:
         self.perm = None
         self.static = None
         self.status = torch.zeros((self.B,), dtype=torch.int32, device=self.device)
-        self._bins = torch.zeros((64,), dtype=torch.int32, device=self.device)
+        self._bins = torch.zeros((128,), dtype=torch.int32, device=self.device)
 
     def prepare(self, flags: int, kick_dt: float, sched_dt: float, dt: float, split_n_max: int = 50,
                 want_static: bool = False):
@@ -145,7 +145,7 @@ class DeviceBucket:
             L.check(L.load().nb_ensemble_run_f64(
                 L.ptr(self.m), L.ptr(self.q), L.ptr(self.v), L.ptr(self.eps), self.G, self.B, self.N, self.mode,
                 int(flags), float(dt), int(n_steps), int(sample_interval), int(n_megno), L.ptr(self.n_sub),
-                L.ptr(self.perm), L.ptr(rdr), L.ptr(rdv), L.ptr(eps_pi), L.ptr(hs_params), L.ptr(dyn),
+                L.ptr(self.perm), L.ptr(self._bins[64:]) if self.perm is not None else None, L.ptr(rdr), L.ptr(rdv), L.ptr(eps_pi), L.ptr(hs_params), L.ptr(dyn),
                 L.ptr(self.status), L.stream_ptr()), "nb_ensemble_run_f64")
         return dyn
 

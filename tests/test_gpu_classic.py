@@ -211,3 +211,47 @@ def test_momentum_conservation_and_energy_order(E):
             assert abs(d["_L1"] - d["_L0"]) <= 1e-13 * abs(d["_L0"])
         slope = math.log(errs[0] / errs[2]) / math.log(4.0)
         assert abs(slope - order) < 0.35, (mode, slope, errs)
+
+
+def test_heavy_substep_mapping_matches_thread_mapping(E, O):
+    """Systems with n_sub > 4 run on the lane-per-body mapping (ensemble_group.cuh) when a sort permutation is
+    given; without one everything runs thread-per-system.  Same arithmetic per body up to summation order."""
+    import nbodysimproject_b200._lib as L
+    rng = np.random.RandomState(17)
+    for N, mode in ((3, "verlet"), (4, "yoshida4"), (5, "yoshida4"), (7, "verlet"), (8, "yoshida4")):
+        B = 70
+        m = rng.uniform(0.5, 5.0, (B, N))
+        q = rng.randn(B, N, 2) * 1.5
+        # make bodies 0/1 a tight pair so that h_sub_ref is small -> n_sub between 5 and 50
+        sep = 10 ** rng.uniform(-2.2, -1.2, B)
+        q[:, 1] = q[:, 0] + np.stack([sep, np.zeros(B)], 1)
+        v = rng.randn(B, N, 2) * 0.3
+        rr, rv = rng.randn(B, N, 2), rng.randn(B, N, 2)
+        res = {}
+        for use_sort in (False, True):
+            bk = E.DeviceBucket(m, q, v, 0.02, 1.0, mode)
+            bk.prepare(L.PREP_REMOVE_COM | L.PREP_CTOR_KICK, 0.01, 0.01, 0.01)
+            if use_sort:
+                bk.sort()
+            dyn = bk.run(0.01, 40, 2, 10, rr, rv, flags=L.RUN_ENERGY | L.RUN_WRITE_STATE)
+            res[use_sort] = (bk.q.cpu().numpy(), bk.v.cpu().numpy(), dyn.cpu().numpy(), bk.n_sub.cpu().numpy(),
+                             bk.status.cpu().numpy())
+        nsub = res[True][3]
+        assert (nsub > 4).sum() > 10 and (nsub <= 4).sum() >= 0
+        assert np.all(res[True][4] == 0)
+        heavy = nsub > 4
+        # light systems: identical bits; heavy systems: agree to rounding (amplified by the close pair)
+        assert np.array_equal(res[True][0][~heavy], res[False][0][~heavy])
+        assert relerr(res[True][0][heavy], res[False][0][heavy]) < 1e-9
+        cols = [L.DYN_COLUMNS.index(c) for c in ("com_drift_mean", "ang_mom_var_mean", "MEGNO", "_E0", "_E1")]
+        assert np.allclose(res[True][2][:, cols], res[False][2][:, cols], rtol=1e-6, atol=1e-12)
+        # and against the oracle for a few heavy systems
+        for b in np.where(heavy)[0][:3]:
+            sim = O.OracleSim(m[b], q[b], v[b], softening=0.02, integrator_mode=mode)
+            assert sim.n_sub_for(0.01) == nsub[b]
+            for _ in range(40):
+                sim.step(0.01)
+            c = sim   # MEGNO continues on the same object in the analysis; compare the state after 40 + 10 steps
+            Y, lyap, _, _ = O.compute_megno(c, 10, 0.01, rr[b], rv[b])
+            assert relerr(res[True][0][b], c.q) < 1e-8
+            assert abs(res[True][2][b, L.DYN_COLUMNS.index("MEGNO")] - Y) < 1e-6 * abs(Y)
