@@ -32,8 +32,8 @@ __device__ __forceinline__ void group_accel(const GroupCtx<N>& c, int b, double 
   if (TANGENT) { dax = 0.0; day = 0.0; }
 #pragma unroll
   for (int j = 0; j < N; ++j) {
-    const double xj = __shfl_sync(c.mask, x, c.base + j);
-    const double yj = __shfl_sync(c.mask, y, c.base + j);
+    const double xj = __shfl_sync(0xffffffffu, x, c.base + j);
+    const double yj = __shfl_sync(0xffffffffu, y, c.base + j);
     const double dx = x - xj, dy = y - yj;
     const double r2 = fma(dx, dx, fma(dy, dy, c.eps2));
     const double w = rsqrt_f64<GUARD>(r2);
@@ -43,8 +43,8 @@ __device__ __forceinline__ void group_accel(const GroupCtx<N>& c, int b, double 
     ax = fma(-cj, dx, ax);
     ay = fma(-cj, dy, ay);
     if (TANGENT) {
-      const double ex = __shfl_sync(c.mask, drx, c.base + j) - drx;   // d = dr_j - dr_i ; D = q_j - q_i = -(dx,dy)
-      const double ey = __shfl_sync(c.mask, dry, c.base + j) - dry;
+      const double ex = __shfl_sync(0xffffffffu, drx, c.base + j) - drx;   // d = dr_j - dr_i ; D = q_j - q_i = -(dx,dy)
+      const double ey = __shfl_sync(0xffffffffu, dry, c.base + j) - dry;
       const double dot = -fma(dx, ex, dy * ey);
       const double c5 = 3.0 * dot * w2 * w3;
       dax = fma(c.gm[j], fma(ex, w3, c5 * dx), dax);
@@ -57,7 +57,7 @@ template <int N>
 __device__ __forceinline__ double group_sum(const GroupCtx<N>& c, double v) {
   double s = 0.0;
 #pragma unroll
-  for (int j = 0; j < N; ++j) s += __shfl_sync(c.mask, v, c.base + j);
+  for (int j = 0; j < N; ++j) s += __shfl_sync(0xffffffffu, v, c.base + j);
   return s;
 }
 
@@ -98,13 +98,20 @@ __device__ __forceinline__ void group_body(const RunArgs& a, int phase, int writ
   constexpr int G = 32 / N;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int g = lane / N, b = lane - g * N;
   const int n_heavy = min(*a.n_heavy, a.B);
-  const int slot = warp * G + g;
-  if (g >= G || slot >= n_heavy) return;
+  if (warp * G >= n_heavy) return;                      // warp-uniform exit
+  // The warp stays fully converged (full-mask shuffles compile to bare SHFL; partial masks cost a WARPSYNC
+  // per shuffle and serialise the dependency chain): spare lanes and empty slots shadow a live system
+  // and simply never write.
+  int g = lane / N;
+  int b = lane - g * N;
+  bool live = g < G;
+  if (!live) { g = G - 1; b = 0; }
+  int slot = warp * G + g;
+  if (slot >= n_heavy) { slot = n_heavy - 1; live = false; }
   GroupCtx<N> c;
-  c.mask = ((1u << N) - 1u) << (g * N);
-  c.base = g * N;
+  c.mask = 0xffffffffu;
+  c.base = (slot == warp * G + g) ? g * N : ((n_heavy - 1) - warp * G) * N;   // lanes that hold this slot's bodies
   const int sys = a.perm[slot];
   const double G_ = a.G;
 #pragma unroll
@@ -115,6 +122,7 @@ __device__ __forceinline__ void group_body(const RunArgs& a, int phase, int writ
   const double eps = a.eps[sys];
   c.eps2 = eps * eps;
   const int n_sub = max(1, a.n_sub[sys]);
+  const int n_sub_warp = __reduce_max_sync(0xffffffffu, n_sub);   // sorted by n_sub: nearly uniform per warp
   const double h = a.dt / (double)n_sub;
   double ax, ay, d1 = 0.0, d2 = 0.0;
   group_accel<N, false, GUARD>(c, b, x, y, ax, ay, 0.0, 0.0, d1, d2);
@@ -129,8 +137,11 @@ __device__ __forceinline__ void group_body(const RunArgs& a, int phase, int writ
     const int interval = a.sample_interval;
     for (int step = 0; step < a.n_steps; ++step) {
 #pragma unroll 1
-      for (int k = 0; k < n_sub; ++k)
-        group_substep<N, MODE, false, GUARD>(c, b, h, x, y, vx, vy, ax, ay, 0.0, 0.0, d1, d2);
+      for (int k = 0; k < n_sub_warp; ++k) {
+        double xs = x, ys = y, us = vx, ws = vy, as = ax, bs = ay;
+        group_substep<N, MODE, false, GUARD>(c, b, h, xs, ys, us, ws, as, bs, 0.0, 0.0, d1, d2);
+        if (k < n_sub) { x = xs; y = ys; vx = us; vy = ws; ax = as; ay = bs; }
+      }
       if (interval > 0 && step == next_sample) {
         next_sample += interval;
         const double Li = mb * (x * vy - y * vx);
@@ -149,7 +160,7 @@ __device__ __forceinline__ void group_body(const RunArgs& a, int phase, int writ
         ++n_samp;
       }
     }
-    if (f && b == 0) {
+    if (f && b == 0 && live) {
       const double inv = n_samp > 0 ? 1.0 / (double)n_samp : nan;
       f[NB_F_COM_MEAN] = n_samp > 0 ? com_sum * inv : nan;
       f[NB_F_COM_MAX] = n_samp > 0 ? com_max : nan;
@@ -181,8 +192,11 @@ __device__ __forceinline__ void group_body(const RunArgs& a, int phase, int writ
     const double dt = a.dt;
     for (int step = 0; step < a.n_megno; ++step) {
 #pragma unroll 1
-      for (int k = 0; k < n_sub - 1; ++k)
-        group_substep<N, MODE, false, GUARD>(c, b, h, x, y, vx, vy, ax, ay, 0.0, 0.0, d1, d2);
+      for (int k = 0; k < n_sub_warp - 1; ++k) {
+        double xs = x, ys = y, us = vx, ws = vy, as = ax, bs = ay;
+        group_substep<N, MODE, false, GUARD>(c, b, h, xs, ys, us, ws, as, bs, 0.0, 0.0, d1, d2);
+        if (k < n_sub - 1) { x = xs; y = ys; vx = us; vy = ws; ax = as; ay = bs; }
+      }
       drx = fma(dvx, dt, drx); dry = fma(dvy, dt, dry);
       group_substep<N, MODE, true, GUARD>(c, b, h, x, y, vx, vy, ax, ay, drx, dry, dax, day);
       dvx = fma(dax, dt, dvx); dvy = fma(day, dt, dvy);
@@ -192,7 +206,7 @@ __device__ __forceinline__ void group_body(const RunArgs& a, int phase, int writ
       const double nv = sqrt(group_sum<N>(c, dvx * dvx + dvy * dvy));
       accum += (nv / nr) * tt * dt;
     }
-    if (f && b == 0) {
+    if (f && b == 0 && live) {
       const double megno = 2.0 * accum / tt;
       f[NB_F_MEGNO] = megno;
       f[NB_F_LYAP_TIME] = (megno == 0.0) ? __longlong_as_double(0x7ff0000000000000LL) : tt / fabs(megno);
@@ -200,14 +214,15 @@ __device__ __forceinline__ void group_body(const RunArgs& a, int phase, int writ
     }
   }
   const bool fin = is_finite(x) && is_finite(y) && is_finite(vx) && is_finite(vy);
-  const unsigned bad = __ballot_sync(c.mask, !fin) & c.mask;
-  if (write_state) {
+  const unsigned grp = ((1u << N) - 1u) << (c.base);
+  const unsigned bad = __ballot_sync(0xffffffffu, !fin) & grp;
+  if (write_state && live) {
     a.q[((size_t)sys * N + b) * 2 + 0] = x;
     a.q[((size_t)sys * N + b) * 2 + 1] = y;
     a.v[((size_t)sys * N + b) * 2 + 0] = vx;
     a.v[((size_t)sys * N + b) * 2 + 1] = vy;
   }
-  if (a.status && b == 0) {
+  if (a.status && b == 0 && live) {
     const int st = bad ? NB_STATUS_NONFINITE : 0;
     if (phase == 0) a.status[sys] = st; else a.status[sys] |= st;
   }

@@ -181,7 +181,16 @@ __device__ __forceinline__ int substep(SysState<N>& s, const double* m, double G
     kick<N>(s, 0.5 * ha);
   } else {  // NB_MODE_WHFAST: Kepler(h/2) . full-force kick(h) . Kepler(h/2)   whfast_scheme.py:71-93
     kep = kepler_drift<N, EXACT>(s, m, G, 0.5 * h);
-    pair_pass<N, false, GUARD>(s, nullptr, nullptr, nullptr, nullptr);
+    if (EXACT) {
+      // physically correct Wisdom-Holman: kick with the INTERACTION acceleration only (the star-planet Kepler
+      // terms are already in the drift); the reference kicks with the full force (whfast_scheme.py:85-88)
+      double ix[N], iy[N];
+      wh_interaction_accel<N>(s, m, G, ix, iy);
+#pragma unroll
+      for (int i = 0; i < N; ++i) { s.ax[i] = ix[i]; s.ay[i] = iy[i]; }
+    } else {
+      pair_pass<N, false, GUARD>(s, nullptr, nullptr, nullptr, nullptr);
+    }
     kick<N>(s, h);
     kep = max(kep, kepler_drift<N, EXACT>(s, m, G, 0.5 * h));
     if (TANGENT) pair_pass<N, true, GUARD>(s, drx, dry, dax, day);
