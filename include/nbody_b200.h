@@ -146,7 +146,7 @@ int nb_host_sync(int slot);
 /* ---- large-N direct sum (new capability, same formula as forces.py:63-75 / 77-112 / potential.py:23-64),
  *      fp32 pair arithmetic, fp64 accumulation across j-tiles.  xym[n_total] = (x, y, m, 0) packed float4.
  *      Rank-local i-range [i0, i0+ni).  acc[ni] float2; sums[2] += {sum_{i in range, j} m_i m_j/rho, sum m_i m_j/rho^3}
- *      (ordered pairs; halve for i<j). */
+ *      (ordered pairs i != j; halve for i<j). */
 int nb_largeN_accel_f32(const float* xym, int n_total, int i0, int ni, float eps, float G, float* acc,
                         double* sums, void* stream);
 /* kick/drift on the rank-local block and re-pack into the gather buffer (fused pack for the all-gather) */

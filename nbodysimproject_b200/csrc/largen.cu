@@ -23,7 +23,7 @@ struct LargeNArgs {
   float eps2;
   float G;
   double* acc64;     // [ni][2] fp64 accumulators (zeroed by the caller wrapper)
-  double* sums;      // [2]: sum m_i m_j / rho, sum m_i m_j / rho^3 over ordered pairs incl. i==j self terms
+  double* sums;      // [2]: sum m_i m_j / rho, sum m_i m_j / rho^3 over ordered pairs i != j
   int n_ichunks;
   int n_jchunks;
   int jchunk;        // j-particles per chunk (multiple of LN_TILE)
@@ -120,21 +120,47 @@ __global__ void __launch_bounds__(LN_TPB) largeN_accel_kernel(LargeNArgs a) {
 #pragma unroll
       for (int k = 0; k < IPT; ++k) { ax[k] = 0.f; ay[k] = 0.f; us[k] = 0.f; s3[k] = 0.f; }
       const float4* tp = tile[buf];
+      const int jt0 = j_begin + t * LN_TILE;
+      // the i == j self pair contributes exactly 0 to the acceleration (dx = dy = 0) but m_i^2/eps to the scalar
+      // sums, where it would swamp the physical sum; only the tile(s) that overlap this CTA's i-range check for it
+      const int gi_lo = a.i0 + ic * (LN_TPB * IPT);
+      const bool diag = SCALARS && (jt0 < gi_lo + LN_TPB * IPT) && (jt0 + cnt > gi_lo);
+      if (!diag) {
 #pragma unroll 8
-      for (int j = 0; j < cnt; ++j) {
-        const float4 pj = tp[j];
+        for (int j = 0; j < cnt; ++j) {
+          const float4 pj = tp[j];
 #pragma unroll
-        for (int k = 0; k < IPT; ++k) {
-          const float dx = pj.x - xi[k];
-          const float dy = pj.y - yi[k];
-          const float r2 = fmaf(dx, dx, fmaf(dy, dy, a.eps2));
-          float w = rsqrtf(r2);
-          if (EPS_ZERO) w = (r2 > 0.f) ? w : 0.f;
-          const float mw = pj.z * w;
-          const float c = mw * (w * w);
-          ax[k] = fmaf(c, dx, ax[k]);
-          ay[k] = fmaf(c, dy, ay[k]);
-          if (SCALARS) { us[k] += mw; s3[k] += c; }
+          for (int k = 0; k < IPT; ++k) {
+            const float dx = pj.x - xi[k];
+            const float dy = pj.y - yi[k];
+            const float r2 = fmaf(dx, dx, fmaf(dy, dy, a.eps2));
+            float w = rsqrtf(r2);
+            if (EPS_ZERO) w = (r2 > 0.f) ? w : 0.f;
+            const float mw = pj.z * w;
+            const float c = mw * (w * w);
+            ax[k] = fmaf(c, dx, ax[k]);
+            ay[k] = fmaf(c, dy, ay[k]);
+            if (SCALARS) { us[k] += mw; s3[k] += c; }
+          }
+        }
+      } else {
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+          const float4 pj = tp[j];
+#pragma unroll
+          for (int k = 0; k < IPT; ++k) {
+            const float dx = pj.x - xi[k];
+            const float dy = pj.y - yi[k];
+            const float r2 = fmaf(dx, dx, fmaf(dy, dy, a.eps2));
+            float w = rsqrtf(r2);
+            if (EPS_ZERO) w = (r2 > 0.f) ? w : 0.f;
+            if (jt0 + j == a.i0 + ii[k]) w = 0.f;
+            const float mw = pj.z * w;
+            const float c = mw * (w * w);
+            ax[k] = fmaf(c, dx, ax[k]);
+            ay[k] = fmaf(c, dy, ay[k]);
+            us[k] += mw; s3[k] += c;
+          }
         }
       }
 #pragma unroll

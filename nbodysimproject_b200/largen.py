@@ -105,11 +105,6 @@ class LargeNSimulation:
         """U = -G sum_{i<j} m_i m_j / rho and dV/deps = G eps sum_{i<j} m_i m_j / rho^3 (all ranks)."""
         self.accelerations(with_sums=True)
         s = self.sums.clone()
-        m_loc = self.local[:, 2].double()
-        self_u = torch_sum(m_loc * m_loc) / max(self.eps, 1e-300) if self.eps > 0 else 0.0
-        self_s3 = torch_sum(m_loc * m_loc) / max(self.eps, 1e-300) ** 3 if self.eps > 0 else 0.0
-        s[0] -= self_u
-        s[1] -= self_s3
         if self.dist is not None and self.world > 1:
             self.dist.all_reduce(s, group=self.group)
         U = -self.G * 0.5 * float(s[0])

@@ -289,7 +289,33 @@ def gen_features(mb):
                 df = mb.BatchStabilityAnalyzer(n_steps=n_steps, dt=0.01, mode="full").analyze_batch(sims, show_progress=False)
         finally:
             np.random.randn = orig
+        # sensitivity: the same batch, same tangent draws, with the reference's force routine swapped for the
+        # equivalent-arithmetic one
+        import minbody.simulation as simmod
+        it = iter([d.copy() for d in draws])
+        sims2 = []
+        orig_force = simmod.gravitational_force
+        simmod.gravitational_force = _alt_force
+        np.random.randn = lambda *shape: next(it)
+        try:
+            for name in keys:
+                m, p, v, soft = S[name]
+                with quiet():
+                    sims2.append(mb.NBodySimulation(masses=m, positions=p, velocities=v, softening=soft,
+                                                    integrator_mode=mode))
+            with quiet():
+                df2 = mb.BatchStabilityAnalyzer(n_steps=n_steps, dt=0.01, mode="full").analyze_batch(sims2, show_progress=False)
+        finally:
+            np.random.randn = orig
+            simmod.gravitational_force = orig_force
         out = {"names": np.array(keys), "n_steps": n_steps, "dt": 0.01, "columns": np.array(list(df.columns))}
+        for i, name in enumerate(keys):
+            for c in df.columns:
+                a, b = df.iloc[i][c], df2.iloc[i][c]
+                if isinstance(a, (str, bool, np.bool_)):
+                    continue
+                d = abs(float(a) - float(b))
+                out[f"{name}__sens__{c}"] = d if np.isfinite(d) else 0.0
         for i, name in enumerate(keys):
             m, p, v, soft = S[name]
             out[f"{name}_m"] = m; out[f"{name}_q"] = p; out[f"{name}_v"] = v; out[f"{name}_soft"] = soft

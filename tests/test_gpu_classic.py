@@ -162,13 +162,14 @@ def test_feature_rows_vs_golden(E, mode, via):
                 assert math.isnan(got), (name, c)
             elif math.isinf(ref):
                 assert got == ref, (name, c)
-            elif c in ("energy_drift", "angular_momentum_drift"):
-                # |E1-E0|/|E0| with E ~ O(1): a 1000-step trajectory difference of 1e-9 moves it by ~1e-9*drift,
-                # rounding of E itself by ~1e-16
-                assert abs(got - ref) <= 2e-13 + 1e-5 * abs(ref), (name, c, got, ref)
             else:
-                tol = _LOOSE.get(c, 1e-8)
-                assert abs(got - ref) <= tol * max(abs(ref), 1e-12) + 1e-14, (name, c, got, ref)
+                # per-column tolerance = what the REFERENCE itself moves by under an equivalent-arithmetic force
+                # routine (chaotic amplification, recorded in the golden file as sens__<col>), floored at the
+                # rounding level of the quantity
+                sens = float(g[f"{name}__sens__{c}"]) if f"{name}__sens__{c}" in g.files else 0.0
+                floor = {"energy_drift": 2e-13, "angular_momentum_drift": 2e-13, "com_drift_mean": 1e-12,
+                         "com_drift_max": 1e-12}.get(c, 1e-9 * max(abs(ref), 1e-12) + 1e-14)
+                assert abs(got - ref) <= floor + 30.0 * sens, (name, c, got, ref, sens)
 
 
 def test_batch_order_and_sort_invariance(E):
@@ -222,14 +223,16 @@ def test_heavy_substep_mapping_matches_thread_mapping(E, O):
         B = 70
         m = rng.uniform(0.5, 5.0, (B, N))
         q = rng.randn(B, N, 2) * 1.5
-        # make bodies 0/1 a tight pair so that h_sub_ref is small -> n_sub between 5 and 50
+        # bodies 0/1 are a tight pair, so the (unsoftened) schedule asks for n_sub between 5 and 50, while the
+        # strong softening below keeps the actual dynamics smooth (a real tight binary would make the 50-step
+        # trajectory ill-conditioned and the oracle comparison meaningless)
         sep = 10 ** rng.uniform(-2.2, -1.2, B)
         q[:, 1] = q[:, 0] + np.stack([sep, np.zeros(B)], 1)
         v = rng.randn(B, N, 2) * 0.3
         rr, rv = rng.randn(B, N, 2), rng.randn(B, N, 2)
         res = {}
         for use_sort in (False, True):
-            bk = E.DeviceBucket(m, q, v, 0.02, 1.0, mode)
+            bk = E.DeviceBucket(m, q, v, 0.3, 1.0, mode)
             bk.prepare(L.PREP_REMOVE_COM | L.PREP_CTOR_KICK, 0.01, 0.01, 0.01)
             if use_sort:
                 bk.sort()
@@ -247,11 +250,11 @@ def test_heavy_substep_mapping_matches_thread_mapping(E, O):
         assert np.allclose(res[True][2][:, cols], res[False][2][:, cols], rtol=1e-6, atol=1e-12)
         # and against the oracle for a few heavy systems
         for b in np.where(heavy)[0][:3]:
-            sim = O.OracleSim(m[b], q[b], v[b], softening=0.02, integrator_mode=mode)
+            sim = O.OracleSim(m[b], q[b], v[b], softening=0.3, integrator_mode=mode)
             assert sim.n_sub_for(0.01) == nsub[b]
             for _ in range(40):
                 sim.step(0.01)
             c = sim   # MEGNO continues on the same object in the analysis; compare the state after 40 + 10 steps
             Y, lyap, _, _ = O.compute_megno(c, 10, 0.01, rr[b], rv[b])
-            assert relerr(res[True][0][b], c.q) < 1e-8
+            assert relerr(res[True][0][b], c.q) < 1e-11
             assert abs(res[True][2][b, L.DYN_COLUMNS.index("MEGNO")] - Y) < 1e-6 * abs(Y)
