@@ -105,3 +105,49 @@ def test_feature_rows(mode):
             sens = float(g[f"{name}__sens__{c}"]) if f"{name}__sens__{c}" in g.files else 0.0
             floor = {"energy_drift": 1e-13, "angular_momentum_drift": 1e-13}.get(c, 1e-9 * max(abs(ref), 1e-12) + 1e-15)
             assert abs(got - ref) <= floor + 30.0 * sens, (name, c, got, ref, sens)
+
+
+def test_hamsoft_oracle_vs_golden():
+    """ham_soft: constructor calibration, eps* + gradient, one S / V half-flow tap, trajectories and the
+    extended Hamiltonian against the live reference's outputs (oracle/make_golden_hamsoft.py)."""
+    from oracle.hamsoft_oracle import HamSoftOracleSim
+    g = load_golden("hamsoft.npz")
+    dt = float(g["dt"])
+    for key in g["names"]:
+        key = str(key)
+        if key.startswith("compact_s0.1"):
+            continue    # 1,500 eps* solves per step: covered by the GPU test, too slow for the CPU suite
+        mk = lambda: HamSoftOracleSim(g[key + "m"], g[key + "q_in"], g[key + "v_in"], softening=float(g[key + "soft"]))
+        sim = mk()
+        ctor = np.array([sim.eps, sim.pi, sim.eps_min, sim.eps_max, sim.alpha_run, sim.k_soft, sim.mu_soft,
+                         sim.frozen_n_sub, sim.omega_spr0])
+        assert np.allclose(ctor, g[key + "ctor"], rtol=1e-14, atol=0), key
+        es, gr = sim.eps_star_and_grad(sim.q)
+        assert es == pytest.approx(float(g[key + "eps_star0"]), rel=1e-14)
+        assert np.allclose(gr, g[key + "grad0"], rtol=1e-12, atol=1e-15)
+        assert sim.extended_hamiltonian() == pytest.approx(float(g[key + "H0"]), rel=1e-14)
+        probe = mk()
+        h = dt / probe.frozen_n_sub
+        probe.s_half(h)
+        t = probe.taps
+        tap = np.array([t["I_tau"], t["J"], t["J_applied"], t["eps_star"], t["theta"], t["kick1"], t["kick2"],
+                        probe.eps, probe.pi])
+        assert np.allclose(tap, g[key + "tap_s"], rtol=1e-12, atol=1e-18), key
+        assert relerr(probe.v, g[key + "tap_s_v"]) < 1e-14
+        probe.v_half_kick(h)
+        assert np.allclose([probe.taps["dVdeps"], probe.taps["dBdeps"], probe.pi], g[key + "tap_v"], rtol=1e-12, atol=1e-18)
+        assert relerr(probe.v, g[key + "tap_v_v"]) < 1e-14
+        done = 0
+        for mark in g[key + "marks"]:
+            mark = int(mark)
+            for _ in range(mark - done):
+                sim.step(dt)
+            done = mark
+            sens = g[key + f"sens{mark}"]
+            assert relerr(sim.q, g[key + f"q{mark}"]) < 1e-12 + 30 * sens[0], (key, mark)
+            assert relerr(sim.v, g[key + f"v{mark}"]) < 1e-11 + 300 * sens[0], (key, mark)
+            ep = g[key + f"ep{mark}"]
+            assert abs(sim.eps - ep[0]) <= (1e-12 + 30 * sens[1]) * abs(ep[0])
+            assert abs(sim.pi - ep[1]) <= (1e-11 + 30 * sens[2]) * max(abs(ep[1]), 1e-12)
+            assert sim.mu_soft == pytest.approx(ep[2], rel=1e-14)
+        assert sim.n_sub_last == int(g[key + "n_sub"])
