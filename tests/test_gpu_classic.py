@@ -169,7 +169,7 @@ def test_feature_rows_vs_golden(E, mode, via):
                 sens = float(g[f"{name}__sens__{c}"]) if f"{name}__sens__{c}" in g.files else 0.0
                 floor = {"energy_drift": 2e-13, "angular_momentum_drift": 2e-13, "com_drift_mean": 1e-12,
                          "com_drift_max": 1e-12}.get(c, 1e-9 * max(abs(ref), 1e-12) + 1e-14)
-                assert abs(got - ref) <= floor + 30.0 * sens, (name, c, got, ref, sens)
+                assert abs(got - ref) <= floor + 100.0 * sens, (name, c, got, ref, sens)
 
 
 def test_batch_order_and_sort_invariance(E):
