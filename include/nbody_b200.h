@@ -78,7 +78,8 @@ enum {
  * one row of hs_params[B][NB_HS_NPARAM] */
 enum {
   NB_HS_K_SOFT = 0, NB_HS_MU_SOFT, NB_HS_EPS_MIN, NB_HS_EPS_MAX, NB_HS_ALPHA_RUN, NB_HS_K_WALL,
-  NB_HS_BARRIER_N, NB_HS_ETA, NB_HS_J_MAX_CAP, NB_HS_LAMBDA, NB_HS_POLICY /*0 soft, 1 reflection, 2 none*/,
+  NB_HS_BARRIER_N, NB_HS_ETA, NB_HS_J_MAX_CAP, NB_HS_LAMBDA, NB_HS_POLICY /*0 soft, 2 none (1 = reflection: not built)*/,
+  NB_HS_THETA_IMP, NB_HS_THETA_CAP, NB_HS_CHI_PI, NB_HS_OMEGA_SPR0, NB_HS_S0,
   NB_HS_NPARAM
 };
 
@@ -119,6 +120,19 @@ int nb_ensemble_run_f64(const double* m, double* q, double* v, const double* eps
                         const double* raw_dr, const double* raw_dv,
                         double* eps_pi, const double* hs_params,
                         double* dyn_features, int32_t* status, void* stream);
+
+/* ---- a11/a14 ham_soft construction-time calibration, one thread per system, in place on hs_params / eps_pi:
+ *      flags bit0: EpsilonModel.calibrate_from_initial_conditions (hamsoft_eps_model.py:645-729: alpha_run,
+ *                  eps_min, eps0) + _calibrate_mu_from_timescales (hamiltonian_softening_integrator.py:251-296);
+ *                  on entry ALPHA_RUN holds cfg.alpha, EPS_MIN/EPS_MAX the simulation.py:88-114 defaults
+ *      flags bit1: _freeze_production_schedule(dt) (:986-1221) -> n_sub[B] */
+int nb_hamsoft_setup_f64(const double* m, const double* q, double G, int B, int N, unsigned flags, double dt,
+                         double* hs_params, double* eps_pi, int32_t* n_sub, void* stream);
+
+/* ---- a14 parity tap: eps*(q), H_ext (diagnostics.py:457-549), fallback flag and grad eps* for B systems;
+ *      out[B][3+2N] = {eps*, H_ext, used_analytic_fallback, g_0x, g_0y, ...} (hamsoft_eps_model.py:94-234) */
+int nb_hamsoft_probe_f64(const double* m, const double* q, const double* v, double G, int B, int N,
+                         const double* eps_pi, const double* hs_params, double* out, void* stream);
 
 /* counting sort of systems by n_sub (descending) -> perm[B]; workspace: 128 int32 on the device;
  * on return workspace[64] = number of systems with n_sub > 4 (the "heavy" head of perm) */

@@ -37,13 +37,13 @@ STATIC_COLUMNS = [
 ]
 N_STATIC = len(STATIC_COLUMNS)
 HS_PARAMS = ["k_soft", "mu_soft", "eps_min", "eps_max", "alpha_run", "k_wall", "barrier_n", "eta",
-             "j_max_cap", "lambda", "policy"]
+             "j_max_cap", "lambda", "policy", "theta_imp", "theta_cap", "chi_pi", "omega_spr0", "s0"]
 N_HS = len(HS_PARAMS)
 
 EXPORTS = [
     "nb_last_error", "nb_version", "nb_pair_batched_f64", "nb_variational_batched_f64",
     "nb_ensemble_prepare_f64", "nb_ensemble_run_f64", "nb_sort_by_nsub", "nb_ensemble_analyze_host",
-    "nb_ensemble_analyze_host_async", "nb_host_sync",
+    "nb_ensemble_analyze_host_async", "nb_host_sync", "nb_hamsoft_setup_f64", "nb_hamsoft_probe_f64",
     "nb_largeN_accel_f32", "nb_largeN_kick_drift_f32", "nb_peak_flops",
 ]
 
@@ -76,6 +76,8 @@ def load():
     lib.nb_ensemble_analyze_host.argtypes = [p, p, p, p, d, i, i, i, u, d, d, d, i, i, i, p, p, p, p, p, p, i]
     lib.nb_ensemble_analyze_host_async.argtypes = lib.nb_ensemble_analyze_host.argtypes + [i]
     lib.nb_host_sync.argtypes = [i]
+    lib.nb_hamsoft_setup_f64.argtypes = [p, p, d, i, i, u, d, p, p, p, p]
+    lib.nb_hamsoft_probe_f64.argtypes = [p, p, p, d, i, i, p, p, p, p]
     lib.nb_largeN_accel_f32.argtypes = [p, i, i, i, f, f, p, p, p]
     lib.nb_largeN_kick_drift_f32.argtypes = [p, p, p, i, f, f, p]
     lib.nb_peak_flops.argtypes = [i, i, C.POINTER(C.c_double)]

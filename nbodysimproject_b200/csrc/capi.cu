@@ -34,6 +34,11 @@ int hamsoft_run(const double* m, double* q, double* v, double G, int B, int N, u
                 int sample_interval, int n_megno, const int32_t* n_sub, const int32_t* perm, const double* raw_dr,
                 const double* raw_dv, double* eps_pi, const double* hs, double* dyn, int32_t* status, cudaStream_t st);
 
+int hamsoft_setup(const double* m, const double* q, double G, int B, int N, unsigned flags, double dt, double* hs,
+                  double* eps_pi, int32_t* n_sub, cudaStream_t st);
+int hamsoft_probe(const double* m, const double* q, const double* v, double G, int B, int N, const double* eps_pi,
+                  const double* hs, double* out, cudaStream_t st);
+
 // ---- peak micro-benchmarks ------------------------------------------------------------------------------
 template <int WHICH>
 __global__ void __launch_bounds__(256) peak_kernel(int iters, float seed, float* out) {
@@ -235,6 +240,20 @@ int nb_ensemble_run_f64(const double* m, double* q, double* v, const double* eps
   if (!eps) { set_error("nb_ensemble_run_f64: eps is required"); return NB_ERR_ARG; }
   RunArgs a{m, q, v, eps, G, B, flags, dt, n_steps, sample_interval, n_megno, n_sub, perm, perm ? n_heavy : nullptr, 0, raw_dr, raw_dv, dyn_features, status};
   return ensemble_run_classic(a, N, mode, (cudaStream_t)stream);
+}
+
+int nb_hamsoft_setup_f64(const double* m, const double* q, double G, int B, int N, unsigned flags, double dt,
+                         double* hs_params, double* eps_pi, int32_t* n_sub, void* stream) {
+  if (!m || !q || !hs_params || !eps_pi || B < 0 || N < NB_MIN_N || N > NB_MAX_N || ((flags & 2u) && !n_sub)) { set_error("nb_hamsoft_setup_f64: bad arguments"); return NB_ERR_ARG; }
+  if (B == 0) return NB_OK;
+  return hamsoft_setup(m, q, G, B, N, flags, dt, hs_params, eps_pi, n_sub, (cudaStream_t)stream);
+}
+
+int nb_hamsoft_probe_f64(const double* m, const double* q, const double* v, double G, int B, int N,
+                         const double* eps_pi, const double* hs_params, double* out, void* stream) {
+  if (!m || !q || !v || !hs_params || !eps_pi || !out || B < 0 || N < NB_MIN_N || N > NB_MAX_N) { set_error("nb_hamsoft_probe_f64: bad arguments"); return NB_ERR_ARG; }
+  if (B == 0) return NB_OK;
+  return hamsoft_probe(m, q, v, G, B, N, eps_pi, hs_params, out, (cudaStream_t)stream);
 }
 
 int nb_sort_by_nsub(const int32_t* n_sub, int B, int32_t* perm, int32_t* workspace, void* stream) {
