@@ -157,7 +157,7 @@ class HamSoftIntegrator:
     # -- device round trips ------------------------------------------------------------------------------
     def _bucket(self):
         sim = self.sim
-        self._hs[0, P["eps_min"]] = float(sim._min_softening) if hasattr(self, "_frozen_n_sub") else self._hs[0, P["eps_min"]]
+        self._hs[0, P["eps_min"]] = float(sim._min_softening)
         self._hs[0, P["eps_max"]] = float(sim._max_softening)
         return HamSoftBucket(sim._mass[None], sim._pos[None], sim._vel[None], self._hs,
                              np.array([[sim._epsilon, sim._pi]]), sim.G, sim.device)
