@@ -111,3 +111,62 @@ def gen_hamsoft(mb, OUT):
     out["dt"] = dt
     np.savez_compressed(os.path.join(OUT, "hamsoft.npz"), **out)
     print("hamsoft:", len(names))
+    gen_hamsoft_features(mb, OUT)
+
+
+def gen_hamsoft_features(mb, OUT):
+    """BatchStabilityAnalyzer('full') rows for ham_soft sims (default integrator mode), tangent draws recorded,
+    plus the per-column sensitivity under the equivalent-arithmetic force routine."""
+    import minbody.hamsoft_stepper as stepper_mod
+    S = hamsoft_systems(mb)
+    keys = ["readme3", "compact_s1.0", "compact3", "compact6"]
+    n_steps = 40
+
+    def build():
+        sims = []
+        for k in keys:
+            m, p, v, soft, _ = S[k]
+            with quiet():
+                sims.append(mb.NBodySimulation(masses=m, positions=p, velocities=v, softening=soft))
+        return sims
+
+    draws = []
+    orig = np.random.randn
+
+    def rec(*shape):
+        a = orig(*shape)
+        draws.append(a.copy())
+        return a
+
+    np.random.seed(99)
+    np.random.randn = rec
+    try:
+        with quiet():
+            df = mb.BatchStabilityAnalyzer(n_steps=n_steps, dt=0.01, mode="full").analyze_batch(build(), show_progress=False)
+    finally:
+        np.random.randn = orig
+    it = iter([d.copy() for d in draws])
+    np.random.randn = lambda *shape: next(it)
+    of = stepper_mod._grav_force
+    stepper_mod._grav_force = _alt_force
+    try:
+        with quiet():
+            df2 = mb.BatchStabilityAnalyzer(n_steps=n_steps, dt=0.01, mode="full").analyze_batch(build(), show_progress=False)
+    finally:
+        np.random.randn = orig
+        stepper_mod._grav_force = of
+    out = {"names": np.array(keys), "n_steps": n_steps, "dt": 0.01, "columns": np.array(list(df.columns)), "seed": 99}
+    for i, k in enumerate(keys):
+        m, p, v, soft, _ = S[k]
+        out[f"{k}_m"] = m; out[f"{k}_q"] = p; out[f"{k}_v"] = v; out[f"{k}_soft"] = soft
+        out[f"{k}_raw_r"] = draws[2 * i]; out[f"{k}_raw_v"] = draws[2 * i + 1]
+        for c in df.columns:
+            val = df.iloc[i][c]
+            if isinstance(val, (str, bool, np.bool_)):
+                out[f"{k}__{c}"] = np.array(str(val))
+            else:
+                out[f"{k}__{c}"] = float(val)
+                d = abs(float(val) - float(df2.iloc[i][c]))
+                out[f"{k}__sens__{c}"] = d if np.isfinite(d) else 0.0
+    np.savez_compressed(os.path.join(OUT, "features_ham_soft.npz"), **out)
+    print("features ham_soft", df.shape)
