@@ -167,6 +167,11 @@ int nb_largeN_accel_f32(const float* xym, int n_total, int i0, int ni, float eps
 int nb_largeN_kick_drift_f32(float* xym_local, float* vel, const float* acc, int ni, float kick_h, float drift_h,
                              void* stream);
 
+/* kernel variant of nb_largeN_accel_f32 (tuning / A-B tests only; process-wide): -1 default (= 8);
+ * 0..7 scalar-fp32 kernel (bit0: TMA staging, bits1-2: 4/2/1 i-particles per thread);
+ * 8 packed f32x2 over j-pairs, 4 i per thread; 9 same with 8 i per thread, 2 CTAs/SM; 10 same with 2 i per thread */
+int nb_largeN_set_variant(int variant);
+
 /* ---- register-resident FMA micro-benchmarks used for the roofline denominators (TFLOP/s) */
 int nb_peak_flops(int which /*0 fp64 DFMA, 1 fp32 FFMA, 2 fp32x2 FFMA2*/, int device, double* tflops);
 

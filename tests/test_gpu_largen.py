@@ -6,8 +6,17 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[8, 9, 10, 1, 0], ids=["x2_ipt4", "x2_ipt8", "x2_ipt2", "v1_tma", "v1_ldg"])
+def variant(request):
+    """Every kernel variant of nb_largeN_accel_f32 (default = 8, packed f32x2) must pass the same parity checks."""
+    from nbodysimproject_b200 import _lib as L
+    L.check(L.load().nb_largeN_set_variant(request.param))
+    yield request.param
+    L.check(L.load().nb_largeN_set_variant(-1))
+
+
 @pytest.mark.parametrize("n,eps", [(1000, 1e-2), (4096, 1e-3), (3000, 0.0)])
-def test_largen_accel_vs_oracle(n, eps):
+def test_largen_accel_vs_oracle(n, eps, variant):
     from nbodysimproject_b200.largen import LargeNSimulation, make_disc
     from oracle import nbody_oracle as O
     m, q, v = make_disc(n, seed=3)
@@ -24,10 +33,10 @@ def test_largen_accel_vs_oracle(n, eps):
         assert abs(dV - O.dV_d_epsilon(q32, m32, eps, 1.0)) < 1e-4 * abs(dV)
 
 
-def test_largen_ragged_sizes_and_momentum():
+def test_largen_ragged_sizes_and_momentum(variant):
     """N not a multiple of the tile / CTA sizes; total force (sum m a) vanishes to fp32 accuracy."""
     from nbodysimproject_b200.largen import LargeNSimulation, make_disc
-    for n in (257, 1025, 5000):
+    for n in (2, 3, 257, 511, 513, 1025, 5000):
         m, q, v = make_disc(n, seed=n)
         sim = LargeNSimulation(m, q, v, softening=5e-3)
         acc = sim.accelerations().cpu().numpy().astype(np.float64)

@@ -58,14 +58,18 @@ def largen(n=1 << 18):
     acc = torch.empty((n, 2), dtype=torch.float32, device="cuda")
     sums = torch.zeros(2, dtype=torch.float64, device="cuda")
     lib = L.load()
-    for with_sums in (False, True):
-        def run():
-            L.check(lib.nb_largeN_accel_f32(L.ptr(d), n, 0, n, 1e-3, 1.0, L.ptr(acc),
-                                            L.ptr(sums) if with_sums else None, L.stream_ptr()))
-        t = ev_time(run)
-        pairs = float(n) * n
-        print(f"largeN n={n} variant={os.environ.get('NB_LARGEN_VARIANT')} sums={with_sums}: {pairs/t:.3e} pairs/s "
-              f"{pairs*14/t*1e-12:.2f} TFLOP/s(14/pair) t={t*1e3:.2f} ms", flush=True)
+    for variant in (1, 8, 9, 10):
+      L.check(lib.nb_largeN_set_variant(variant))
+      os.environ["NB_LARGEN_VARIANT"] = str(variant)
+      for with_sums in (False, True):
+          def run():
+              L.check(lib.nb_largeN_accel_f32(L.ptr(d), n, 0, n, 1e-3, 1.0, L.ptr(acc),
+                                              L.ptr(sums) if with_sums else None, L.stream_ptr()))
+          run()
+          t = ev_time(run)
+          pairs = float(n) * n
+          print(f"largeN n={n} variant={os.environ.get('NB_LARGEN_VARIANT')} sums={with_sums}: {pairs/t:.3e} pairs/s "
+                f"{pairs*14/t*1e-12:.2f} TFLOP/s(14/pair) t={t*1e3:.2f} ms", flush=True)
 
 
 if __name__ == "__main__":
