@@ -167,6 +167,24 @@ int nb_largeN_accel_f32(const float* xym, int n_total, int i0, int ni, float eps
 int nb_largeN_kick_drift_f32(float* xym_local, float* vel, const float* acc, int ni, float kick_h, float drift_h,
                              void* stream);
 
+/* ---- the O(N^2) reductions of the ham_soft epsilon flow for one large-N system (same tile pipeline as the
+ *      force kernel; fp32 pair arithmetic, fp64 accumulation; rank-local i-range [i0, i0+ni)):
+ *      NB_LN_DENSITY : out[ni][2] = sum_{j!=i} m_j e^{-r^2/h_i^2} {1, r^2}; iparam[ni] = h_i
+ *                      (EpsilonModel._solve_hi sweep, hamsoft_eps_model.py:316-400; Sigma and dSigma/dh of
+ *                      _production_grad :451-556)
+ *      NB_LN_EPSGRAD : out[ni][2] = sum_{j!=i} (q_i-q_j)[A_i m_j e^{-r^2/h_i^2} + A_j m_i e^{-r^2/h_j^2}];
+ *                      jaux[round_up(n_total,2)][2] = (-log2(e)/h_j^2, A_j) for ALL particles
+ *                      (_production_grad's scatter loop in gather form)
+ *      NB_LN_UNITGRAD: out[ni][2] = sum_{j!=i} (q_i-q_j)/r^3 (direction of softening.py:86-131 grad_eps_target)
+ *      NB_LN_TAUMIN  : out[ni]    = min_{j!=i} (r^2+eps^2)^{3/2}/(m_i+m_j)
+ *                      (tau_grav^2 G, hamiltonian_softening_integrator.py:251-296) */
+#define NB_LN_DENSITY 0
+#define NB_LN_EPSGRAD 1
+#define NB_LN_UNITGRAD 2
+#define NB_LN_TAUMIN 3
+int nb_largeN_pass_f32(int kind, const float* xym, const float* jaux, int n_total, int i0, int ni,
+                       const float* iparam, float eps, double* out, void* stream);
+
 /* kernel variant of nb_largeN_accel_f32 (tuning / A-B tests only; process-wide): -1 default (= 8);
  * 0..7 scalar-fp32 kernel (bit0: TMA staging, bits1-2: 4/2/1 i-particles per thread);
  * 8 packed f32x2 over j-pairs, 4 i per thread; 9 same with 8 i per thread, 2 CTAs/SM; 10 same with 2 i per thread */

@@ -44,7 +44,8 @@ EXPORTS = [
     "nb_last_error", "nb_version", "nb_pair_batched_f64", "nb_variational_batched_f64",
     "nb_ensemble_prepare_f64", "nb_ensemble_run_f64", "nb_sort_by_nsub", "nb_ensemble_analyze_host",
     "nb_ensemble_analyze_host_async", "nb_host_sync", "nb_hamsoft_setup_f64", "nb_hamsoft_probe_f64",
-    "nb_largeN_accel_f32", "nb_largeN_kick_drift_f32", "nb_largeN_set_variant", "nb_peak_flops",
+    "nb_largeN_accel_f32", "nb_largeN_kick_drift_f32", "nb_largeN_set_variant", "nb_largeN_pass_f32",
+    "nb_peak_flops",
 ]
 
 _lib = None
@@ -81,6 +82,7 @@ def load():
     lib.nb_largeN_accel_f32.argtypes = [p, i, i, i, f, f, p, p, p]
     lib.nb_largeN_kick_drift_f32.argtypes = [p, p, p, i, f, f, p]
     lib.nb_largeN_set_variant.argtypes = [i]
+    lib.nb_largeN_pass_f32.argtypes = [i, p, p, i, i, i, p, f, p, p]
     lib.nb_peak_flops.argtypes = [i, i, C.POINTER(C.c_double)]
     for name in EXPORTS:
         fn = getattr(lib, name)

@@ -29,6 +29,8 @@ int sort_by_nsub(const int32_t* n_sub, int B, int32_t* perm, int32_t* ws, cudaSt
 int largeN_accel(const float* xym, int n_total, int i0, int ni, float eps, float G, float* acc, double* sums,
                  cudaStream_t st);
 int largeN_set_variant(int variant);
+int largeN_pass(int kind, const float* xym, const float* jaux, int n_total, int i0, int ni, const float* iparam,
+                float eps, double* out, cudaStream_t st);
 int largeN_kick_drift(float* xym_local, float* vel, const float* acc, int ni, float kick_h, float drift_h,
                       cudaStream_t st);
 int hamsoft_run(const double* m, double* q, double* v, double G, int B, int N, unsigned flags, double dt, int n_steps,
@@ -347,6 +349,10 @@ int nb_largeN_accel_f32(const float* xym, int n_total, int i0, int ni, float eps
 }
 
 int nb_largeN_set_variant(int variant) { return largeN_set_variant(variant); }
+int nb_largeN_pass_f32(int kind, const float* xym, const float* jaux, int n_total, int i0, int ni, const float* iparam,
+                       float eps, double* out, void* stream) {
+  return largeN_pass(kind, xym, jaux, n_total, i0, ni, iparam, eps, out, (cudaStream_t)stream);
+}
 int nb_largeN_kick_drift_f32(float* xym_local, float* vel, const float* acc, int ni, float kick_h, float drift_h,
                              void* stream) {
   return largeN_kick_drift(xym_local, vel, acc, ni, kick_h, drift_h, (cudaStream_t)stream);

@@ -8,12 +8,11 @@
 // Work decomposition: unit = (i-block of TPB*IPT particles) x (j-chunk).  Units are dealt round-robin to a
 // persistent grid sized as a multiple of the SM count, partial sums go to fp64 accumulators with
 // atomicAdd, so the tail is at most one unit per CTA.
-#include "common.cuh"
+#include "largen_tile.cuh"
 
 namespace nb {
 
-constexpr int LN_TPB = 256;        // threads per CTA
-constexpr int LN_TILE = 1024;      // j-particles per shared-memory tile (16 KB of float4)
+constexpr int LN_TILE = 1024;      // v1: j-particles per shared-memory tile (16 KB of float4)
 
 struct LargeNArgs {
   const float4* xym;
@@ -26,36 +25,8 @@ struct LargeNArgs {
   double* sums;      // [2]: sum m_i m_j / rho, sum m_i m_j / rho^3 over ordered pairs i != j
   int n_ichunks;
   int n_jchunks;
-  int jchunk;        // j-particles per chunk (multiple of LN_TILE)
+  int jchunk;        // j-particles per chunk (multiple of the tile size)
 };
-
-// ---- TMA 1-D bulk copy helpers (cp.async.bulk + mbarrier) ---------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 
 template <int IPT, bool SCALARS, bool EPS_ZERO, bool USE_TMA>
 __global__ void __launch_bounds__(LN_TPB) largeN_accel_kernel(LargeNArgs a) {
@@ -209,12 +180,6 @@ __global__ void __launch_bounds__(LN_TPB) largeN_accel_kernel(LargeNArgs a) {
 // Padding entries (m = 0 at the origin) contribute exactly 0.
 // ------------------------------------------------------------------------------------------------
 constexpr int LN2_TILE = 512;      // j-particles per tile: raw 8 KB + rows 6 KB, double buffered = 28 KB
-
-__device__ __forceinline__ float rsqrt_ftz(float x) {
-  float y;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 template <int IPT, int MINB, bool SCALARS, bool EPS_ZERO>
 __global__ void __launch_bounds__(LN_TPB, MINB) largeN_accel_x2_kernel(LargeNArgs a) {

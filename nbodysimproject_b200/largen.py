@@ -128,6 +128,386 @@ class LargeNSimulation:
         return out.cpu().numpy()
 
 
+LN_DENSITY, LN_EPSGRAD, LN_UNITGRAD, LN_TAUMIN = 0, 1, 2, 3
+_LOG2E = 1.4426950408889634
+
+
+class LargeNHamSoftSimulation(LargeNSimulation):
+    """ham_soft (adaptive-epsilon Strang split) for ONE large-N system: BASELINE.json configs[4].
+
+    Same flow as the small-N path -- S(h/2) V(h/2) T(h) V(h/2) S(h/2) on (q, p, eps, pi),
+    hamsoft_stepper.py:247-308 -- with the reference's O(N^2) Python pair loops replaced by tile-streamed GPU passes
+    (`nb_largeN_pass_f32`) and, as SURVEY.md section 7 step 5 prescribes for large N, the ANALYTIC eps* gradient
+    (`_production_grad`, hamsoft_eps_model.py:451-556, sign-aligned with softening.py:86-131 exactly as the
+    reference's fallback branch does, :200-230) instead of the 4N-solve central difference.  eps, pi and every
+    scalar of the spring rotation are fp64 host values replicated on all ranks; reductions go through
+    torch.distributed.  Constructor calibration follows hamiltonian_softening_integrator.py:47-141.
+    """
+
+    def __init__(self, masses, positions, velocities=None, G: float = 1.0, softening: float = 1e-3,
+                 min_softening: float = 0.0, k_soft: float = 1.0e3, k_wall: float = 1.0e9, barrier_exponent: int = 5,
+                 theta_cap: float = 0.1, theta_imp: float = 0.5, alpha: float = 0.1, eta: float = 1.35,
+                 chi_pi: float = 0.2, j_max_cap: float = 0.02, initial_dt: float = 0.01, use_soft_barrier: bool = True,
+                 disable_barrier: bool = False, split_n_max: int = 50, device=None, group=None):
+        min_softening = max(0.0, float(min_softening))
+        softening = float(softening)
+        if softening < 0.0:
+            softening = min_softening
+        if min_softening == 0.0 and softening > 0.0:
+            min_softening = 0.1 * softening                         # simulation.py:88-114
+        s0 = max(softening, min_softening)
+        super().__init__(masses, positions, velocities, G=G, softening=s0, integrator_mode="verlet", device=device,
+                         group=group)
+        torch = self.torch
+        self.mode = "ham_soft"
+        self.s0 = s0
+        self.eps_min, self.eps_max = float(min_softening), 10.0 * s0
+        self.pi = 0.0
+        self.k_soft, self.mu_soft, self.k_wall, self.n_exp = float(k_soft), 1.0, float(k_wall), int(barrier_exponent)
+        self.theta_cap, self.theta_imp, self.alpha_cfg, self.eta = float(theta_cap), float(theta_imp), alpha, float(eta)
+        self.chi_pi, self.j_max_cap = float(chi_pi), float(j_max_cap)
+        self.soft_policy = bool(use_soft_barrier) and not bool(disable_barrier)
+        if not self.soft_policy and not disable_barrier:
+            raise L.NBodyB200Error("ham_soft barrier policy 'reflection' is not built")
+        self.split_n_max = int(split_n_max)
+        self.alpha_run = None
+        self.n_passes = 0
+        self.last_sweeps = 0
+        self.m64 = self.local[:, 2].double()
+        n_pad = (self.n + 1) // 2 * 2
+        self.jaux = torch.zeros((n_pad, 2), dtype=torch.float32, device=self.device)
+        self.out64 = torch.zeros((self.ni, 2), dtype=torch.float64, device=self.device)
+        self.acc_sums = torch.zeros((2,), dtype=torch.float64, device=self.device)
+        # ---- constructor calibration
+        self._calibrate_from_initial_conditions()
+        if not (math.isfinite(self.k_soft) and self.k_soft > 0.0):
+            em = self.eps_min if (math.isfinite(self.eps_min) and self.eps_min > 0.0) else max(self.s0 * 0.1, 1e-12)
+            self.k_soft = 8.0 * self.G * float(self._allsum(self.m64.sum())) ** 2 / em ** 3
+        self._calibrate_mu_from_timescales()
+        self._freeze_production_schedule(float(initial_dt))
+
+    # ---- collectives on scalars --------------------------------------------------------------------
+    def _allsum(self, t):
+        if self.dist is not None and self.world > 1:
+            t = t.clone()
+            self.dist.all_reduce(t, group=self.group)
+        return t
+
+    def _allmax(self, t):
+        if self.dist is not None and self.world > 1:
+            t = t.clone()
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def _allmin(self, t):
+        if self.dist is not None and self.world > 1:
+            t = t.clone()
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+        return t
+
+    def _pass(self, kind, iparam=None, eps=0.0):
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            L.check(L.load().nb_largeN_pass_f32(kind, L.ptr(self.xym), L.ptr(self.jaux), self.n, self.i0, self.ni,
+                                                L.ptr(iparam), float(eps), L.ptr(self.out64), L.stream_ptr()),
+                    "nb_largeN_pass_f32")
+        self.n_passes += 1
+        return self.out64
+
+    # ---- barrier (barrier.py:66-113) ----------------------------------------------------------------
+    def _fbar(self, eps):
+        if not self.soft_policy or not (math.isfinite(self.k_wall) and self.k_wall > 0.0):
+            return 0.0
+        e = max(2, self.n_exp) - 2
+        la, rb = max(0.0, self.eps_min - eps), max(0.0, eps - self.eps_max)
+        left = (1.0 if e == 0 else la ** e) if la > 0.0 else 0.0
+        right = (1.0 if e == 0 else rb ** e) if rb > 0.0 else 0.0
+        return self.k_wall * (left - right)
+
+    def _alpha(self):
+        if self.alpha_run is not None and self.alpha_run > 0.0:
+            return float(self.alpha_run)
+        if isinstance(self.alpha_cfg, (int, float)) and self.alpha_cfg > 0.0:
+            return float(self.alpha_cfg)
+        return 1.0
+
+    # ---- eps* model -----------------------------------------------------------------------------------
+    def solve_hi(self):
+        """hamsoft_eps_model.py:316-400: Jacobi sweeps (<= 8, tol 1e-6) from the CURRENT epsilon; one DENSITY pass each."""
+        torch = self.torch
+        lo, hi = self.eps_min, self.eps_max
+        if hi < lo:
+            lo, hi = hi, lo
+        floor = max(lo, 1.0e-12)
+        cap = max(floor, hi)
+        h0 = float(self.eps)
+        if not math.isfinite(h0) or h0 <= 0.0:
+            h0 = 1.0
+        h0 = min(max(h0, floor), cap)
+        h = torch.full((self.ni,), h0, dtype=torch.float64, device=self.device)
+        it = 0
+        while it < 8:
+            S = self._pass(LN_DENSITY, h.float().contiguous())
+            Sigma = torch.clamp_min(S[:, 0] / (math.pi * h * h), 1.0e-30)
+            hn = self.eta * torch.sqrt(self.m64 / Sigma)
+            hn = torch.where(torch.isfinite(hn) & (hn > 0.0), hn, h).clamp(floor, cap)
+            changed = float(self._allmax(((hn - h).abs() / h.clamp_min(1.0e-12)).max()))
+            h = hn
+            if changed < 1.0e-6:
+                break
+            it += 1
+        self.last_sweeps = min(it + 1, 8)
+        return h
+
+    def _softmin(self, h):
+        a = self._alpha()
+        t = -h / a
+        tmax = float(self._allmax(t.max()))
+        ex = torch_exp(self.torch, t - tmax)
+        den = float(self._allsum(ex.sum()))
+        return a, tmax, ex, den
+
+    def eps_target(self, h=None):
+        """hamsoft_eps_model.py:240-289 eps_target_production: eps* = -alpha ln sum_i exp(-h_i/alpha), clamped."""
+        if h is None:
+            h = self.solve_hi()
+        a, tmax, _, den = self._softmin(h)
+        es = self.s0 if (den <= 0.0 or not math.isfinite(den)) else -a * (tmax + math.log(den))
+        if self.soft_policy:
+            lo, hi = min(self.eps_min, self.eps_max), max(self.eps_min, self.eps_max)
+            es = min(max(es, lo), hi)
+        return float(es)
+
+    def production_grad(self, h):
+        """hamsoft_eps_model.py:451-556 in gather form + the sign alignment of :200-230 (softening.py:86-131)."""
+        torch = self.torch
+        a, tmax, ex, den = self._softmin(h)
+        if den <= 0.0 or not math.isfinite(den):
+            return torch.zeros((self.ni, 2), dtype=torch.float64, device=self.device)
+        floor = max(self.eps_min, 1.0e-12)
+        hj = h.clamp_min(max(1.0e-12, 0.1 * floor))
+        w = ex / den
+        S = self._pass(LN_DENSITY, hj.float().contiguous())
+        c = 1.0 / (math.pi * hj * hj)
+        Sigma = torch.clamp_min(c * S[:, 0], 1.0e-30)
+        Sd = c * (-2.0 / hj * S[:, 0] + 2.0 / (hj * hj * hj) * S[:, 1])
+        Om = 1.0 + hj * Sd / (2.0 * Sigma)
+        Om = torch.where(torch.isfinite(Om) & (Om != 0.0), Om, torch.ones_like(Om))
+        Pi = -hj / (2.0 * Sigma * Om)
+        s_i = -w * Pi
+        A = s_i * (-2.0 / (math.pi * hj ** 4))
+        loc = torch.stack([-_LOG2E / (hj * hj), A], 1).float()
+        self.jaux[self.i0:self.i0 + self.ni] = loc
+        if self.dist is not None and self.world > 1:
+            self.dist.all_gather_into_tensor(self.jaux[:self.n], self.jaux[self.i0:self.i0 + self.ni], group=self.group)
+        g = self._pass(LN_EPSGRAD).clone()
+        g = torch.where(torch.isfinite(g), g, torch.zeros_like(g))
+        u = self._pass(LN_UNITGRAD)                 # legacy gradient = -c_pref * u with c_pref > 0
+        dot = float(self._allsum(-(g * u).sum()))
+        if math.isfinite(dot) and dot < 0.0:
+            g = -g
+        return g
+
+    def eps_star_and_grad(self):
+        h = self.solve_hi()
+        return self.eps_target(h), self.production_grad(h)
+
+    # ---- calibration and schedule -----------------------------------------------------------------------
+    def _gather_vector(self, t):
+        if self.dist is not None and self.world > 1:
+            out = self.torch.empty((self.n,), dtype=t.dtype, device=self.device)
+            self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+            return out
+        return t
+
+    def _calibrate_from_initial_conditions(self):
+        """hamsoft_eps_model.py:645-729."""
+        a_seed = float(self.alpha_cfg) if isinstance(self.alpha_cfg, (int, float)) and self.alpha_cfg > 0 else max(self.eps, 1e-12)
+        h0 = self._gather_vector(self.solve_hi())
+        hs = self.torch.sort(h0).values                     # np.median: mean of the two middle values for even n
+        med = float(0.5 * (hs[(self.n - 1) // 2] + hs[self.n // 2]))
+        if not math.isfinite(med) or med <= 0.0:
+            med = a_seed
+        self.alpha_run = 0.3 * med
+        if not math.isfinite(self.alpha_run) or self.alpha_run <= 0.0:
+            self.alpha_run = a_seed
+        cand = 0.25 * med
+        emin0 = self.eps_min if (math.isfinite(self.eps_min) and self.eps_min >= 0.0) else 0.0
+        emax = self.eps_max if (math.isfinite(self.eps_max) and self.eps_max > 0.0) else 10.0 * self.s0
+        if not math.isfinite(cand):
+            cand = emin0
+        cand = min(cand, emax)
+        new = emin0 if emin0 >= cand else cand
+        self.eps_min = float(min(new, emax))
+        if self.eps < self.eps_min:
+            self.eps = float(self.eps_min)
+
+    def _tau_grav_soft(self, fallback):
+        """hamiltonian_softening_integrator.py:251-296: min over pairs of sqrt(rho^3 / (G (m_i + m_j)))."""
+        tau = math.inf
+        if self.n >= 2 and self.G != 0.0:
+            out = self._pass(LN_TAUMIN, eps=self.eps)
+            vmin = float(self._allmin(out.view(-1)[:self.ni].min()))
+            if vmin < 1.0e38 and vmin > 0.0:
+                tau = math.sqrt(vmin / self.G)
+        if (not math.isfinite(tau)) or tau <= 0.0:
+            tau = fallback
+        return float(tau)
+
+    def _calibrate_mu_from_timescales(self):
+        tau = self._tau_grav_soft(1.0)
+        k = self.k_soft if (math.isfinite(self.k_soft) and self.k_soft > 0.0) else 0.0
+        om = 8.0 / tau if tau > 0.0 else 0.0
+        mu = (k / (om * om) if k > 0.0 else 1.0) if om > 0.0 else 1.0
+        if (not math.isfinite(mu)) or mu <= 0.0:
+            mu = 1.0
+        self.mu_soft, self.omega_spr0 = float(mu), float(om)
+
+    def dV_d_epsilon(self):
+        """forces.py:77-112 through the force kernel's fused scalar sums."""
+        _, dV = self.potential_and_dVdeps()
+        return dV
+
+    def _estimate_pi_budget_h(self, dt_abs):
+        """hamiltonian_softening_integrator.py:1125-1221."""
+        k = self.k_soft
+        if (not math.isfinite(k)) or k <= 0.0:
+            return float(dt_abs)
+        Delta = self.eps - self.eps_target()
+        s0 = self.s0 if (math.isfinite(self.s0) and self.s0 > 0.0) else 1.0
+        d_eff = max(abs(Delta), 1.0e-4 * s0)
+        dV = self.dV_d_epsilon() if (self.n >= 2 and self.G != 0.0) else 0.0
+        dB = -self._fbar(self.eps) if self.soft_policy else 0.0
+        tot = max(abs(dV + dB), 1.0e-16)
+        h_pi = (2.0 * self.chi_pi * math.sqrt(k) * d_eff) / tot
+        if (not math.isfinite(h_pi)) or h_pi < 0.0:
+            h_pi = float(dt_abs)
+        return float(h_pi)
+
+    def _freeze_production_schedule(self, dt_user):
+        """hamiltonian_softening_integrator.py:986-1119."""
+        dt_abs = abs(float(dt_user))
+        if (not math.isfinite(dt_abs)) or dt_abs <= 0.0:
+            dt_abs = 1.0e-2
+        tau = self._tau_grav_soft(dt_abs)
+        om = self.omega_spr0
+        if (not math.isfinite(om)) or om <= 0.0:
+            om = 8.0 / tau if tau > 0.0 else 0.0
+            self.omega_spr0 = om
+        theta_cap = self.theta_cap if (math.isfinite(self.theta_cap) and self.theta_cap > 0.0) else 0.1
+        h_g = 0.9 * tau
+        h_o = theta_cap / om if om > 0.0 else math.inf
+        h_theta = min(h_g, h_o) if (math.isfinite(h_o) and h_o > 0.0) else h_g
+        h_pi = self._estimate_pi_budget_h(dt_abs)
+        if (not math.isfinite(h_pi)) or h_pi <= 0.0:
+            h_pi = dt_abs
+        h_sub = min(h_theta, h_pi)
+        if (not math.isfinite(h_sub)) or h_sub <= 0.0:
+            h_sub = dt_abs
+        n_sub = int(math.ceil(dt_abs / h_sub)) if h_sub > 0.0 else 1
+        self.frozen_n_sub = max(1, n_sub)
+        self.macro_dt_frozen = dt_abs
+        self.h_theta, self.h_pi = h_theta, h_pi
+
+    def strang_substeps(self, dt):
+        """hamiltonian_softening_integrator.py:781-888 (mu floor :232-242, frozen n_sub within 1 % of the frozen dt)."""
+        dt_abs = abs(float(dt))
+        mu_macro = self.k_soft * (dt_abs / self.theta_imp) ** 2
+        if math.isfinite(self.k_soft) and self.k_soft > 0.0 and self.mu_soft < mu_macro:
+            self.mu_soft = float(mu_macro)
+        prev = self.macro_dt_frozen
+        if not (prev > 0.0 and abs(dt_abs - prev) / prev <= 0.01):
+            self._freeze_production_schedule(dt_abs)
+        return int(self.frozen_n_sub)
+
+    # ---- flows (hamsoft_stepper.py:47-308, hamsoft_flows.py:427-762, 1102-1132) ---------------------------------
+    def s_half(self, h):
+        torch = self.torch
+        dt = 0.5 * float(h)
+        eps0, pi0 = float(self.eps), float(self.pi)
+        es, grad = self.eps_star_and_grad()
+        k, mu = self.k_soft, self.mu_soft
+        om = math.sqrt(k / mu) if (k > 0.0 and mu > 0.0) else 0.0
+        th = om * dt
+        if abs(th) < 1.0e-8:
+            th2 = th * th
+            sn = th - th2 * th / 6.0 + th2 * th2 * th / 120.0
+            cs = 1.0 - th2 / 2.0 + th2 * th2 / 24.0
+        else:
+            sn, cs = math.sin(th), math.cos(th)
+        kick1 = -0.5 * dt * (-self._fbar(eps0)) if self.soft_policy else 0.0
+        D0 = eps0 - es
+        pin = pi0 + kick1
+        if om != 0.0 and mu != 0.0:
+            mo = math.sqrt(mu * max(k, 0.0))
+            dlt = D0 * cs + (pin / (mu * om)) * sn
+            eta_t = pin * cs - mo * D0 * sn
+            den = mu * om * om
+            I = (D0 / om) * sn + (pin / den) * (1.0 - cs) if den != 0.0 else 0.0
+        else:
+            dlt, eta_t, I = D0, pin, 0.0
+        eps_rot = es + dlt
+        kick2 = -0.5 * dt * (-self._fbar(eps_rot)) if self.soft_policy else 0.0
+        J = k * I
+        v64 = self.vel.double()
+        pn = float(self._allmax((self.m64 * torch.sqrt((v64 * v64).sum(1))).max()))
+        gn = float(self._allmax(torch.sqrt((grad * grad).sum(1)).max()))
+        p_scale = max(pn, 1.0e-12)
+        dp_inf = abs(J) * gn
+        thr = self.j_max_cap * p_scale
+        Ja = J * (thr / dp_inf) if (dp_inf > thr and dp_inf > 0.0) else J
+        self.vel += (Ja * grad / self.m64[:, None]).float()
+        self.eps = float(eps_rot)
+        self.pi = float(eta_t + kick2)
+        self.taps = dict(eps_star=es, J=J, J_applied=Ja, theta=th, sweeps=self.last_sweeps)
+
+    def v_half_kick(self, h):
+        hh = 0.5 * float(h)
+        e = float(self.eps)
+        dU = 0.0
+        if self.n >= 2 and self.G != 0.0:
+            self.accelerations(with_sums=True)               # force kernel at the CURRENT epsilon + fused sum m_i m_j / rho^3
+            s = self._allsum(self.sums)
+            dU = self.G * e * 0.5 * float(s[1]) if e != 0.0 else 0.0
+            self._kick_drift(hh, 0.0)
+        dB = -self._fbar(e) if self.soft_policy else 0.0
+        self.pi = float(self.pi) - (dU + dB) * hh
+
+    def strang_step(self, h):
+        self.s_half(h)
+        self.v_half_kick(h)
+        self._kick_drift(0.0, h)
+        self._gather()
+        self.v_half_kick(h)
+        self.s_half(h)
+
+    def step(self, dt):
+        """hamiltonian_softening_integrator.py:496-557."""
+        if dt == 0.0 or self.n == 0:
+            return
+        n_pred = max(1, self.strang_substeps(dt))
+        h = float(dt) / float(n_pred)
+        for _ in range(n_pred):
+            self.strang_step(h)
+        self.n_sub_last = n_pred
+
+    def extended_hamiltonian(self):
+        """hamsoft_energy.py:48-162: T + U + pi^2/2mu + k/2 (eps - eps*)^2 + S_bar."""
+        U, _ = self.potential_and_dVdeps()
+        T = self.kinetic_energy()
+        es = self.eps_target()
+        H = T + U + self.pi * self.pi / (2.0 * self.mu_soft) + 0.5 * self.k_soft * (self.eps - es) ** 2
+        if self.soft_policy and math.isfinite(self.k_wall) and self.k_wall > 0.0 and self.n_exp >= 2:
+            a, b = min(self.eps_min, self.eps_max), max(self.eps_min, self.eps_max)
+            p = self.n_exp - 1
+            H += (self.k_wall / p) * (max(0.0, a - self.eps) ** p + max(0.0, self.eps - b) ** p)
+        return H
+
+
+def torch_exp(torch, t):
+    return torch.exp(t)
+
+
 def torch_sum(t):
     return float(t.sum())
 

@@ -151,3 +151,25 @@ def test_hamsoft_oracle_vs_golden():
             assert abs(sim.pi - ep[1]) <= (1e-11 + 30 * sens[2]) * max(abs(ep[1]), 1e-12)
             assert sim.mu_soft == pytest.approx(ep[2], rel=1e-14)
         assert sim.n_sub_last == int(g[key + "n_sub"])
+
+
+def test_largen_hamsoft_oracle_dense_equals_pinned_loops():
+    """The dense restatement used for large-N parity equals the loop version (the one pinned bit-for-bit against the
+    reference in hamsoft.npz) -- calibration, eps*, analytic gradient and three macro steps."""
+    from oracle.largen_hamsoft_oracle import LargeNHamSoftOracle
+    rng = np.random.default_rng(0)
+    for n in (3, 5, 8):
+        m = rng.uniform(0.5, 1.5, n)
+        q = rng.standard_normal((n, 2))
+        v = rng.standard_normal((n, 2)) * 0.3
+        a = LargeNHamSoftOracle(m, q, v, softening=0.05, dense=True)
+        b = LargeNHamSoftOracle(m, q, v, softening=0.05, dense=False)
+        assert (a.eps_min, a.alpha_run, a.frozen_n_sub) == (b.eps_min, b.alpha_run, b.frozen_n_sub)
+        assert abs(a.mu_soft - b.mu_soft) <= 1e-13 * b.mu_soft
+        ea, ga = a.eps_star_and_grad(a.q)
+        eb, gb = b.eps_star_and_grad(b.q)
+        assert abs(ea - eb) <= 1e-14 and np.max(np.abs(ga - gb)) <= 1e-12 * np.max(np.abs(gb))
+        for _ in range(3):
+            a.step(0.01)
+            b.step(0.01)
+        assert np.max(np.abs(a.q - b.q)) <= 1e-12 and abs(a.eps - b.eps) <= 1e-13 and abs(a.pi - b.pi) <= 1e-12
