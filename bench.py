@@ -157,10 +157,34 @@ def run_cpu(n_jobs: int, cores: int, seed: int = 777):
     return done / dt, dt
 
 
+def impl_reference_largen(args):
+    from nbodysimproject_b200.largen import cpu_pairs_per_s
+    n = 4096
+    times = []
+    for it in range(args.warmup + args.steps):
+        rate, dt = cpu_pairs_per_s(n, 3)
+        if it >= args.warmup:
+            times.append(dt)
+    dt = sum(times) / len(times)
+    value = float(n) * n / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "pair-interactions/s at N=2^20", "value": value, "unit": "pair-interactions/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * dt,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C5 large-N direct sum; CPU path bounded to N=4096 (dense (N,N,2) fp64 temporaries: "
+                               "N=2^20 would need 17.6 TB), pairs/s is size-independent for N >= 256"},
+        "cpu_baseline": {"value": value, "unit": "pair-interactions/s", "cores": 1, "kind": "port",
+                         "sample": "oracle dense gravitational_force at N=4096, 3 calls per step"},
+        "e2e": {"value": value, "unit": "pair-interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
 def impl_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "largen":
+        return impl_reference_largen(args)
     cores = os.cpu_count() or 1
     n_jobs = max(cores, 8) * 4
     times, done = [], 0
@@ -376,11 +400,33 @@ def impl_b200(args):
                 "flop_model": "SURVEY.md 8d: per sub-step 3 x 14 N(N-1) + 36 N",
                 "share_of_step": best / (t_dev / args.steps), "per_bucket_solo": per}
 
+    # ---- second half of BASELINE.json's metric: pair-interactions/s of the large-N direct sum at N = 2^20
+    # (all ranks take part: i-blocks sharded, in-place NCCL all-gather of the packed positions per evaluation)
+    largen = None
+    if not args.no_largen:
+        from nbodysimproject_b200 import largen as LN
+        n_ln = 1 << 20
+        mm, qq, vv = LN.make_disc(n_ln, seed=1)
+        lsim = LN.LargeNSimulation(mm, qq, vv, G=1.0, softening=1e-3, device=dev)
+        k_ln = 3
+        t_ln = LN.measure_force(lsim, k_ln, 3)
+        if rank == 0:
+            peak32 = L.peak_flops(1, local)
+            rate = float(n_ln) * n_ln * k_ln / t_ln
+            largen = {"metric": "pair-interactions/s at N=2^20", "value": rate, "unit": "pair-interactions/s",
+                      "n": n_ln, "ms_per_force_evaluation": 1e3 * t_ln / k_ln, "scaling": "strong", "dtype": "f32",
+                      "gpu_launches": 2 * k_ln,
+                      "roofline": {"bound": "fp32", "kernel": "largeN_accel_x2_kernel",
+                                   "achieved": 14.0 * rate * 1e-12 / world, "peak": peak32, "unit": "TFLOP/s",
+                                   "frac": 14.0 * rate * 1e-12 / world / peak32, "flops_per_pair": 14,
+                                   "peak_source": "nb_peak_flops(1): FFMA micro-benchmark, same GPU, same run"}}
+        del lsim
+
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        n_jobs = max(cores, 8) * 24
+        n_jobs = max(cores, 8) * 96          # ~10-15 s of CPU work on the box's cores
         rate, dt_cpu = run_cpu(n_jobs, cores)
         cpu = {"value": rate, "unit": "system-steps/s", "cores": cores, "kind": "port",
                "sample": f"{n_jobs} systems x {STEPS_PER_SYSTEM} steps of the same generator, NumPy oracle in "
@@ -402,7 +448,7 @@ def impl_b200(args):
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps,
                     "api": "nb_ensemble_analyze_host_async (C ABI, pinned host buffers)"},
             "gpu_launches": int(launches_per_step * args.steps),
-            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "largen": largen,
             "checks": {"e2e_equals_device_path": bool(same), "systems_with_nonzero_status": n_bad},
         }
         print(json.dumps(line))
@@ -428,7 +474,10 @@ def main():
     ap.add_argument("--workload", default="ensemble", choices=["ensemble", "largen"])
     ap.add_argument("--systems", type=int, default=1 << 20, help="systems per GPU (weak scaling)")
     ap.add_argument("--n", type=int, default=1 << 20, help="particles for --workload largen")
+    ap.add_argument("--n-hamsoft", type=int, default=0, dest="n_hamsoft",
+                    help="particles for the ham_soft Strang sub-step timing of --workload largen (default min(n, 2^18))")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-largen", action="store_true", help="skip the secondary large-N force measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -20,11 +20,11 @@ from . import _lib as L
 
 class LargeNSimulation:
     def __init__(self, masses, positions, velocities=None, G: float = 1.0, softening: float = 1e-3,
-                 integrator_mode: str = "verlet", device=None, group=None):
+                 integrator_mode: str = "verlet", device=None, group=None, distributed: bool = True):
         torch = L.require_cuda()
         import torch.distributed as dist
         self.torch = torch
-        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.dist = dist if (distributed and dist.is_available() and dist.is_initialized()) else None
         self.group = group
         self.world = self.dist.get_world_size(group) if self.dist else 1
         self.rank = self.dist.get_rank(group) if self.dist else 0
@@ -148,7 +148,8 @@ class LargeNHamSoftSimulation(LargeNSimulation):
                  min_softening: float = 0.0, k_soft: float = 1.0e3, k_wall: float = 1.0e9, barrier_exponent: int = 5,
                  theta_cap: float = 0.1, theta_imp: float = 0.5, alpha: float = 0.1, eta: float = 1.35,
                  chi_pi: float = 0.2, j_max_cap: float = 0.02, initial_dt: float = 0.01, use_soft_barrier: bool = True,
-                 disable_barrier: bool = False, split_n_max: int = 50, device=None, group=None):
+                 disable_barrier: bool = False, split_n_max: int = 50, device=None, group=None,
+                 distributed: bool = True):
         min_softening = max(0.0, float(min_softening))
         softening = float(softening)
         if softening < 0.0:
@@ -157,7 +158,7 @@ class LargeNHamSoftSimulation(LargeNSimulation):
             min_softening = 0.1 * softening                         # simulation.py:88-114
         s0 = max(softening, min_softening)
         super().__init__(masses, positions, velocities, G=G, softening=s0, integrator_mode="verlet", device=device,
-                         group=group)
+                         group=group, distributed=distributed)
         torch = self.torch
         self.mode = "ham_soft"
         self.s0 = s0
@@ -525,38 +526,56 @@ def make_disc(n: int, seed: int = 0):
     return m, q, v
 
 
+def cpu_pairs_per_s(n: int = 4096, reps: int = 3):
+    """CPU baseline for the large-N metric: the oracle's dense gravitational_force (forces.py:63-75 restated) at the
+    largest N whose (N,N,2) fp64 temporaries fit comfortably; pairs/s on one core (the reference is single-threaded)."""
+    from oracle import nbody_oracle as O
+    m, q, _ = make_disc(n, seed=5)
+    O.accelerations(q, m, 1e-3, 1.0)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        O.accelerations(q, m, 1e-3, 1.0)
+    dt = (time.perf_counter() - t0) / reps
+    return float(n) * float(n) / dt, dt
+
+
+def measure_force(sim, steps: int, warmup: int = 3):
+    """CUDA-event time of `steps` x (in-place position all-gather + one force evaluation); returns seconds (this rank)."""
+    torch = sim.torch
+    for _ in range(max(warmup, 3)):
+        sim._gather()
+        sim.accelerations()
+    torch.cuda.synchronize()
+    if sim.dist is not None and sim.world > 1:
+        sim.dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        sim._gather()
+        sim.accelerations()
+    e1.record()
+    torch.cuda.synchronize()
+    if sim.dist is not None and sim.world > 1:
+        sim.dist.barrier()
+    t = e0.elapsed_time(e1) * 1e-3
+    if sim.dist is not None and sim.world > 1:
+        tt = torch.tensor([t], dtype=torch.float64, device=sim.device)
+        sim.dist.all_reduce(tt, op=sim.dist.ReduceOp.MAX)
+        t = float(tt[0])
+    return t
+
+
 def bench_largen(args, world, rank, local, dev):
     """pair-interactions/s of one force evaluation over all ordered pairs of an N-particle system
-    (strong scaling: N fixed, i-blocks sharded, one in-place position all-gather per evaluation)."""
+    (strong scaling: N fixed, i-blocks sharded, one in-place position all-gather per evaluation), plus the wall
+    time of one full ham_soft Strang sub-step S V T V S (adaptive epsilon) on the same particles."""
     import torch
     import torch.distributed as dist
     n = int(args.n)
     m, q, v = make_disc(n, seed=1)
     sim = LargeNSimulation(m, q, v, G=1.0, softening=1e-3, device=dev)
-
-    def step():
-        sim._gather()
-        sim.accelerations()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t = e0.elapsed_time(e1) * 1e-3
-    if world > 1:
-        tt = torch.tensor([t], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t = float(tt[0])
+    t = measure_force(sim, args.steps, args.warmup)
     # e2e: host positions in, host accelerations out, every step
     xym_h = sim.xym.cpu().pin_memory()
     acc_h = torch.empty((sim.ni, 2), dtype=torch.float32).pin_memory()
@@ -568,10 +587,42 @@ def bench_largen(args, world, rank, local, dev):
         acc_h.copy_(sim.acc, non_blocking=True)
         torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = float(tt[0])
+    # full Strang sub-step of the adaptive-epsilon flow (C5 as BASELINE.json words it)
+    strang = None
+    n_hs = int(getattr(args, "n_hamsoft", 0) or min(n, 1 << 18))
+    if n_hs > 0:
+        mh, qh, vh = make_disc(n_hs, seed=1)
+        hs = LargeNHamSoftSimulation(mh, qh, vh, softening=2.0 / math.sqrt(n_hs), initial_dt=1e-3, device=dev)
+        hsub = 1e-3 / hs.frozen_n_sub
+        hs.strang_step(hsub)
+        torch.cuda.synchronize()
+        p0, f0 = hs.n_passes, hs.force_evals
+        t0 = time.perf_counter()
+        hs.strang_step(hsub)
+        torch.cuda.synchronize()
+        ts = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([ts], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ts = float(tt[0])
+        n_pass = (hs.n_passes - p0) + (hs.force_evals - f0)
+        strang = {"n": n_hs, "ms": 1e3 * ts, "n2_passes": n_pass, "solver_sweeps": hs.last_sweeps,
+                  "pair_evaluations_per_s": n_pass * float(n_hs) * n_hs / ts, "frozen_n_sub": hs.frozen_n_sub,
+                  "eps": hs.eps, "eps_min": hs.eps_min, "eps_max": hs.eps_max}
     if rank != 0:
         return None
     pairs = float(n) * float(n) * args.steps
     peak32 = L.peak_flops(1, local)
+    cpu = None
+    if world == 1 and not getattr(args, "no_cpu", False):
+        rate, dtc = cpu_pairs_per_s(4096, 5)
+        cpu = {"value": rate, "unit": "pair-interactions/s", "cores": 1, "kind": "port",
+               "sample": f"oracle dense gravitational_force at N=4096 ({dtc*1e3:.0f} ms per call; the (N,N,2) fp64 "
+                         "temporaries make N=2^20 impossible on the CPU path: 17.6 TB)"}
     line = {
         "metric": "pair-interactions/s at N=2^20", "value": pairs / t, "unit": "pair-interactions/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t / args.steps,
@@ -582,8 +633,10 @@ def bench_largen(args, world, rank, local, dev):
         "e2e": {"value": pairs / t_e2e, "unit": "pair-interactions/s", "h2d_bytes_per_step": int(n * 16),
                 "d2h_bytes_per_step": int(sim.ni * 8)},
         "gpu_launches": 2 * args.steps,
-        "roofline": {"bound": "fp32", "kernel": "largeN_accel_kernel", "achieved": 14.0 * pairs / t * 1e-12 / world,
+        "roofline": {"bound": "fp32", "kernel": "largeN_accel_x2_kernel", "achieved": 14.0 * pairs / t * 1e-12 / world,
                      "peak": peak32, "unit": "TFLOP/s", "frac": 14.0 * pairs / t * 1e-12 / world / peak32,
-                     "traffic": None, "peak_source": "nb_peak_flops(1): register-resident FFMA micro-benchmark"},
+                     "traffic": None, "flops_per_pair": 14,
+                     "peak_source": "nb_peak_flops(1): register-resident FFMA micro-benchmark, same GPU, same run"},
+        "hamsoft_strang_substep": strang, "cpu_baseline": cpu,
     }
     return line
