@@ -238,6 +238,11 @@ def impl_b200(args):
 
     if args.workload == "largen":
         return bench_largen(args, torch, dist, world, rank, local, dev)
+    if args.workload in ("c4", "c1"):
+        bench_secondary(args, torch, dist, world, rank, local, dev)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     B_total = args.systems
     inp = make_inputs(B_total, seed=42 + rank)
@@ -456,6 +461,188 @@ def impl_b200(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------
+# secondary ensemble workloads: C4 (whfast planetary) and C1 (README 3-body ham_soft, batched)
+# ---------------------------------------------------------------------------------------------
+
+def _c4_inputs(B, seed):
+    """star + 2/3/4 planets near 3:2 / 2:1 / 5:3 chains, half of them the TTV cohort."""
+    from nbodysimproject_b200.generators import EnsembleInputs
+    rng = np.random.default_rng(seed)
+    out = {}
+    per = [B // 3, B // 3, B - 2 * (B // 3)]
+    for npl, b in zip((2, 3, 4), per):
+        parts = [EnsembleInputs.planetary(rng, b - b // 2, npl, ttv=False), EnsembleInputs.planetary(rng, b // 2, npl, ttv=True)]
+        out[npl + 1] = tuple(np.concatenate([p[k] for p in parts]) for k in range(4))
+    return out
+
+
+def _c1_inputs(B, seed):
+    """README example (masses [1, 0.5, 0.1], collinear), jittered by 1e-3 randn so the systems differ."""
+    rng = np.random.default_rng(seed)
+    m = np.tile(np.array([1.0, 0.5, 0.1]), (B, 1))
+    q = np.tile(np.array([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0]]), (B, 1, 1)) + 1e-3 * rng.standard_normal((B, 3, 2))
+    v = np.tile(np.array([[0.0, 0.0], [0.0, 1.0], [0.0, 0.5]]), (B, 1, 1)) + 1e-3 * rng.standard_normal((B, 3, 2))
+    v = v - np.sum(m[:, :, None] * v, axis=1, keepdims=True) / np.sum(m, axis=1)[:, None, None]
+    return m, q, v
+
+
+def _cpu_c4(job):
+    from oracle import nbody_oracle as O
+    m, q, v, n_steps, dt = job
+    sim = O.OracleSim(m, q, v, softening=0.0, integrator_mode="whfast")
+    for _ in range(n_steps):
+        sim.step(dt)
+    return n_steps
+
+
+def _cpu_c1(job):
+    from oracle.hamsoft_oracle import HamSoftOracleSim
+    m, q, v, n_steps, dt = job
+    sim = HamSoftOracleSim(m, q, v, softening=1e-3)
+    for _ in range(n_steps):
+        sim.step(dt)
+    return n_steps
+
+
+def _cpu_pool(fn, jobs, cores):
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        done = sum(pool.map(fn, jobs, chunksize=1))
+    dt = time.perf_counter() - t0
+    return done / dt, dt
+
+
+def bench_secondary(args, torch, dist, world, rank, local, dev):
+    """--workload c4 | c1: system-steps/s of the whfast planetary ensemble / the batched README ham_soft system.
+    One bench step = n_steps integrator steps of every system in one persistent-kernel launch per bucket."""
+    from nbodysimproject_b200 import _lib as L
+    from nbodysimproject_b200 import ensemble as E
+    from nbodysimproject_b200 import hamsoft as H
+    c4 = args.workload == "c4"
+    n_steps = 1000
+    dt = 0.01 * 2.0 * np.pi if c4 else 0.01
+    B = args.systems if c4 else min(args.systems, 1 << 17)
+    runs = []
+    if c4:
+        inp = _c4_inputs(B, 42 + rank)
+        for N, (m, q, v, eps) in sorted(inp.items()):
+            bk = E.DeviceBucket(m, q, v, eps, 1.0, "whfast", dev)
+            bk.q0, bk.v0 = bk.q.clone(), bk.v.clone()
+            bk.stream = torch.cuda.Stream(device=dev)
+            runs.append(bk)
+    else:
+        m, q, v = _c1_inputs(B, 42 + rank)
+        hs, s0 = H.default_params(object(), 1e-3, 1e-4, B)
+        ep = np.stack([np.maximum(s0, hs[:, H.P["eps_min"]]), np.zeros(B)], 1)
+        hb = H.HamSoftBucket(m, q, v, hs, ep, 1.0, dev)
+        hb.setup(calibrate=True, freeze_dt=dt)
+        hb.q0, hb.v0, hb.ep0, hb.hs0 = hb.bk.q.clone(), hb.bk.v.clone(), hb.eps_pi.clone(), hb.hs.clone()
+        runs.append(hb)
+
+    def step():
+        cur = torch.cuda.current_stream()
+        if c4:
+            for bk in runs:
+                bk.stream.wait_stream(cur)
+                with torch.cuda.stream(bk.stream):
+                    bk.q.copy_(bk.q0); bk.v.copy_(bk.v0)
+                    bk.prepare(L.PREP_REMOVE_COM | L.PREP_CTOR_KICK, dt, dt, dt, 50)
+                    bk.run(dt, n_steps, 0, 0, flags=L.RUN_WRITE_STATE, want_dyn=False)
+            for bk in runs:
+                cur.wait_stream(bk.stream)
+        else:
+            hb = runs[0]
+            hb.bk.q.copy_(hb.q0); hb.bk.v.copy_(hb.v0); hb.eps_pi.copy_(hb.ep0); hb.hs.copy_(hb.hs0)
+            hb.run(dt, n_steps)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(); torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    # e2e: pinned host state in, final host state out, every step
+    host = []
+    for r in runs:
+        bk = r if c4 else r.bk
+        host.append((bk.q0.cpu().pin_memory() if c4 else r.q0.cpu().pin_memory(),
+                     bk.v0.cpu().pin_memory() if c4 else r.v0.cpu().pin_memory(),
+                     torch.empty(bk.q.shape, dtype=torch.float64).pin_memory(),
+                     torch.empty(bk.v.shape, dtype=torch.float64).pin_memory()))
+    h2d = sum(a.numel() * 8 + b.numel() * 8 for a, b, _, _ in host)
+    d2h = h2d
+
+    def step_e2e():
+        for r, (q0h, v0h, qh, vh) in zip(runs, host):
+            if c4:
+                r.q0.copy_(q0h, non_blocking=True); r.v0.copy_(v0h, non_blocking=True)
+            else:
+                r.q0.copy_(q0h, non_blocking=True); r.v0.copy_(v0h, non_blocking=True)
+        step()
+        for r, (q0h, v0h, qh, vh) in zip(runs, host):
+            bk = r if c4 else r.bk
+            qh.copy_(bk.q, non_blocking=True); vh.copy_(bk.v, non_blocking=True)
+        torch.cuda.synchronize()
+
+    step_e2e()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(tt[0]), float(tt[1])
+    n_bad = int(sum(int(((r if c4 else r.bk).status != 0).sum()) for r in runs))
+    if rank != 0:
+        return
+    sys_steps = float(B) * world * n_steps * args.steps
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        if c4:
+            inp = _c4_inputs(3 * cores * 2, 7)
+            jobs = [(inp[N][0][i], inp[N][1][i], inp[N][2][i], 2000, dt) for N in sorted(inp) for i in range(inp[N][0].shape[0])]
+            rate, dtc = _cpu_pool(_cpu_c4, jobs, cores)
+            sample = f"{len(jobs)} planetary systems x 2000 whfast steps, NumPy oracle in {cores} processes, {dtc:.1f} s"
+        else:
+            m, q, v = _c1_inputs(cores, 7)
+            jobs = [(m[i], q[i], v[i], 1000, dt) for i in range(cores)]
+            rate, dtc = _cpu_pool(_cpu_c1, jobs, cores)
+            sample = f"{cores} jittered README systems x 1000 ham_soft steps, oracle in {cores} processes, {dtc:.1f} s"
+        cpu = {"value": rate, "unit": "system-steps/s", "cores": cores, "kind": "port", "sample": sample}
+    name = ("C4 WHFast + Kepler planetary ensemble (BASELINE.json configs[3]): star + 2-4 planets near 3:2/2:1/5:3, "
+            "half TTV cohort, dt = 0.01 x 2 pi, bug-compatible Kepler solver") if c4 else \
+           ("C1 README 3-body ham_soft (BASELINE.json configs[0]) batched: jittered copies, dt = 0.01, adaptive-epsilon "
+            "Strang flow with the finite-difference eps* gradient")
+    line = {
+        "metric": "system-steps/s", "value": sys_steps / t_dev, "unit": "system-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "systems_per_gpu": B, "integrator_steps_per_bench_step": n_steps,
+                   "buckets": {str((r if c4 else r.bk).N): int((r if c4 else r.bk).B) for r in runs}},
+        "e2e": {"value": sys_steps / t_e2e, "unit": "system-steps/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps},
+        "gpu_launches": int((2 * len(runs) if c4 else 1) * args.steps), "roofline": None, "cpu_baseline": cpu,
+        "clocks": clocks, "checks": {"systems_with_nonzero_status": n_bad},
+    }
+    print(json.dumps(line))
+
+
 def bench_largen(args, torch, dist, world, rank, local, dev):
     from nbodysimproject_b200.largen import bench_largen as run
     line = run(args, world, rank, local, dev)
@@ -471,7 +658,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="ensemble", choices=["ensemble", "largen"])
+    ap.add_argument("--workload", default="ensemble", choices=["ensemble", "largen", "c4", "c1"])
     ap.add_argument("--systems", type=int, default=1 << 20, help="systems per GPU (weak scaling)")
     ap.add_argument("--n", type=int, default=1 << 20, help="particles for --workload largen")
     ap.add_argument("--n-hamsoft", type=int, default=0, dest="n_hamsoft",

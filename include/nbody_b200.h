@@ -111,7 +111,8 @@ int nb_ensemble_prepare_f64(const double* m, const double* q, double* v, const d
  *      further steps with the tangent map (evolution_features.py:34-66; raw_dr/raw_dv are the two
  *      randn(N,2) draws per system).  perm[B] (optional) maps thread -> system so that callers can sort
  *      by n_sub; n_heavy (optional, device int32 = workspace[64] of nb_sort_by_nsub) says how many leading
- *      entries of perm have n_sub > 4: those run on the latency-optimised lane-per-body mapping.
+ *      entries of perm are sub-step-heavy: those run on the latency-optimised mappings (one body per lane;
+ *      one pair per lane for N >= 5).
  *      q, v are advanced in place when NB_RUN_WRITE_STATE, NB_RUN_ENERGY or n_megno > 0 is requested.
  *      ham_soft additionally takes eps_pi[B][2] (epsilon, pi; in/out) and hs_params. */
 int nb_ensemble_run_f64(const double* m, double* q, double* v, const double* eps, double G, int B, int N,
@@ -135,8 +136,13 @@ int nb_hamsoft_probe_f64(const double* m, const double* q, const double* v, doub
                          const double* eps_pi, const double* hs_params, double* out, void* stream);
 
 /* counting sort of systems by n_sub (descending) -> perm[B]; workspace: 128 int32 on the device;
- * on return workspace[64] = number of systems with n_sub > 4 (the "heavy" head of perm) */
-int nb_sort_by_nsub(const int32_t* n_sub, int B, int32_t* perm, int32_t* workspace, void* stream);
+ * on return workspace[64] = number of systems in the "heavy" head of perm (n_sub > workspace[65]) that the run
+ * kernels map for latency instead of throughput.  The threshold is chosen per batch, >= 4, from N (bodies per
+ * system, 0 = unknown), the largest n_sub present and sum(n_sub): a system is heavy only when its own sequential
+ * sub-step chain would otherwise set the run time of the launch. */
+int nb_sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* workspace, void* stream);
+/* override the heavy threshold (process-wide; tests and tuning): -1 = automatic (default), 0..63 = fixed */
+int nb_ensemble_set_heavy_nsub(int threshold);
 
 /* ---- the same path end to end with HOST buffers (BatchStabilityAnalyzer.analyze_batch,
  *      batch_stability_analyzer.py:62-80): prepare(flags) -> sort -> run -> features.

@@ -25,7 +25,8 @@ int pair_batched(const double* q, const double* m, const double* eps, double G, 
                  double* dV, cudaStream_t st);
 int variational_batched(const double* q, const double* m, const double* s2, const double* dr, double G, int B, int N,
                         double* da, cudaStream_t st);
-int sort_by_nsub(const int32_t* n_sub, int B, int32_t* perm, int32_t* ws, cudaStream_t st);
+int sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* ws, cudaStream_t st);
+int set_heavy_nsub(int thr);
 int largeN_accel(const float* xym, int n_total, int i0, int ni, float eps, float G, float* acc, double* sums,
                  cudaStream_t st);
 int largeN_set_variant(int variant);
@@ -259,10 +260,12 @@ int nb_hamsoft_probe_f64(const double* m, const double* q, const double* v, doub
   return hamsoft_probe(m, q, v, G, B, N, eps_pi, hs_params, out, (cudaStream_t)stream);
 }
 
-int nb_sort_by_nsub(const int32_t* n_sub, int B, int32_t* perm, int32_t* workspace, void* stream) {
+int nb_ensemble_set_heavy_nsub(int threshold) { return set_heavy_nsub(threshold); }
+
+int nb_sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* workspace, void* stream) {
   if (!n_sub || !perm || !workspace || B < 0) { set_error("nb_sort_by_nsub: bad arguments"); return NB_ERR_ARG; }
   if (B == 0) return NB_OK;
-  return sort_by_nsub(n_sub, B, perm, workspace, (cudaStream_t)stream);
+  return sort_by_nsub(n_sub, B, N, perm, workspace, (cudaStream_t)stream);
 }
 
 int nb_ensemble_analyze_host_async(const double* m, const double* q, double* v, const double* eps, double G, int B, int N,
@@ -311,7 +314,7 @@ int nb_ensemble_analyze_host_async(const double* m, const double* q, double* v, 
   if (rc != NB_OK) return rc;
   if (pf & (NB_PREP_REMOVE_COM | NB_PREP_CTOR_KICK | NB_PREP_SNAPSHOT_KICK))
     NB_CUDA_CHECK(cudaMemcpyAsync(v, d_v, bn * 16, cudaMemcpyDeviceToHost, st));   // the reference mutates the caller's sims
-  rc = sort_by_nsub(d_nsub, B, d_perm, d_bins, st);
+  rc = sort_by_nsub(d_nsub, B, N, d_perm, d_bins, st);
   if (rc != NB_OK) return rc;
   const int interval = n_steps / 100 > 1 ? n_steps / 100 : 1;
   RunArgs ra{d_m, d_q, d_v, d_eps, G, B, NB_RUN_ENERGY, dt, n_steps, interval, n_megno, d_nsub, d_perm, d_bins + 64, 0, d_dr, d_dv, d_dyn, d_status};

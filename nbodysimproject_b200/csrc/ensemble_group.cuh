@@ -5,8 +5,8 @@
 // is ~17 N(N-1)/2 dependent-issue FP64 instructions (N = 8: ~520, >= 1040 cycles on one SMSP), so a system
 // that needs n_sub = 50 sub-steps per step (integrator.py:86-92 caps at split_n_max = 50) keeps ONE warp busy
 // for ~100 ms while the rest of the GPU has long finished.  Here lane b evaluates only a_b = sum_j (N pair
-// terms, ~14 N FP64 instructions), i.e. a ~5x shorter critical path at N = 8, at the price of evaluating every
-// ordered pair (no Newton's-third-law sharing).  Used for the n_sub > NB_HEAVY_NSUB head of the n_sub-sorted
+// terms, ~14 (N-1) FP64 instructions), i.e. a ~5x shorter critical path at N = 8, at the price of evaluating every
+// ordered pair (no Newton's-third-law sharing).  Used for the heavy head (nb_sort_by_nsub) of the n_sub-sorted
 // permutation: CTAs [0, group_blocks) of the main / MEGNO kernels run this body, the rest run the
 // throughput-optimal thread-per-system body, so both mappings overlap inside one launch.
 #pragma once
@@ -15,13 +15,14 @@
 
 namespace nb {
 
-constexpr int NB_HEAVY_NSUB = 4;   // systems with n_sub > this go to the lane-per-body mapping
+constexpr int NB_HEAVY_NSUB = 4;   // smallest threshold: systems with n_sub <= this never leave the thread mapping
 
 template <int N>
 struct GroupCtx {
   unsigned mask;
   int base;
-  double gm[N];
+  double gmk[N - 1];     // G m of the t-th partner (ascending body index, self skipped)
+  int src[N - 1];        // lane that holds the t-th partner
   double eps2;
 };
 
@@ -30,25 +31,27 @@ __device__ __forceinline__ void group_accel(const GroupCtx<N>& c, int b, double 
                                             double drx, double dry, double& dax, double& day) {
   ax = 0.0; ay = 0.0;
   if (TANGENT) { dax = 0.0; day = 0.0; }
+  // partners in ascending body index, the self pair skipped: t-th partner of body b is src[t] = t + (t >= b)
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
-    const double xj = __shfl_sync(0xffffffffu, x, c.base + j);
-    const double yj = __shfl_sync(0xffffffffu, y, c.base + j);
+  for (int t = 0; t < N - 1; ++t) {
+    const int src = c.src[t];
+    const double xj = __shfl_sync(0xffffffffu, x, src);
+    const double yj = __shfl_sync(0xffffffffu, y, src);
     const double dx = x - xj, dy = y - yj;
     const double r2 = fma(dx, dx, fma(dy, dy, c.eps2));
     const double w = rsqrt_f64<GUARD>(r2);
     const double w2 = w * w;
-    const double w3 = (j == b) ? 0.0 : w2 * w;          // zero self term
-    const double cj = c.gm[j] * w3;
+    const double w3 = w2 * w;
+    const double cj = c.gmk[t] * w3;
     ax = fma(-cj, dx, ax);
     ay = fma(-cj, dy, ay);
     if (TANGENT) {
-      const double ex = __shfl_sync(0xffffffffu, drx, c.base + j) - drx;   // d = dr_j - dr_i ; D = q_j - q_i = -(dx,dy)
-      const double ey = __shfl_sync(0xffffffffu, dry, c.base + j) - dry;
+      const double ex = __shfl_sync(0xffffffffu, drx, src) - drx;   // d = dr_j - dr_i ; D = q_j - q_i = -(dx,dy)
+      const double ey = __shfl_sync(0xffffffffu, dry, src) - dry;
       const double dot = -fma(dx, ex, dy * ey);
       const double c5 = 3.0 * dot * w2 * w3;
-      dax = fma(c.gm[j], fma(ex, w3, c5 * dx), dax);
-      day = fma(c.gm[j], fma(ey, w3, c5 * dy), day);
+      dax = fma(c.gmk[t], fma(ex, w3, c5 * dx), dax);
+      day = fma(c.gmk[t], fma(ey, w3, c5 * dy), day);
     }
   }
 }
@@ -115,7 +118,11 @@ __device__ __forceinline__ void group_body(const RunArgs& a, int phase, int writ
   const int sys = a.perm[slot];
   const double G_ = a.G;
 #pragma unroll
-  for (int j = 0; j < N; ++j) c.gm[j] = G_ * a.m[(size_t)sys * N + j];
+  for (int t = 0; t < N - 1; ++t) {
+    const int k = t < b ? t : t + 1;
+    c.gmk[t] = G_ * a.m[(size_t)sys * N + k];
+    c.src[t] = c.base + k;
+  }
   const double mb = a.m[(size_t)sys * N + b];
   double x = a.q[((size_t)sys * N + b) * 2 + 0], y = a.q[((size_t)sys * N + b) * 2 + 1];
   double vx = a.v[((size_t)sys * N + b) * 2 + 0], vy = a.v[((size_t)sys * N + b) * 2 + 1];
@@ -135,6 +142,7 @@ __device__ __forceinline__ void group_body(const RunArgs& a, int phase, int writ
     bool have_first = false, cos_nan = false;
     int n_samp = 0, next_sample = 0;
     const int interval = a.sample_interval;
+  const double theta_eps = (eps != 0.0) ? atan2(0.0, eps) : nan;   // diagnostics.py:246-249 with pi = 0: loop-invariant
     for (int step = 0; step < a.n_steps; ++step) {
 #pragma unroll 1
       for (int k = 0; k < n_sub_warp; ++k) {
@@ -156,7 +164,7 @@ __device__ __forceinline__ void group_body(const RunArgs& a, int phase, int writ
         com_sum += com; com_max = fmax(com_max, com);
         var_sum += var; var_max = fmax(var_max, var);
         cos_sum += cc; cos_min = fmin(cos_min, cc);
-        th_sum += (eps != 0.0) ? atan2(0.0, eps) : nan;
+        th_sum += theta_eps;
         ++n_samp;
       }
     }

@@ -19,6 +19,7 @@
 #include "kepler.cuh"
 #include "args.cuh"
 #include "ensemble_group.cuh"
+#include "ensemble_pairlane.cuh"
 
 namespace nb {
 
@@ -237,14 +238,22 @@ __device__ __forceinline__ int store_state(const RunArgs& a, int sys, const SysS
   return finite ? 0 : NB_STATUS_NONFINITE;
 }
 
+template <int N, int MODE>
+__host__ __device__ constexpr bool use_pairlane() { return N >= 5 && MODE != NB_MODE_WHFAST; }
+
 // ---------------------------------------------------------------------------------------------
 // phase 1: the main loop, n_steps macro steps with step_metrics sampling (stability_analyzer.py:113-128).
 // Nothing in here takes the address of the state, so it stays in registers for the whole run.
 // ---------------------------------------------------------------------------------------------
 template <int N, int MODE, bool GUARD, bool EXACT>
 __global__ void __launch_bounds__(128) ensemble_main_kernel(RunArgs a, int write_state) {
-  if (MODE != NB_MODE_WHFAST && (int)blockIdx.x < a.group_blocks) {   // lane-per-body mapping for the n_sub-heavy head
-    group_body<N, MODE == NB_MODE_WHFAST ? NB_MODE_VERLET : MODE, GUARD>(a, 0, write_state);
+  if (MODE != NB_MODE_WHFAST && (int)blockIdx.x < a.group_blocks) {   // latency-optimised mappings for the n_sub-heavy head
+    if constexpr (use_pairlane<N, MODE>()) {
+      __shared__ __align__(16) double pl_smem[PairLane<N>::SMEM_DOUBLES];
+      pairlane_main<N, MODE, GUARD>(a, write_state, pl_smem);          // one pair per lane (N >= 5)
+    } else {
+      group_body<N, MODE == NB_MODE_WHFAST ? NB_MODE_VERLET : MODE, GUARD>(a, 0, write_state);   // one body per lane
+    }
     return;
   }
   const int nh = (a.group_blocks > 0) ? min(*a.n_heavy, a.B) : 0;
@@ -266,6 +275,8 @@ __global__ void __launch_bounds__(128) ensemble_main_kernel(RunArgs a, int write
   bool have_first = false, cos_nan = false;
   int n_samp = 0, next_sample = 0;
   const int interval = a.sample_interval;
+  // diagnostics.py:246-249 with pi = 0: loop-invariant
+  const double theta_eps = (eps != 0.0) ? atan2(0.0, eps) : __longlong_as_double(0x7ff8000000000000LL);
   for (int step = 0; step < a.n_steps; ++step) {
 #pragma unroll 1
     for (int k = 0; k < n_sub; ++k)
@@ -293,7 +304,7 @@ __global__ void __launch_bounds__(128) ensemble_main_kernel(RunArgs a, int write
       com_sum += com; com_max = fmax(com_max, com);
       var_sum += var; var_max = fmax(var_max, var);
       cos_sum += c; cos_min = fmin(cos_min, c);
-      th_sum += (eps != 0.0) ? atan2(0.0, eps) : __longlong_as_double(0x7ff8000000000000LL);
+      th_sum += theta_eps;
       ++n_samp;
     }
   }
@@ -412,7 +423,9 @@ template <int N, int MODE>
 static int launch_run_mode(const RunArgs& a_in, int phase, int write_state, cudaStream_t st) {
   RunArgs a = a_in;
   const int threads = 128;
-  a.group_blocks = (MODE != NB_MODE_WHFAST && a.n_heavy && a.perm) ? group_blocks_for<N>(a.B) : 0;
+  a.group_blocks = (MODE != NB_MODE_WHFAST && a.n_heavy && a.perm)
+                       ? ((phase == 0 && use_pairlane<N, MODE>()) ? pairlane_blocks_for<N>(a.B) : group_blocks_for<N>(a.B))
+                       : 0;
   const int blocks = a.group_blocks + (a.B + threads - 1) / threads;
   const bool exact = MODE == NB_MODE_WHFAST && (a.flags & NB_RUN_KEPLER_EXACT) != 0;
   if (phase == 0) {

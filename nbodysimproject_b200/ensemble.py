@@ -132,7 +132,7 @@ class DeviceBucket:
         torch = self.torch
         self.perm = torch.empty((self.B,), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
-            L.check(L.load().nb_sort_by_nsub(L.ptr(self.n_sub), self.B, L.ptr(self.perm), L.ptr(self._bins),
+            L.check(L.load().nb_sort_by_nsub(L.ptr(self.n_sub), self.B, self.N, L.ptr(self.perm), L.ptr(self._bins),
                                              L.stream_ptr()), "nb_sort_by_nsub")
 
     def run(self, dt, n_steps, sample_interval=0, n_megno=0, raw_dr=None, raw_dv=None, flags=0, want_dyn=True,

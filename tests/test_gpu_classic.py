@@ -215,11 +215,13 @@ def test_momentum_conservation_and_energy_order(E):
 
 
 def test_heavy_substep_mapping_matches_thread_mapping(E, O):
-    """Systems with n_sub > 4 run on the lane-per-body mapping (ensemble_group.cuh) when a sort permutation is
+    """Systems with n_sub > 4 run on the latency-optimised mappings (one body per lane, ensemble_group.cuh; one pair per
+    lane for N >= 5 in the main loop, ensemble_pairlane.cuh) when a sort permutation is
     given; without one everything runs thread-per-system.  Same arithmetic per body up to summation order."""
     import nbodysimproject_b200._lib as L
     rng = np.random.RandomState(17)
-    for N, mode in ((3, "verlet"), (4, "yoshida4"), (5, "yoshida4"), (7, "verlet"), (8, "yoshida4")):
+    for N, mode in ((3, "verlet"), (4, "yoshida4"), (5, "yoshida4"), (5, "verlet"), (6, "yoshida4"), (7, "verlet"),
+                    (8, "yoshida4")):
         B = 70
         m = rng.uniform(0.5, 5.0, (B, N))
         q = rng.randn(B, N, 2) * 1.5
@@ -231,6 +233,9 @@ def test_heavy_substep_mapping_matches_thread_mapping(E, O):
         v = rng.randn(B, N, 2) * 0.3
         rr, rv = rng.randn(B, N, 2), rng.randn(B, N, 2)
         res = {}
+        # force the fixed threshold 4 so that every N exercises its latency mapping (the automatic threshold keeps
+        # e.g. all N = 3 systems on the thread mapping, where the fast mapping gains nothing)
+        L.check(L.load().nb_ensemble_set_heavy_nsub(4))
         for use_sort in (False, True):
             bk = E.DeviceBucket(m, q, v, 0.3, 1.0, mode)
             bk.prepare(L.PREP_REMOVE_COM | L.PREP_CTOR_KICK, 0.01, 0.01, 0.01)
@@ -239,6 +244,7 @@ def test_heavy_substep_mapping_matches_thread_mapping(E, O):
             dyn = bk.run(0.01, 40, 2, 10, rr, rv, flags=L.RUN_ENERGY | L.RUN_WRITE_STATE)
             res[use_sort] = (bk.q.cpu().numpy(), bk.v.cpu().numpy(), dyn.cpu().numpy(), bk.n_sub.cpu().numpy(),
                              bk.status.cpu().numpy())
+        L.check(L.load().nb_ensemble_set_heavy_nsub(-1))
         nsub = res[True][3]
         assert (nsub > 4).sum() > 10 and (nsub <= 4).sum() >= 0
         assert np.all(res[True][4] == 0)
@@ -258,3 +264,33 @@ def test_heavy_substep_mapping_matches_thread_mapping(E, O):
             Y, lyap, _, _ = O.compute_megno(c, 10, 0.01, rr[b], rv[b])
             assert relerr(res[True][0][b], c.q) < 1e-11
             assert abs(res[True][2][b, L.DYN_COLUMNS.index("MEGNO")] - Y) < 1e-6 * abs(Y)
+
+
+def test_automatic_heavy_threshold_is_batch_dependent_and_result_invariant(E, O):
+    """nb_sort_by_nsub picks the heavy threshold from N, max n_sub and sum n_sub; whatever it picks, features agree
+    with a run that forces everything onto the thread mapping (threshold 63) to rounding."""
+    import nbodysimproject_b200._lib as L
+    rng = np.random.RandomState(5)
+    N, B = 6, 3000
+    m = rng.uniform(0.5, 5.0, (B, N))
+    q = rng.randn(B, N, 2) * 1.5
+    sep = 10 ** rng.uniform(-2.2, -0.5, B)
+    q[:, 1] = q[:, 0] + np.stack([sep, np.zeros(B)], 1)
+    v = rng.randn(B, N, 2) * 0.3
+    out = {}
+    for thr in (-1, 63):
+        L.check(L.load().nb_ensemble_set_heavy_nsub(thr))
+        bk = E.DeviceBucket(m, q, v, 0.3, 1.0, "yoshida4")
+        bk.prepare(L.PREP_REMOVE_COM | L.PREP_CTOR_KICK, 0.01, 0.01, 0.01)
+        bk.sort()
+        dyn = bk.run(0.01, 30, 3, 0, flags=L.RUN_ENERGY | L.RUN_WRITE_STATE)
+        out[thr] = (bk.q.cpu().numpy(), dyn.cpu().numpy(), int(bk._bins[64]), int(bk._bins[65]), bk.n_sub.cpu().numpy())
+    L.check(L.load().nb_ensemble_set_heavy_nsub(-1))
+    n_heavy, thr = out[-1][2], out[-1][3]
+    nsub = out[-1][4]
+    assert out[63][2] == 0 and out[63][3] == 63
+    assert 4 <= thr < 63 and n_heavy == int((nsub > thr).sum()) and n_heavy > 0
+    assert thr >= int(nsub.max() / 3.0)                     # N = 6: measured chain speed-up 3.0
+    light = nsub <= thr
+    assert np.array_equal(out[-1][0][light], out[63][0][light])
+    assert relerr(out[-1][0][~light], out[63][0][~light]) < 1e-9
