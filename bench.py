@@ -398,7 +398,11 @@ def impl_b200(args):
             best = min(best, a.elapsed_time(b) * 1e-3)
         ach = tot_fl / best * 1e-12
         roof = {"bound": "fp64", "kernel": "ensemble_main_kernel<N=3..8, yoshida4> (6 concurrent launches per step)",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of the six launches of one step (ncu, this workload at
+                # 2^20 systems per GPU: profiles/r1_main_kernels_dram.csv), scaled by the batch size
+                "traffic": 3.377e8 * (B_total / float(1 << 20)),
+                "traffic_note": "bytes per step over the six launches; the state is read once and lives in registers",
                 "flops_per_step": tot_fl, "ms": best * 1e3,
                 "peak_source": "nb_peak_flops(0): register-resident DFMA micro-benchmark, same GPU, same run "
                                "(MEASURED_PEAKS.json has no FP64 figure; nominal 64 DFMA/clk/SM x 148 x 1.965 GHz = 37.2)",
