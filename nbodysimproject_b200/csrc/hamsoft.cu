@@ -13,7 +13,8 @@
 // calibrate_from_initial_conditions), softening.py:86-131 (legacy gradient, sign reference),
 // barrier.py:35-113, hamiltonian_softening_integrator.py:145-296, 986-1221 (mu calibration, frozen schedule),
 // diagnostics.py:241-285, 457-549 (step_metrics, extended Hamiltonian).
-// Barrier policies: 0 = soft (shipped default), 2 = none (disable_barrier); the reflection policy is not built.
+// Barrier policies: 0 = soft (shipped default), 1 = reflection (fold eps into [eps_min, eps_max], flip pi;
+// hamsoft_utils.py:150-176), 2 = none (disable_barrier).
 #include "pair_small.cuh"
 #include "args.cuh"
 
@@ -328,12 +329,26 @@ struct HsState {
   double eps, pi;
 };
 
+// reflect_and_bounce(eps, pi, h = 0) = reflect_if_needed (hamsoft_barrier_controller.py:27-69, hamsoft_utils.py:105-176)
+__device__ __forceinline__ void hs_fold(double& eps, double& pi, const HsPar& P) {
+  if (P.policy != 1) return;
+  const double a = P.eps_min, b = P.eps_max;
+  const double R = b - a;
+  if (!is_finite(R) || R <= 0.0) { eps = a; pi = -pi; return; }
+  const double per = 2.0 * R;
+  double y = fmod(eps - a, per);                 // Python float modulo: result takes the sign of the divisor
+  if (y != 0.0) { if (y < 0.0) y += per; } else y = 0.0;
+  if (y <= R) { eps = a + y; }
+  else { eps = b - (y - R); pi = -pi; }
+}
+
 // S half-flow: hamsoft_stepper.py:47-88 -> spring_oscillation (live definition) hamsoft_flows.py:427-762
 template <int N>
 __device__ __forceinline__ void hs_s_half(HsState<N>& s, const HsPar& P, double h, int lane) {
   const double dt = 0.5 * h;
   double gx[N], gy[N];
   bool fb;
+  hs_fold(s.eps, s.pi, P);                       // hamsoft_stepper.py:107-113
   const double es = hs_eps_star_and_grad<N>(s.x, s.y, s.m, s.eps, P, lane, gx, gy, fb);
   const double k = P.k, mu = P.mu;
   const double om = (k > 0.0 && mu > 0.0) ? sqrt(k / mu) : 0.0;
@@ -382,6 +397,7 @@ __device__ __forceinline__ void hs_s_half(HsState<N>& s, const HsPar& P, double 
   }
   s.eps = eps_rot;
   s.pi = eta_t + kick2;
+  hs_fold(s.eps, s.pi, P);                       // hamsoft_stepper.py:72-80
 }
 
 // V half-kick: hamsoft_stepper.py:543-663 + pi_half_kick hamsoft_flows.py:1102-1132
@@ -419,12 +435,14 @@ __device__ __forceinline__ void hs_v_half(HsState<N>& s, const HsPar& P, double 
 
 template <int N>
 __device__ __forceinline__ void hs_strang(HsState<N>& s, const HsPar& P, double G, double h, int lane) {
+  hs_fold(s.eps, s.pi, P);                       // hamsoft_stepper.py:261-264
   hs_s_half<N>(s, P, h, lane);
   hs_v_half<N>(s, P, G, h);
 #pragma unroll
   for (int i = 0; i < N; ++i) { s.x[i] = fma(h, s.vx[i], s.x[i]); s.y[i] = fma(h, s.vy[i], s.y[i]); }
   hs_v_half<N>(s, P, G, h);
   hs_s_half<N>(s, P, h, lane);
+  hs_fold(s.eps, s.pi, P);                       // hamsoft_stepper.py:300-303
 }
 
 // diagnostics.py:457-549: T + V (double-double, each rounded to fp64) + pi^2/2mu + k/2 (eps-eps*)^2 + S_bar

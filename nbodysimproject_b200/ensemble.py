@@ -28,7 +28,10 @@ def _to_dev(a, dtype, device):
         return None
     if isinstance(a, torch.Tensor):
         return a.to(device=device, dtype=dtype).contiguous()
-    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device)
+    a = np.ascontiguousarray(a)
+    if not a.flags.writeable:            # e.g. np.broadcast_to views, npz members: torch wants a writable buffer
+        a = a.copy()
+    return torch.as_tensor(a, dtype=dtype).to(device)
 
 
 # ---------------------------------------------------------------------------------------------

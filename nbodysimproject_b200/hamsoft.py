@@ -22,10 +22,8 @@ def default_params(cfg, softening, min_softening, B=1):
     min_softening = np.broadcast_to(np.asarray(min_softening, dtype=np.float64), (B,))
     hs = np.zeros((B, L.N_HS))
     s0 = np.maximum(softening, min_softening)
-    soft = bool(getattr(cfg, "use_soft_barrier", True)) and not bool(getattr(cfg, "disable_barrier", False))
-    if not soft and not bool(getattr(cfg, "disable_barrier", False)):
-        raise L.NBodyB200Error("ham_soft barrier policy 'reflection' is not built; use use_soft_barrier=True "
-                               "(the shipped default) or disable_barrier=True")
+    disabled = bool(getattr(cfg, "disable_barrier", False))
+    soft = bool(getattr(cfg, "use_soft_barrier", True)) and not disabled
     alpha = getattr(cfg, "alpha", 0.1)
     hs[:, P["k_soft"]] = float(getattr(cfg, "k_soft", 1.0e3))
     hs[:, P["mu_soft"]] = 1.0
@@ -37,7 +35,8 @@ def default_params(cfg, softening, min_softening, B=1):
     hs[:, P["eta"]] = float(getattr(cfg, "eta", 1.35))
     hs[:, P["j_max_cap"]] = float(getattr(cfg, "j_max_cap", 0.02))
     hs[:, P["lambda"]] = float(getattr(cfg, "lambda_softening", 0.3))
-    hs[:, P["policy"]] = 0.0 if soft else 2.0
+    # hamiltonian_softening_integrator.py:96-108: 0 soft barrier, 1 reflection (fold), 2 barrier disabled
+    hs[:, P["policy"]] = 0.0 if soft else (2.0 if disabled else 1.0)
     hs[:, P["theta_imp"]] = float(getattr(cfg, "theta_imp", 0.5))
     hs[:, P["theta_cap"]] = float(getattr(cfg, "theta_cap", 0.1))
     hs[:, P["chi_pi"]] = float(getattr(cfg, "chi_pi", 0.2))

@@ -101,3 +101,45 @@ def test_hamsoft_batch_matches_single_and_oracle():
             o.step(0.01)
         assert relerr(qa[i], o.q) < 1e-8
         assert abs(ea[i, 0] - o.eps) < 1e-8 * abs(o.eps)
+
+
+def test_hamsoft_barrier_policies_vs_golden():
+    """Reflection fold and disabled barrier (hamsoft_utils.py:150-176, hamsoft_stepper.py:72-80, 107-113, 261-303) against
+    the live reference's outputs; the 'tight' cases fold epsilon at both walls of a squeezed [eps_min, eps_max]."""
+    from nbodysimproject_b200 import hamsoft as H, ensemble as E, _lib as L
+    from nbodysimproject_b200.simulation import SimConfig
+    from nbodysimproject_b200.hamsoft import P
+    g = load_golden("hamsoft_policies.npz")
+    dt = float(g["dt"])
+    for key in g["names"]:
+        key = str(key)
+        use_soft, disabled = [bool(x) for x in g[key + "flags"]]
+        m, q, v, soft = g[key + "m"], g[key + "q_in"], g[key + "v_in"], float(g[key + "soft"])
+        bk0 = E.DeviceBucket(m[None], q[None], v[None], soft, 1.0, "verlet")
+        bk0.prepare(L.PREP_REMOVE_COM, 0.0, 0.01, 0.01)
+        cfg = SimConfig()
+        cfg.use_soft_barrier, cfg.disable_barrier = use_soft, disabled
+        hs, s0 = H.default_params(cfg, soft, 0.1 * soft)
+        assert hs[0, P["policy"]] == (2.0 if disabled else 1.0)
+        b = H.HamSoftBucket(m[None], q[None], bk0.v.cpu().numpy(), hs, np.array([[s0[0], 0.0]]), 1.0)
+        b.setup(calibrate=True, freeze_dt=0.01)
+        ctor = g[key + "ctor"]
+        if "tight" in key:
+            b.hs[0, P["eps_min"]] = float(ctor[2])
+            b.hs[0, P["eps_max"]] = float(ctor[3])
+        hsv, ep = b.hs.cpu().numpy()[0], b.eps_pi.cpu().numpy()[0]
+        mine = np.array([ep[0], ep[1], hsv[P["eps_min"]], hsv[P["eps_max"]], hsv[P["alpha_run"]], hsv[P["k_soft"]],
+                         hsv[P["mu_soft"]], float(b.n_sub[0]), hsv[P["omega_spr0"]]])
+        assert np.allclose(mine, ctor, rtol=1e-12, atol=0), (key, mine, ctor)
+        done = 0
+        for mark in g[key + "marks"]:
+            mark = int(mark)
+            b.run(dt, mark - done)
+            done = mark
+            ep = b.eps_pi.cpu().numpy()[0]
+            ref = g[key + f"ep{mark}"]
+            assert relerr(b.bk.q.cpu().numpy()[0], g[key + f"q{mark}"]) < 1e-8, (key, mark)
+            assert abs(ep[0] - ref[0]) <= 1e-7 * abs(ref[0]), (key, mark, ep, ref)
+            assert abs(ep[1] - ref[1]) <= 1e-5 * max(abs(ref[1]), 1e-6), (key, mark, ep, ref)
+            if not disabled:
+                assert hsv[P["eps_min"]] <= ep[0] <= hsv[P["eps_max"]]

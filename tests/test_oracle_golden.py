@@ -173,3 +173,42 @@ def test_largen_hamsoft_oracle_dense_equals_pinned_loops():
             a.step(0.01)
             b.step(0.01)
         assert np.max(np.abs(a.q - b.q)) <= 1e-12 and abs(a.eps - b.eps) <= 1e-13 and abs(a.pi - b.pi) <= 1e-12
+
+
+def test_hamsoft_barrier_policies_vs_golden():
+    """Reflection fold (hamsoft_utils.py:150-176) and disabled barrier against the live reference
+    (oracle/make_golden_hamsoft_policy.py).  The 'tight' cases squeeze [eps_min, eps_max] so that epsilon is folded
+    at both walls within a few steps."""
+    from oracle.hamsoft_oracle import HamSoftOracleSim
+    g = load_golden("hamsoft_policies.npz")
+    dt = float(g["dt"])
+    n_checked = 0
+    for key in g["names"]:
+        key = str(key)
+        if key.startswith("compact_s0.3") or key.startswith("compact6"):
+            continue        # n_sub = 13 / 8 with N = 4 / 6: left to the GPU test (same goldens), too slow here
+        use_soft, disabled = [bool(x) for x in g[key + "flags"]]
+        sim = HamSoftOracleSim(g[key + "m"], g[key + "q_in"], g[key + "v_in"], softening=float(g[key + "soft"]),
+                               use_soft_barrier=use_soft, disable_barrier=disabled)
+        ctor = g[key + "ctor"]
+        if "tight" in key:
+            sim.eps_min, sim.eps_max = float(ctor[2]), float(ctor[3])
+        mine = np.array([sim.eps, sim.pi, sim.eps_min, sim.eps_max, sim.alpha_run, sim.k_soft, sim.mu_soft,
+                         sim.frozen_n_sub, sim.omega_spr0])
+        assert np.allclose(mine, ctor, rtol=1e-14, atol=0), key
+        assert sim.extended_hamiltonian() == pytest.approx(float(g[key + "H0"]), rel=1e-13)
+        done = 0
+        for mark in g[key + "marks"]:
+            mark = int(mark)
+            for _ in range(mark - done):
+                sim.step(dt)
+            done = mark
+            ep = g[key + f"ep{mark}"]
+            assert relerr(sim.q, g[key + f"q{mark}"]) < 1e-11, (key, mark)
+            assert abs(sim.eps - ep[0]) <= 1e-10 * abs(ep[0]), (key, mark, sim.eps, ep[0])
+            assert abs(sim.pi - ep[1]) <= 1e-8 * max(abs(ep[1]), 1e-6), (key, mark, sim.pi, ep[1])
+            assert sim.extended_hamiltonian() == pytest.approx(float(g[key + f"H{mark}"]), rel=1e-9)
+        if "reflection" in key:
+            assert sim.eps_min <= sim.eps <= sim.eps_max
+        n_checked += 1
+    assert n_checked >= 6
