@@ -122,6 +122,17 @@ int nb_ensemble_run_f64(const double* m, double* q, double* v, const double* eps
                         double* eps_pi, const double* hs_params,
                         double* dyn_features, int32_t* status, void* stream);
 
+/* ---- classic ADAPTIVE softening (adaptive_softening=True with verlet / yoshida4): n_steps macro steps in which the
+ *      softening is re-derived from the minimum separation after every sub-step (integrator.py:126-136, 204-225;
+ *      SofteningManager.softening_from_min_sep / refresh_softening / _compute_energy_correction,
+ *      softening_manager.py:298-336, 423-471, 541-547).  eps[B] = manager.s (in/out); soft_par[B][3] = {s0,
+ *      min_softening, softening_scale}; energy_delta[B] = sim.softening_energy_delta (in/out, may be NULL);
+ *      eps_hist[B][n_steps] = softening after each macro step (may be NULL).  q, v advance in place. */
+int nb_ensemble_run_adaptive_f64(const double* m, double* q, double* v, double* eps, const double* soft_par, double G,
+                                 int B, int N, int mode, double dt, int n_steps, const int32_t* n_sub, double k_wall,
+                                 int barrier_exponent, double* energy_delta, double* eps_hist, int32_t* status,
+                                 void* stream);
+
 /* ---- a11/a14 ham_soft construction-time calibration, one thread per system, in place on hs_params / eps_pi:
  *      flags bit0: EpsilonModel.calibrate_from_initial_conditions (hamsoft_eps_model.py:645-729: alpha_run,
  *                  eps_min, eps0) + _calibrate_mu_from_timescales (hamiltonian_softening_integrator.py:251-296);

@@ -27,6 +27,9 @@ int variational_batched(const double* q, const double* m, const double* s2, cons
                         double* da, cudaStream_t st);
 int sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* ws, cudaStream_t st);
 int set_heavy_nsub(int thr);
+int ensemble_run_adaptive(const double* m, double* q, double* v, double* eps, const double* soft_par, double G, int B,
+                          int N, int mode, double dt, int n_steps, const int32_t* n_sub, double k_wall, int n_exp,
+                          double* e_delta, double* eps_hist, int32_t* status, cudaStream_t st);
 int largeN_accel(const float* xym, int n_total, int i0, int ni, float eps, float G, float* acc, double* sums,
                  cudaStream_t st);
 int largeN_set_variant(int variant);
@@ -261,6 +264,14 @@ int nb_hamsoft_probe_f64(const double* m, const double* q, const double* v, doub
 }
 
 int nb_ensemble_set_heavy_nsub(int threshold) { return set_heavy_nsub(threshold); }
+
+int nb_ensemble_run_adaptive_f64(const double* m, double* q, double* v, double* eps, const double* soft_par, double G,
+                                 int B, int N, int mode, double dt, int n_steps, const int32_t* n_sub, double k_wall,
+                                 int barrier_exponent, double* energy_delta, double* eps_hist, int32_t* status,
+                                 void* stream) {
+  return ensemble_run_adaptive(m, q, v, eps, soft_par, G, B, N, mode, dt, n_steps, n_sub, k_wall, barrier_exponent,
+                               energy_delta, eps_hist, status, (cudaStream_t)stream);
+}
 
 int nb_sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* workspace, void* stream) {
   if (!n_sub || !perm || !workspace || B < 0) { set_error("nb_sort_by_nsub: bad arguments"); return NB_ERR_ARG; }

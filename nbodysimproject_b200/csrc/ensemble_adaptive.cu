@@ -1,0 +1,174 @@
+// ensemble_adaptive.cu -- classic ADAPTIVE softening for verlet / yoshida4 ensembles.
+//
+// Reference flow (integrator.py:78-136, 200-227; softening_manager.py:186-199, 246-257, 298-336, 423-471, 541-547):
+// after EVERY sub-step the softening is re-derived from the current minimum separation,
+//     eps_new = clamp(max(eps_min, r_min / softening_scale), <= 10 s0), limited to [eps/2, 2 eps],
+// the potential-energy jump G sum_{i<j} m_i m_j (1/rho_new - 1/rho_old) (+ the barrier-energy difference) is booked
+// into softening_energy_delta, and the following force evaluations use the new epsilon.  One thread per system,
+// state in registers like the fixed-softening kernel; because epsilon changes between sub-steps the first
+// acceleration of a sub-step is re-evaluated (the FSAL reuse is only valid inside a sub-step).
+#include "pair_small.cuh"
+#include "args.cuh"
+
+namespace nb {
+
+struct AdaptArgs {
+  const double* m;
+  double* q;
+  double* v;
+  double* eps;              // [B] current softening manager.s, in/out
+  const double* soft_par;   // [B][3]: s0, min_softening, softening_scale
+  double G;
+  int B;
+  double dt;
+  int n_steps;
+  const int32_t* n_sub;
+  double k_wall;
+  int n_exp;
+  double* e_delta;          // [B] softening_energy_delta, in/out
+  double* eps_hist;         // [B][n_steps] softening after each macro step (optional)
+  int32_t* status;
+};
+
+__device__ __forceinline__ double barrier_energy_dev(double eps, double a, double b, double k_wall, int n) {  // barrier.py:35-63
+  if (!(is_finite(k_wall) && k_wall > 0.0 && n >= 2)) return 0.0;
+  if (b < a) { const double t = a; a = b; b = t; }
+  const int p = n - 1;
+  const double l = fmax(0.0, a - eps), r = fmax(0.0, eps - b);
+  double lp = 1.0, rp = 1.0;
+  for (int i = 0; i < p; ++i) { lp *= l; rp *= r; }
+  return (k_wall / (double)p) * (lp + rp);
+}
+
+template <int N, int MODE>
+__global__ void __launch_bounds__(128) ensemble_adaptive_kernel(AdaptArgs a) {
+  const int sys = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sys >= a.B) return;
+  SysState<N> s;
+  double m[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    m[i] = a.m[(size_t)sys * N + i];
+    s.gm[i] = a.G * m[i];
+    s.x[i] = a.q[((size_t)sys * N + i) * 2 + 0];
+    s.y[i] = a.q[((size_t)sys * N + i) * 2 + 1];
+    s.vx[i] = a.v[((size_t)sys * N + i) * 2 + 0];
+    s.vy[i] = a.v[((size_t)sys * N + i) * 2 + 1];
+  }
+  double soft = a.eps[sys];
+  const double s0 = a.soft_par[(size_t)sys * 3 + 0], eps_min = a.soft_par[(size_t)sys * 3 + 1];
+  const double scale = a.soft_par[(size_t)sys * 3 + 2];
+  const double eps_cap = 10.0 * s0;
+  double e_delta = a.e_delta ? a.e_delta[sys] : 0.0;
+  const int n_sub = a.n_sub ? max(1, a.n_sub[sys]) : 1;
+  const double h = a.dt / (double)n_sub;
+  const double cbrt2 = 1.2599210498948731648;
+  const double ha = (1.0 / (2.0 - cbrt2)) * h, hb = (-cbrt2 / (2.0 - cbrt2)) * h;
+
+  auto vkernel = [&](double hh) {     // integration_scheme_base.py:129-149 with the start acceleration already in s.ax/ay
+    const double h2 = 0.5 * hh;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { s.vx[i] = fma(h2, s.ax[i], s.vx[i]); s.vy[i] = fma(h2, s.ay[i], s.vy[i]); }
+#pragma unroll
+    for (int i = 0; i < N; ++i) { s.x[i] = fma(hh, s.vx[i], s.x[i]); s.y[i] = fma(hh, s.vy[i], s.y[i]); }
+    pair_pass<N, false, true>(s, nullptr, nullptr, nullptr, nullptr);
+#pragma unroll
+    for (int i = 0; i < N; ++i) { s.vx[i] = fma(h2, s.ax[i], s.vx[i]); s.vy[i] = fma(h2, s.ay[i], s.vy[i]); }
+  };
+
+  for (int step = 0; step < a.n_steps; ++step) {
+    double pending = 0.0;                                   // begin_step
+#pragma unroll 1
+    for (int k = 0; k < n_sub; ++k) {
+      const double ef = sqrt(soft * soft);                  // simulation.py:539-581: eps = sqrt(manager.step_s2)
+      s.eps2 = ef * ef;
+      pair_pass<N, false, true>(s, nullptr, nullptr, nullptr, nullptr);
+      if (MODE == NB_MODE_YOSHIDA4) { vkernel(ha); vkernel(hb); vkernel(ha); }
+      else vkernel(h);
+      // ---- refresh_softening(softening_from_min_sep(min separation))
+      double r2min = __longlong_as_double(0x7ff0000000000000LL);
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = i + 1; j < N; ++j) {
+          const double dx = s.x[i] - s.x[j], dy = s.y[i] - s.y[j];
+          r2min = fmin(r2min, dx * dx + dy * dy);
+        }
+      const double min_sep = fmax(sqrt(r2min), 1e-12);      // simulation.py:659-665
+      double eps_new = soft;
+      if (is_finite(min_sep) && min_sep > 0.0) {
+        double prop = fmax(eps_min, min_sep / scale);
+        prop = fmin(prop, eps_cap);
+        eps_new = fmax(soft / 2.0, fmin(soft * 2.0, prop));
+      }
+      if (eps_new != soft && is_finite(soft) && is_finite(eps_new)) {     // softening_manager.py:423-471
+        double dE = 0.0;
+        const double e2o = soft * soft, e2n = eps_new * eps_new;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+          for (int j = i + 1; j < N; ++j) {
+            const double dx = s.x[i] - s.x[j], dy = s.y[i] - s.y[j];
+            const double r2 = dx * dx + dy * dy;
+            const double wn = rsqrt_f64<true>(r2 + e2n), wo = rsqrt_f64<true>(r2 + e2o);
+            dE = fma(m[i] * m[j], wn - wo, dE);
+          }
+        dE *= a.G;
+        dE += barrier_energy_dev(eps_new, eps_min, eps_cap, a.k_wall, a.n_exp) -
+              barrier_energy_dev(soft, eps_min, eps_cap, a.k_wall, a.n_exp);
+        if (is_finite(dE)) pending += dE;
+      }
+      soft = eps_new;
+      if (pending != 0.0) { e_delta += pending; pending = 0.0; }          // commit_substep
+    }
+    if (a.eps_hist) a.eps_hist[(size_t)sys * a.n_steps + step] = soft;
+  }
+  bool finite = true;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    finite = finite && is_finite(s.x[i]) && is_finite(s.y[i]) && is_finite(s.vx[i]) && is_finite(s.vy[i]);
+    a.q[((size_t)sys * N + i) * 2 + 0] = s.x[i];
+    a.q[((size_t)sys * N + i) * 2 + 1] = s.y[i];
+    a.v[((size_t)sys * N + i) * 2 + 0] = s.vx[i];
+    a.v[((size_t)sys * N + i) * 2 + 1] = s.vy[i];
+  }
+  a.eps[sys] = soft;
+  if (a.e_delta) a.e_delta[sys] = e_delta;
+  if (a.status) a.status[sys] = finite ? 0 : NB_STATUS_NONFINITE;
+}
+
+template <int MODE>
+static int launch_adaptive(const AdaptArgs& a, int N, cudaStream_t st) {
+  const int threads = 128, blocks = (a.B + threads - 1) / threads;
+  switch (N) {
+    case 2: ensemble_adaptive_kernel<2, MODE><<<blocks, threads, 0, st>>>(a); break;
+    case 3: ensemble_adaptive_kernel<3, MODE><<<blocks, threads, 0, st>>>(a); break;
+    case 4: ensemble_adaptive_kernel<4, MODE><<<blocks, threads, 0, st>>>(a); break;
+    case 5: ensemble_adaptive_kernel<5, MODE><<<blocks, threads, 0, st>>>(a); break;
+    case 6: ensemble_adaptive_kernel<6, MODE><<<blocks, threads, 0, st>>>(a); break;
+    case 7: ensemble_adaptive_kernel<7, MODE><<<blocks, threads, 0, st>>>(a); break;
+    case 8: ensemble_adaptive_kernel<8, MODE><<<blocks, threads, 0, st>>>(a); break;
+    default: set_error("N must be in 2..8"); return NB_ERR_ARG;
+  }
+  NB_CUDA_CHECK(cudaGetLastError());
+  return NB_OK;
+}
+
+int ensemble_run_adaptive(const double* m, double* q, double* v, double* eps, const double* soft_par, double G, int B,
+                          int N, int mode, double dt, int n_steps, const int32_t* n_sub, double k_wall, int n_exp,
+                          double* e_delta, double* eps_hist, int32_t* status, cudaStream_t st) {
+  if (!m || !q || !v || !eps || !soft_par || B < 0 || n_steps < 0) {
+    set_error("nb_ensemble_run_adaptive_f64: bad arguments");
+    return NB_ERR_ARG;
+  }
+  if (mode != NB_MODE_VERLET && mode != NB_MODE_YOSHIDA4) {
+    set_error("nb_ensemble_run_adaptive_f64: adaptive softening exists for verlet and yoshida4 (the reference turns whfast "
+              "into verlet, simulation.py:103-107; ham_soft has its own epsilon flow)");
+    return NB_ERR_UNSUPPORTED;
+  }
+  if (B == 0) return NB_OK;
+  AdaptArgs a{m, q, v, eps, soft_par, G, B, dt, n_steps, n_sub, k_wall, n_exp, e_delta, eps_hist, status};
+  return mode == NB_MODE_YOSHIDA4 ? launch_adaptive<NB_MODE_YOSHIDA4>(a, N, st) : launch_adaptive<NB_MODE_VERLET>(a, N, st);
+}
+
+}  // namespace nb

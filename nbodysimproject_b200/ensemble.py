@@ -214,3 +214,31 @@ def advance_bucket(m, q, v, eps, h_sub_ref, G=1.0, mode="verlet", dt=0.01, n_ste
     flags = L.RUN_WRITE_STATE | (L.RUN_KEPLER_EXACT if kepler_exact else 0)
     bk.run(dt, n_steps, 0, 0, flags=flags, want_dyn=False)
     return bk.q.cpu().numpy(), bk.v.cpu().numpy(), bk.status.cpu().numpy()
+
+
+def advance_bucket_adaptive(m, q, v, eps, s0, min_softening, softening_scale, h_sub_ref, G=1.0, mode="verlet", dt=0.01,
+                            n_steps=1, split_n_max=50, k_wall=1.0e9, barrier_exponent=5, energy_delta=None, device=None):
+    """n_steps x NBodySimulation(adaptive_softening=True).step(dt) for B same-N systems (classic adaptive softening,
+    softening_manager.py:298-336, 423-471, 541-547): returns q, v, eps_after_each_step[B, n_steps],
+    softening_energy_delta[B], status[B]."""
+    torch = L.require_cuda()
+    dev = _dev(device)
+    m_d = _to_dev(m, torch.float64, dev)
+    q_d = _to_dev(q, torch.float64, dev).clone()
+    v_d = _to_dev(v, torch.float64, dev).clone()
+    B, N = int(m_d.shape[0]), int(m_d.shape[1])
+    bc = lambda x: np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), (B,)))
+    eps_d = _to_dev(bc(eps), torch.float64, dev).clone()
+    par = _to_dev(np.stack([bc(s0), bc(min_softening), bc(softening_scale)], 1), torch.float64, dev)
+    h = _to_dev(bc(h_sub_ref), torch.float64, dev)
+    n_sub = torch.clamp(torch.ceil(abs(float(dt)) / h), 1, int(split_n_max)).to(torch.int32).contiguous()
+    e_d = _to_dev(bc(0.0 if energy_delta is None else energy_delta), torch.float64, dev).clone()
+    hist = torch.empty((B, int(n_steps)), dtype=torch.float64, device=dev)
+    status = torch.zeros((B,), dtype=torch.int32, device=dev)
+    imode = L.MODES[mode] if isinstance(mode, str) else int(mode)
+    with torch.cuda.device(dev):
+        L.check(L.load().nb_ensemble_run_adaptive_f64(
+            L.ptr(m_d), L.ptr(q_d), L.ptr(v_d), L.ptr(eps_d), L.ptr(par), float(G), B, N, imode, float(dt), int(n_steps),
+            L.ptr(n_sub), float(k_wall), int(barrier_exponent), L.ptr(e_d), L.ptr(hist), L.ptr(status), L.stream_ptr()),
+            "nb_ensemble_run_adaptive_f64")
+    return (q_d.cpu().numpy(), v_d.cpu().numpy(), hist.cpu().numpy(), e_d.cpu().numpy(), status.cpu().numpy())

@@ -181,9 +181,6 @@ class NBodySimulation:
         if not self._build_state(bodies, masses, positions, velocities):
             self._disable_simulation()
             return
-        if self._adaptive_softening or self._adaptive_timestep:
-            raise L.NBodyB200Error("classic adaptive softening / adaptive dt is not on the B200 hot path "
-                                   "(SURVEY.md section 8f); use fixed-step modes or ham_soft")
         min_softening = max(0.0, min_softening)
         if softening < 0.0:
             softening = min_softening
@@ -198,7 +195,9 @@ class NBodySimulation:
         if self.G == 0.0 and self._integrator_mode != "ham_soft":
             self._integrator_mode = "verlet"
         if self._integrator_mode == "whfast" and self.n_bodies > 0:
-            if np.max(self._mass) / np.sum(self._mass) < 0.2:
+            if self._adaptive_softening:                                 # simulation.py:104-107
+                self._integrator_mode = "verlet"
+            elif np.max(self._mass) / np.sum(self._mass) < 0.2:
                 self._integrator_mode = "verlet"
         self.manager = SofteningManager(self, softening, self._min_softening)
         self._max_softening = 10.0 * self.manager.s0
@@ -227,7 +226,8 @@ class NBodySimulation:
             self._integrator = _ClassicIntegrator(self, self.cfg.split_n_max)
             self._integrator._top_dt = getattr(self.cfg, "initial_dt", self.cfg.max_fraction_of_dt)
             flags = L.PREP_REMOVE_COM if remove_com else 0
-            if not skip_init_corrector and self.G != 0.0 and int(self.cfg.corrector_order) > 0:
+            if (not skip_init_corrector and self.G != 0.0 and int(self.cfg.corrector_order) > 0
+                    and not self._adaptive_softening and not self._adaptive_timestep):     # simulation.py:150-157
                 flags |= L.PREP_CTOR_KICK
             self._prepare(flags, float(self._integrator._top_dt), schedule=True)
 
@@ -355,6 +355,31 @@ class NBodySimulation:
         else:
             integ = self._integrator
             integ._top_dt = abs(dt)
+            if self._adaptive_softening and self.n_bodies >= 2 and self.G != 0.0:
+                # classic adaptive softening: epsilon follows the minimum separation after every sub-step
+                # (integrator.py:126-136, 204-225; softening_manager.py:298-336, 423-471, 541-547)
+                mgr = self.manager
+                q, v, hist, dE, st = E.advance_bucket_adaptive(
+                    self._mass[None], self._pos[None], self._vel[None], mgr.s, mgr.s0, self._min_softening,
+                    float(self._softening_scale), np.array([integ.h_sub_ref]), self.G, self._integrator_mode, dt,
+                    int(n_steps), integ.split_n_max, float(getattr(self.cfg, "k_wall", 1.0e9)),
+                    int(getattr(self.cfg, "barrier_exponent", 5)), self.softening_energy_delta, self.device)
+                self._pos[...] = q[0]
+                self._vel[...] = v[0]
+                self._status |= int(st[0])
+                # begin_step records the softening each macro step STARTS with (softening_manager.py:186-199)
+                starts = [mgr.s] + [float(x) for x in hist[0][:-1]]
+                for x in starts[-1024:]:
+                    mgr._history.append(x)
+                mgr.s = float(hist[0][-1])
+                mgr._step_s2 = mgr.s * mgr.s
+                self.softening_energy_delta = float(dE[0])
+                integ._substeps_in_last_step = integ.n_sub_for(dt)
+                mgr.finish_step()
+                self._has_integrated = True
+                self._acc_cached = False
+                self._last_dt = dt
+                return
             for _ in range(min(int(n_steps), 1024)):
                 self.manager.begin_step()
             if self.n_bodies >= 2:

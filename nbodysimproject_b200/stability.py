@@ -188,6 +188,10 @@ def analyze_simulations(sims, n_steps: int, dt: float, mode: str, via: str = "de
         if s.n_bodies < 2:
             rows[i] = {"is_stable": float("nan"), "mode": mode}
             continue
+        if getattr(s, "_adaptive_softening", False) and _mode_of(s) != "ham_soft":
+            raise L.NBodyB200Error("stability analysis of classic adaptive-softening simulations is not built: the "
+                                   "adaptive path covers NBodySimulation.step / nb_ensemble_run_adaptive_f64 "
+                                   "(SURVEY.md section 8f item 1); analyse with fixed softening or ham_soft")
         buckets.setdefault((s.n_bodies, _mode_of(s), float(s.G), str(s.device)), []).append(i)
     for (N, imode, G, _dev), idx in buckets.items():
         group = [sims[i] for i in idx]

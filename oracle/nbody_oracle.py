@@ -260,13 +260,24 @@ YOSHIDA_W2 = -_CBRT2 / (2.0 - _CBRT2)
 # --------------------------------------------------------------------------
 
 
+def _barrier_energy(eps, a, b, k_wall=1.0e9, n=5):
+    """barrier.py:35-63."""
+    if not (np.isfinite(k_wall) and k_wall > 0.0 and n >= 2):
+        return 0.0
+    if b < a:
+        a, b = b, a
+    p = n - 1
+    return float((k_wall / float(p)) * (max(0.0, a - eps) ** p + max(0.0, eps - b) ** p))
+
+
 class OracleSim:
     """Restates NBodySimulation for integrator_mode in {verlet, yoshida4, whfast}
     (simulation.py:39-162 ctor, :667-676 step, :319-326 commit_state/snapshot kick)."""
 
     def __init__(self, masses, positions, velocities=None, G=1.0, softening=1e-3, min_softening=0.0,
                  integrator_mode="verlet", skip_init_corrector=False, skip_cm_recenter=False,
-                 initial_dt=0.01, split_n_max=50, corrector_order=5):
+                 initial_dt=0.01, split_n_max=50, corrector_order=5, adaptive_softening=False, adaptive_timestep=None,
+                 softening_scale=1.0, k_wall=1.0e9, barrier_exponent=5):
         m = np.asarray(list(masses), dtype=np.float64)
         q = np.asarray(list(positions), dtype=np.float64).reshape(-1, 2).copy()
         if velocities is None or len(velocities) == 0:
@@ -287,10 +298,22 @@ class OracleSim:
         self.min_softening = float(min_softening)
         self.G = float(G)
         mode = str(integrator_mode)
+        # simulation.py:62-74: adaptive softening implies the adaptive-timestep flag (whose only live effect is
+        # that the constructor corrector is skipped, :150-157)
+        self.adaptive_softening = bool(adaptive_softening)
+        self.adaptive_timestep = bool(adaptive_timestep) if adaptive_timestep is not None else False
+        if self.adaptive_softening:
+            self.adaptive_timestep = True
+        self.softening_scale = float(softening_scale)
+        self.k_wall, self.barrier_exponent = float(k_wall), int(barrier_exponent)
+        self.softening_energy_delta = 0.0
+        self.pending_energy_delta = 0.0
         if self.G == 0.0 and mode != "ham_soft":                    # :101-102
             mode = "verlet"
         if mode == "whfast" and self.n > 0:                         # :103-111
-            if np.max(self.m) / np.sum(self.m) < 0.2:
+            if self.adaptive_softening:
+                mode = "verlet"
+            elif np.max(self.m) / np.sum(self.m) < 0.2:
                 mode = "verlet"
         self.s0 = float(max(softening, self.min_softening))         # softening_manager.py:48
         self.s = self.s0
@@ -306,7 +329,8 @@ class OracleSim:
         self.top_dt = self.initial_dt                               # :148
         self.history = [self.s]
         self.force_evals = 0
-        if not skip_init_corrector and self.G != 0.0:               # :150-157
+        if (not skip_init_corrector and self.G != 0.0 and not self.adaptive_softening
+                and not self.adaptive_timestep):                    # :150-157
             self.apply_corrector()
 
     # -- force -------------------------------------------------------------
@@ -447,7 +471,8 @@ class OracleSim:
         self.top_dt = abs(dt)
         n_sub = self.n_sub_for(dt)
         h = dt / n_sub
-        self.step_s2 = self.s ** 2                                   # begin_step
+        self.step_s2 = self.s ** 2                                   # begin_step (softening_manager.py:186-199)
+        self.pending_energy_delta = 0.0
         self.history.append(self.s)
         if len(self.history) > 1024:
             self.history = self.history[-1024:]
@@ -460,6 +485,60 @@ class OracleSim:
                 self._wisdom_holman(h)
             else:
                 self._verlet_kernel(h)
+            if self.adaptive_softening:                              # integrator.py:126-136, 204-225
+                self.refresh_softening(self.softening_from_min_sep(self.min_separation()))
+            if self.pending_energy_delta != 0.0:                     # commit_substep (softening_manager.py:246-257)
+                self.softening_energy_delta = self.softening_energy_delta + self.pending_energy_delta
+                self.pending_energy_delta = 0.0
+
+    # -- classic adaptive softening (softening_manager.py:298-336, 423-471, 541-547) ------------------
+    def min_separation(self):
+        """simulation.py:659-665."""
+        if self.n < 2:
+            return float("inf")
+        d = self.q[:, None, :] - self.q[None, :, :]
+        d2 = (d ** 2).sum(axis=-1)
+        np.fill_diagonal(d2, np.inf)
+        return max(float(d2.min()) ** 0.5, 1e-12)
+
+    def softening_from_min_sep(self, min_sep):
+        if not math.isfinite(min_sep) or min_sep <= 0.0:
+            return self.s
+        proposed = max(self.min_softening, min_sep / self.softening_scale)
+        proposed = min(proposed, 10.0 * self.s0)
+        return max(self.s / 2.0, min(self.s * 2.0, proposed))       # _limited_softening, factor 2
+
+    def energy_correction(self, eps_old, eps_new):
+        """softening_manager.py:423-471 for the classic integrators (k_soft = 0: no spring term)."""
+        if eps_old == eps_new:
+            return 0.0
+        dE = 0.0
+        if self.n >= 2 and self.G != 0.0:
+            diff = self.q[:, None, :] - self.q[None, :, :]
+            r2 = np.einsum("ijk,ijk->ij", diff, diff, optimize=True)
+            np.fill_diagonal(r2, np.inf)
+            inv_old = 1.0 / np.sqrt(r2 + eps_old ** 2)
+            inv_new = 1.0 / np.sqrt(r2 + eps_new ** 2)
+            np.fill_diagonal(inv_old, 0.0)
+            np.fill_diagonal(inv_new, 0.0)
+            iu, ju = np.triu_indices(self.n, 1)
+            dE += self.G * float(np.sum(self.m[iu] * self.m[ju] * (inv_new[iu, ju] - inv_old[iu, ju])))
+        dE += (_barrier_energy(eps_new, self.min_softening, 10.0 * self.s0, self.k_wall, self.barrier_exponent)
+               - _barrier_energy(eps_old, self.min_softening, 10.0 * self.s0, self.k_wall, self.barrier_exponent))
+        return float(dE)
+
+    def refresh_softening(self, eps_new):
+        eps_old, eps_new = float(self.s), float(eps_new)
+        dE = 0.0
+        if math.isfinite(eps_old) and math.isfinite(eps_new):
+            val = self.energy_correction(eps_old, eps_new)
+            if math.isfinite(val):
+                dE = val
+        self.pending_energy_delta = self.pending_energy_delta + dE
+        self.s = eps_new
+        self.step_s2 = eps_new * eps_new
+        # softening_manager.py:331-335 appends to `self.history`, a property that returns a COPY of the deque: the
+        # append is lost, so only begin_step records history entries
 
     # -- snapshot / restore ------------------------------------------------------------
     def snapshot_restore(self):

@@ -212,3 +212,34 @@ def test_hamsoft_barrier_policies_vs_golden():
             assert sim.eps_min <= sim.eps <= sim.eps_max
         n_checked += 1
     assert n_checked >= 6
+
+
+def test_adaptive_softening_oracle_vs_golden():
+    """Classic adaptive softening (softening_manager.py:298-336, 423-471, 541-547; integrator.py:126-136, 204-225):
+    epsilon after every step, the accumulated softening_energy_delta, history and trajectories against the live
+    reference (oracle/make_golden_adaptive.py)."""
+    from oracle import nbody_oracle as O
+    g = load_golden("adaptive_softening.npz")
+    dt = float(g["dt"])
+    for key in g["names"]:
+        key = str(key)
+        mode = key.split("__")[1].rstrip("_")
+        sim = O.OracleSim(g[key + "m"], g[key + "q_in"], g[key + "v_in"], softening=float(g[key + "soft"]),
+                          integrator_mode=mode, adaptive_softening=True)
+        assert sim.mode == str(g[key + "mode_used"])
+        assert relerr(sim.v, g[key + "v0"]) < 1e-15                      # no constructor corrector kick
+        assert sim.h_sub_ref == pytest.approx(float(g[key + "h_sub_ref"]), rel=1e-14)
+        eps_t, dE_t = g[key + "eps_t"], g[key + "dE_t"]
+        marks = set(int(t) for t in g[key + "marks"])
+        # tolerance = base + 100 x the reference's divergence from ITSELF under an equivalent-arithmetic force routine
+        sens = np.maximum.accumulate(g[key + "sens_t"], axis=0)
+        for t in range(1, len(eps_t) + 1):
+            sim.step(dt)
+            sq, se, sd = 100.0 * sens[t - 1]
+            assert sim.s == pytest.approx(float(eps_t[t - 1]), rel=1e-10 + se), (key, t)
+            assert sim.softening_energy_delta == pytest.approx(float(dE_t[t - 1]), rel=1e-9 + sd, abs=1e-12), (key, t)
+            if t in marks:
+                assert relerr(sim.q, g[key + f"q{t}"]) < 1e-10 + sq, (key, t)
+                assert relerr(sim.v, g[key + f"v{t}"]) < 1e-9 + 10 * sq, (key, t)
+        assert len(sim.history) == int(g[key + "history_len"])
+        assert np.allclose(sim.history[-64:], g[key + "history_tail"], rtol=1e-10 + 100.0 * float(sens[-1, 1]))
