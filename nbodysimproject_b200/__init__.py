@@ -23,7 +23,8 @@ def __getattr__(name):
         "InitialConditionGenerator": "generators", "GeneratorConfig": "generators",
         "SpecializedGenerators": "generators", "set_global_seed": "generators",
         "MLTrainingPipeline": "pipeline",
-        "LargeNSimulation": "largen",
+        "LargeNSimulation": "largen", "LargeNHamSoftSimulation": "largen",
+        "StabilityDataset": "dataset", "save_feature_table": "dataset", "table_from_tensors": "dataset",
     }
     if name in table:
         mod = importlib.import_module("." + table[name], __name__)

@@ -298,12 +298,43 @@ class StabilityAnalyzer:
         self.dt = float(dt)
         self.mode = mode
         self.diagnostics = Diagnostics(sim)
+        self._initial = (sim._mass.copy(), sim._pos.copy(), sim._vel.copy())      # stability_analyzer.py:42-44
 
     def run_stability_analysis(self) -> Dict[str, float]:
         row = analyze_simulations([self.sim], self.n_steps, self.dt, self.mode)[0]
         for k in ("pathological_energy", "softening_policy", "_status"):
             row.pop(k, None)
         return row
+
+    def serialize_to_dict(self, diagnostics: Dict[str, float], max_bodies: int = None) -> Dict:
+        """stability_analyzer.py:521-561 (its `sim._adaptive` does not exist in the reference -- the call raises
+        AttributeError there; here the flag falls back to adaptive_timestep)."""
+        sim = self.sim
+        m0, q0, v0 = self._initial
+        data = {"n_bodies": sim.n_bodies, "G": sim.G, "softening": sim.manager.softening,
+                "min_softening": sim._min_softening,
+                "adaptive": float(getattr(sim, "_adaptive", getattr(sim, "_adaptive_timestep", False))),
+                "integrator_mode": sim._integrator_mode}
+        if max_bodies is not None and sim.n_bodies > max_bodies:
+            for name, arr in (("mass", m0), ("x", q0[:, 0]), ("y", q0[:, 1]), ("vx", v0[:, 0]), ("vy", v0[:, 1])):
+                data[f"{name}_min"] = float(np.min(arr)); data[f"{name}_max"] = float(np.max(arr))
+                data[f"{name}_mean"] = float(np.mean(arr)); data[f"{name}_std"] = float(np.std(arr))
+        else:
+            for i, mass in enumerate(m0):
+                data[f"mass_{i}"] = mass
+            for i in range(len(q0)):
+                data[f"x_{i}"] = q0[i, 0]; data[f"y_{i}"] = q0[i, 1]
+            for i in range(len(v0)):
+                data[f"vx_{i}"] = v0[i, 0]; data[f"vy_{i}"] = v0[i, 1]
+        data.update(diagnostics)
+        return data
+
+    def save_to_csv(self, filename: str, diagnostics: Dict[str, float] = None):
+        """stability_analyzer.py:563-568."""
+        import pandas as pd
+        if diagnostics is None:
+            diagnostics = self.run_stability_analysis()
+        pd.DataFrame([self.serialize_to_dict(diagnostics)]).to_csv(filename, index=False)
 
 
 class BatchStabilityAnalyzer:
