@@ -97,13 +97,14 @@ __device__ __forceinline__ void hs_solve_hi(const double* qx, const double* qy, 
       const double hj = fmax(h[i], 1.0e-12);
       const double h2 = hj * hj;
       const double c = 1.0 / (NB_PI * h2);
+      const double nih2 = -1.0 / h2;            // one division per body and sweep instead of one per pair
       double S = 0.0;
 #pragma unroll
       for (int j = 0; j < N; ++j) {
         if (j == i) continue;
         const int a = i < j ? i : j, b = i < j ? j : i;
         const double rr = r2[a * N - a * (a + 1) / 2 + (b - a - 1)];
-        S += m[j] * (c * exp(-rr / h2));
+        S += m[j] * (c * exp(rr * nih2));
       }
       const double Si = fmax(S, 1.0e-30);
       double v = P.eta * sqrt(m[i] / Si);
@@ -487,7 +488,7 @@ struct Welford {
 };
 
 template <int N>
-__global__ void __launch_bounds__(128) hamsoft_run_kernel(HsArgs a) {
+__global__ void __launch_bounds__(128, (N <= 4 ? 4 : 2)) hamsoft_run_kernel(HsArgs a) {
   const int lane = threadIdx.x & 31;
   const int sys = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (sys >= a.B) return;                               // warp-uniform

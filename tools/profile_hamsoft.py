@@ -1,0 +1,25 @@
+"""Short driver for ncu: hamsoft_run_kernel<3> on jittered README systems.  python tools/profile_hamsoft.py [B] [steps]"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from nbodysimproject_b200 import hamsoft as H
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 15
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+m, q, v = bench._c1_inputs(B, 42)
+hs, s0 = H.default_params(object(), 1e-3, 1e-4, B)
+ep = np.stack([np.maximum(s0, hs[:, H.P["eps_min"]]), np.zeros(B)], 1)
+hb = H.HamSoftBucket(m, q, v, hs, ep, 1.0)
+hb.setup(calibrate=True, freeze_dt=0.01)
+print("n_sub", int(hb.n_sub.max()), int(hb.n_sub.min()))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for rep in range(3):
+    e0.record(); hb.run(0.01, steps); e1.record(); torch.cuda.synchronize()
+t = e0.elapsed_time(e1) * 1e-3
+print(f"hamsoft N=3 B={B} steps={steps}: {t*1e3:.2f} ms, {B*steps/t:.3e} system-steps/s")
