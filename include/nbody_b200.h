@@ -207,6 +207,15 @@ int nb_largeN_pass_f32(int kind, const float* xym, const float* jaux, int n_tota
  * 8 packed f32x2 over j-pairs, 4 i per thread; 9 same with 8 i per thread, 2 CTAs/SM; 10 same with 2 i per thread */
 int nb_largeN_set_variant(int variant);
 
+/* ---- stability-classifier inference on the feature tensors (model_zoo.py:18-33 MLP F-128-64-1 with ReLU;
+ *      train_mlp.py:141-217 sigmoid + threshold; stability_dataset.py:83-85 nan_to_num; StandardScaler).
+ *      feature_index[F]: value c < 64 reads dyn_features[:, c], c >= 64 reads static_features[:, c - 64]; F <= 64.
+ *      w1[F][128] and w2[128][64] are INPUT-major (the transpose of torch's nn.Linear.weight); prob[B], label[B]. */
+int nb_mlp_classify_f32(const double* dyn_features, const double* static_features, const int32_t* feature_index, int F,
+                        const float* mean, const float* inv_scale, const float* w1, const float* b1, const float* w2,
+                        const float* b2, const float* w3, float b3, float threshold, int B, float* prob, int32_t* label,
+                        void* stream);
+
 /* ---- register-resident FMA micro-benchmarks used for the roofline denominators (TFLOP/s) */
 int nb_peak_flops(int which /*0 fp64 DFMA, 1 fp32 FFMA, 2 fp32x2 FFMA2*/, int device, double* tflops);
 

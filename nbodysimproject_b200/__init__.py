@@ -24,7 +24,7 @@ def __getattr__(name):
         "SpecializedGenerators": "generators", "set_global_seed": "generators",
         "MLTrainingPipeline": "pipeline",
         "LargeNSimulation": "largen", "LargeNHamSoftSimulation": "largen",
-        "StabilityDataset": "dataset", "save_feature_table": "dataset", "table_from_tensors": "dataset",
+        "StabilityClassifier": "classifier", "StabilityDataset": "dataset", "save_feature_table": "dataset", "table_from_tensors": "dataset",
     }
     if name in table:
         mod = importlib.import_module("." + table[name], __name__)

@@ -27,6 +27,9 @@ int variational_batched(const double* q, const double* m, const double* s2, cons
                         double* da, cudaStream_t st);
 int sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* ws, cudaStream_t st);
 int set_heavy_nsub(int thr);
+int mlp_classify(const double* dyn, const double* stat, const int32_t* idx, int F, const float* mean,
+                 const float* inv_scale, const float* w1, const float* b1, const float* w2, const float* b2,
+                 const float* w3, float b3, float threshold, int B, float* prob, int32_t* label, cudaStream_t st);
 int ensemble_run_adaptive(const double* m, double* q, double* v, double* eps, const double* soft_par, double G, int B,
                           int N, int mode, double dt, int n_steps, const int32_t* n_sub, double k_wall, int n_exp,
                           double* e_delta, double* eps_hist, int32_t* status, cudaStream_t st);
@@ -370,6 +373,14 @@ int nb_largeN_pass_f32(int kind, const float* xym, const float* jaux, int n_tota
 int nb_largeN_kick_drift_f32(float* xym_local, float* vel, const float* acc, int ni, float kick_h, float drift_h,
                              void* stream) {
   return largeN_kick_drift(xym_local, vel, acc, ni, kick_h, drift_h, (cudaStream_t)stream);
+}
+
+int nb_mlp_classify_f32(const double* dyn_features, const double* static_features, const int32_t* feature_index, int F,
+                        const float* mean, const float* inv_scale, const float* w1, const float* b1, const float* w2,
+                        const float* b2, const float* w3, float b3, float threshold, int B, float* prob, int32_t* label,
+                        void* stream) {
+  return mlp_classify(dyn_features, static_features, feature_index, F, mean, inv_scale, w1, b1, w2, b2, w3, b3, threshold,
+                      B, prob, label, (cudaStream_t)stream);
 }
 
 int nb_peak_flops(int which, int device, double* tflops) { return peak_flops(which, device, tflops); }
