@@ -207,6 +207,21 @@ int nb_largeN_pass_f32(int kind, const float* xym, const float* jaux, int n_tota
  * 8 packed f32x2 over j-pairs, 4 i per thread; 9 same with 8 i per thread, 2 CTAs/SM; 10 same with 2 i per thread */
 int nb_largeN_set_variant(int variant);
 
+/* ---- on-GPU initial conditions with a counter-based RNG (Philox4x32-10 keyed by seed, counted by the GLOBAL system
+ *      index first_index + b): the distributions of InitialConditionGenerator.generate_single
+ *      (initial_condition_generator.py:49-104), SpecializedGenerators (specialized_generators.py:23-94) and the cohort
+ *      parameters of MLTrainingPipeline.generate_diverse_dataset (ml_training_pipeline.py:44-122).
+ *      cohort: 0 random virial, 1 hierarchical triple (N = 3), 2 equal-mass polygon, 3 close encounter,
+ *              4 planetary resonant chain, 5 planetary TTV.  Outputs m[B][N], q[B][N][2], v[B][N][2], eps[B]. */
+#define NB_GEN_RANDOM 0
+#define NB_GEN_HIERARCHICAL 1
+#define NB_GEN_POLYGON 2
+#define NB_GEN_CLOSE 3
+#define NB_GEN_PLANETARY 4
+#define NB_GEN_PLANETARY_TTV 5
+int nb_generate_ensemble_f64(int cohort, int N, int B, uint64_t seed, uint64_t first_index, double* m, double* q, double* v,
+                             double* eps, void* stream);
+
 /* ---- stability-classifier inference on the feature tensors (model_zoo.py:18-33 MLP F-128-64-1 with ReLU;
  *      train_mlp.py:141-217 sigmoid + threshold; stability_dataset.py:83-85 nan_to_num; StandardScaler).
  *      feature_index[F]: value c < 64 reads dyn_features[:, c], c >= 64 reads static_features[:, c - 64]; F <= 64.

@@ -45,7 +45,7 @@ EXPORTS = [
     "nb_ensemble_prepare_f64", "nb_ensemble_run_f64", "nb_sort_by_nsub", "nb_ensemble_set_heavy_nsub",
     "nb_ensemble_run_adaptive_f64", "nb_ensemble_analyze_host",
     "nb_ensemble_analyze_host_async", "nb_host_sync", "nb_hamsoft_setup_f64", "nb_hamsoft_probe_f64",
-    "nb_largeN_accel_f32", "nb_largeN_kick_drift_f32", "nb_largeN_set_variant", "nb_largeN_pass_f32", "nb_mlp_classify_f32",
+    "nb_largeN_accel_f32", "nb_largeN_kick_drift_f32", "nb_largeN_set_variant", "nb_largeN_pass_f32", "nb_mlp_classify_f32", "nb_generate_ensemble_f64",
     "nb_peak_flops",
 ]
 
@@ -87,6 +87,7 @@ def load():
     lib.nb_largeN_set_variant.argtypes = [i]
     lib.nb_largeN_pass_f32.argtypes = [i, p, p, i, i, i, p, f, p, p]
     lib.nb_mlp_classify_f32.argtypes = [p, p, p, i, p, p, p, p, p, p, p, f, f, i, p, p, p]
+    lib.nb_generate_ensemble_f64.argtypes = [i, i, i, C.c_uint64, C.c_uint64, p, p, p, p, p]
     lib.nb_peak_flops.argtypes = [i, i, C.POINTER(C.c_double)]
     for name in EXPORTS:
         fn = getattr(lib, name)

@@ -27,6 +27,8 @@ int variational_batched(const double* q, const double* m, const double* s2, cons
                         double* da, cudaStream_t st);
 int sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* ws, cudaStream_t st);
 int set_heavy_nsub(int thr);
+int generate_ensemble(int cohort, int N, int B, uint64_t seed, uint64_t first, double* m, double* q, double* v, double* eps,
+                      cudaStream_t st);
 int mlp_classify(const double* dyn, const double* stat, const int32_t* idx, int F, const float* mean,
                  const float* inv_scale, const float* w1, const float* b1, const float* w2, const float* b2,
                  const float* w3, float b3, float threshold, int B, float* prob, int32_t* label, cudaStream_t st);
@@ -381,6 +383,11 @@ int nb_mlp_classify_f32(const double* dyn_features, const double* static_feature
                         void* stream) {
   return mlp_classify(dyn_features, static_features, feature_index, F, mean, inv_scale, w1, b1, w2, b2, w3, b3, threshold,
                       B, prob, label, (cudaStream_t)stream);
+}
+
+int nb_generate_ensemble_f64(int cohort, int N, int B, uint64_t seed, uint64_t first_index, double* m, double* q, double* v,
+                             double* eps, void* stream) {
+  return generate_ensemble(cohort, N, B, seed, first_index, m, q, v, eps, (cudaStream_t)stream);
 }
 
 int nb_peak_flops(int which, int device, double* tflops) { return peak_flops(which, device, tflops); }

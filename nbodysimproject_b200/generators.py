@@ -277,3 +277,24 @@ class EnsembleInputs:
         vc = np.sqrt((1.0 + m[:, 1:]) / a)
         v[:, 1:, 0] = -vc * np.sin(ph); v[:, 1:, 1] = vc * np.cos(ph)
         return m, q, v, np.zeros(B)
+
+
+COHORTS = {"random": 0, "hierarchical": 1, "polygon": 2, "close": 3, "planetary": 4, "planetary_ttv": 5}
+
+
+def generate_on_device(cohort, N: int, B: int, seed: int = 42, first_index: int = 0, device=None):
+    """B systems of `cohort` ('random', 'hierarchical', 'polygon', 'close', 'planetary', 'planetary_ttv') built on
+    the GPU by `nb_generate_ensemble_f64` (counter-based RNG: system k depends only on (seed, first_index + k)).
+    Returns device tensors m[B,N], q[B,N,2], v[B,N,2], softening[B] ready for ensemble.DeviceBucket."""
+    from . import _lib as L
+    torch = L.require_cuda()
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    c = COHORTS[cohort] if isinstance(cohort, str) else int(cohort)
+    m = torch.empty((B, N), dtype=torch.float64, device=dev)
+    q = torch.empty((B, N, 2), dtype=torch.float64, device=dev)
+    v = torch.empty((B, N, 2), dtype=torch.float64, device=dev)
+    eps = torch.empty((B,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().nb_generate_ensemble_f64(c, int(N), int(B), int(seed), int(first_index), L.ptr(m), L.ptr(q),
+                                                  L.ptr(v), L.ptr(eps), L.stream_ptr()), "nb_generate_ensemble_f64")
+    return m, q, v, eps
