@@ -62,6 +62,9 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.perf_counter()          # nvidia-smi needs a moment to attach: wait for its first line
+            while not self.lines and time.perf_counter() - t0 < 5.0:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
@@ -69,7 +72,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """Index of the next sample: call at the start and at the end of the timed region."""
+        return len(self.lines)
+
+    def stop(self, lo: int = 0, hi: int = None):
+        """Clocks / throttle reasons of the samples [lo, hi) (the timed region); when the region is shorter than
+        three sampling periods, the neighbouring samples (warm-up before, the e2e leg after: the same kernels) are
+        included so that the figure is still measured under load."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -77,9 +87,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        hi = len(self.lines) if hi is None else hi
+        note = "timed region"
+        if hi - lo < 3:
+            lo, hi, note = max(0, lo - 10), min(len(self.lines), hi + 10), "timed region +- 0.5 s (same kernels)"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[lo:hi]:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -92,10 +106,8 @@ class ClockSampler:
                     reasons.add(nm)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # "under load" = upper half of the samples
-        s = sorted(sm)
-        return {"sm_mhz": float(np.median(s[len(s) // 2:])), "sm_max_mhz": float(max(mx)),
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "window": note}
 
 
 def make_inputs(n_systems: int, seed: int):
@@ -314,19 +326,20 @@ def impl_b200(args):
             torch.cuda.synchronize()
 
     # ---- value: device-resident
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    mark0 = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step_device()
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    mark1 = sampler.mark()
     t_dev = e0.elapsed_time(e1) * 1e-3
     # ---- e2e: host buffers through the C ABI
     for _ in range(max(1, min(args.warmup, 2))):
@@ -338,6 +351,7 @@ def impl_b200(args):
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
+    clocks = sampler.stop(mark0, mark1) if rank == 0 else None
     if world > 1:
         tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -569,6 +583,7 @@ def bench_secondary(args, torch, dist, world, rank, local, dev):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    mark0 = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -577,7 +592,7 @@ def bench_secondary(args, torch, dist, world, rank, local, dev):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(mark0, sampler.mark()) if rank == 0 else None
     t_dev = e0.elapsed_time(e1) * 1e-3
     # e2e: pinned host state in, final host state out, every step
     host = []
@@ -649,7 +664,11 @@ def bench_secondary(args, torch, dist, world, rank, local, dev):
 
 def bench_largen(args, torch, dist, world, rank, local, dev):
     from nbodysimproject_b200.largen import bench_largen as run
-    line = run(args, world, rank, local, dev)
+    sampler = None
+    if rank == 0:
+        sampler = ClockSampler(local)
+        sampler.start()
+    line = run(args, world, rank, local, dev, sampler)
     if rank == 0 and line is not None:
         print(json.dumps(line))
     if world > 1:
@@ -659,7 +678,7 @@ def bench_largen(args, torch, dist, world, rank, local, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 20; 5 for c4 / c1 / largen)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ensemble", choices=["ensemble", "largen", "c4", "c1"])
@@ -670,6 +689,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-largen", action="store_true", help="skip the secondary large-N force measurement")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 20 if (args.workload == "ensemble" and args.impl == "b200") else 5
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         impl_reference(args)

@@ -566,7 +566,7 @@ def measure_force(sim, steps: int, warmup: int = 3):
     return t
 
 
-def bench_largen(args, world, rank, local, dev):
+def bench_largen(args, world, rank, local, dev, sampler=None):
     """pair-interactions/s of one force evaluation over all ordered pairs of an N-particle system
     (strong scaling: N fixed, i-blocks sharded, one in-place position all-gather per evaluation), plus the wall
     time of one full ham_soft Strang sub-step S V T V S (adaptive epsilon) on the same particles."""
@@ -575,7 +575,9 @@ def bench_largen(args, world, rank, local, dev):
     n = int(args.n)
     m, q, v = make_disc(n, seed=1)
     sim = LargeNSimulation(m, q, v, G=1.0, softening=1e-3, device=dev)
+    mark0 = sampler.mark() if sampler is not None else 0
     t = measure_force(sim, args.steps, args.warmup)
+    mark1 = sampler.mark() if sampler is not None else 0
     # e2e: host positions in, host accelerations out, every step
     xym_h = sim.xym.cpu().pin_memory()
     acc_h = torch.empty((sim.ni, 2), dtype=torch.float32).pin_memory()
@@ -638,5 +640,6 @@ def bench_largen(args, world, rank, local, dev):
                      "traffic": None, "flops_per_pair": 14,
                      "peak_source": "nb_peak_flops(1): register-resident FFMA micro-benchmark, same GPU, same run"},
         "hamsoft_strang_substep": strang, "cpu_baseline": cpu,
+        "clocks": sampler.stop(mark0, mark1) if sampler is not None else None,
     }
     return line
