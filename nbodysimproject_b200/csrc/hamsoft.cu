@@ -242,15 +242,22 @@ __device__ __forceinline__ double hs_fd_step(double x) {
 // eps*(q) and its gradient, cooperatively over the warp: lane 0 evaluates the unperturbed configuration,
 // lane 1+2c+s the coordinate c = 2 i + a perturbed by +h (s = 0) or -h (s = 1).  Every lane returns the full
 // gradient.  hamsoft_eps_model.py:94-234.
+// lanes per system: 4 N + 1 evaluations fit a half warp for N <= 3, so two systems share a warp there
+template <int N>
+struct HsLanes { static constexpr int LPS = (4 * N + 1 <= 16) ? 16 : 32; };
+
 template <int N>
 __device__ __forceinline__ double hs_eps_star_and_grad(const double* x, const double* y, const double* m,
-                                                       double eps_cur, const HsPar& P, int lane, double* gx,
+                                                       double eps_cur, const HsPar& P, int lane_full, double* gx,
                                                        double* gy, bool& used_fallback) {
   constexpr int NE = 4 * N + 1;
+  constexpr int LPS = HsLanes<N>::LPS;
+  const int lane = lane_full & (LPS - 1);     // lane within this system's group
+  const int base = lane_full - lane;          // first lane of the group
   double f[2] = {0.0, 0.0};
 #pragma unroll
-  for (int pass = 0; pass < (NE + 31) / 32; ++pass) {
-    const int e = lane + 32 * pass;           // evaluation index
+  for (int pass = 0; pass < (NE + LPS - 1) / LPS; ++pass) {
+    const int e = lane + LPS * pass;          // evaluation index
     const int ee = e < NE ? e : 0;            // idle lanes redo the unperturbed one
     const int c = (ee - 1) >> 1;              // perturbed coordinate (ee >= 1)
     const double sgn = ((ee - 1) & 1) ? -1.0 : 1.0;
@@ -264,7 +271,7 @@ __device__ __forceinline__ double hs_eps_star_and_grad(const double* x, const do
     }
     f[pass] = hs_eps_target<N>(px, py, m, eps_cur, P);
   }
-  const double es = __shfl_sync(0xffffffffu, f[0], 0);
+  const double es = __shfl_sync(0xffffffffu, f[0], base);
   double gmax2 = 0.0;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
@@ -272,8 +279,10 @@ __device__ __forceinline__ double hs_eps_star_and_grad(const double* x, const do
     for (int a = 0; a < 2; ++a) {
       const int c = 2 * i + a;
       const int ep = 1 + 2 * c, em = 2 + 2 * c;
-      const double fp = ep < 32 ? __shfl_sync(0xffffffffu, f[0], ep & 31) : __shfl_sync(0xffffffffu, f[1], ep & 31);
-      const double fm = em < 32 ? __shfl_sync(0xffffffffu, f[0], em & 31) : __shfl_sync(0xffffffffu, f[1], em & 31);
+      const double fp = ep < LPS ? __shfl_sync(0xffffffffu, f[0], base + (ep & (LPS - 1)))
+                                 : __shfl_sync(0xffffffffu, f[1], base + (ep & (LPS - 1)));
+      const double fm = em < LPS ? __shfl_sync(0xffffffffu, f[0], base + (em & (LPS - 1)))
+                                 : __shfl_sync(0xffffffffu, f[1], base + (em & (LPS - 1)));
       const double h = hs_fd_step(a == 0 ? x[i] : y[i]);
       double g = (fp - fm) / (2.0 * h);
       if (!is_finite(g)) g = 0.0;
@@ -488,10 +497,21 @@ struct Welford {
 };
 
 template <int N>
+static inline int hs_run_blocks(int B) {
+  const int spw = 32 / HsLanes<N>::LPS;
+  const int warps = (B + spw - 1) / spw;
+  return (warps + 3) / 4;
+}
+
+template <int N>
 __global__ void __launch_bounds__(128, (N <= 4 ? 4 : 2)) hamsoft_run_kernel(HsArgs a) {
+  constexpr int LPS = HsLanes<N>::LPS, SPW = 32 / LPS;   // lanes per system, systems per warp
   const int lane = threadIdx.x & 31;
-  const int sys = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (sys >= a.B) return;                               // warp-uniform
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp * SPW >= a.B) return;                        // warp-uniform
+  // an odd tail slot shadows the warp's first system (same arithmetic, no writes) so the warp stays converged
+  const bool live = warp * SPW + lane / LPS < a.B;
+  const int sys = live ? warp * SPW + lane / LPS : warp * SPW;
   HsState<N> s;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
@@ -506,7 +526,21 @@ __global__ void __launch_bounds__(128, (N <= 4 ? 4 : 2)) hamsoft_run_kernel(HsAr
   HsPar P = hs_load(a.hs + (size_t)sys * NB_HS_NPARAM);
   const double G = a.G;
   const int n_sub = max(1, a.n_sub ? a.n_sub[sys] : 1);
+  const int n_sub_warp = SPW > 1 ? __reduce_max_sync(0xffffffffu, n_sub) : n_sub;
   const double h = a.dt / (double)n_sub;
+  // one macro step = n_sub Strang sub-steps; systems sharing a warp run to the larger count and discard the excess
+  auto macro_step = [&]() {
+#pragma unroll 1
+    for (int k = 0; k < n_sub_warp; ++k) {
+      if (SPW > 1) {
+        HsState<N> t = s;
+        hs_strang<N>(t, P, G, h, lane);
+        if (k < n_sub) s = t;
+      } else {
+        hs_strang<N>(s, P, G, h, lane);
+      }
+    }
+  };
   // hamiltonian_softening_integrator.py:232-242: mu is raised to k (dt/theta_imp)^2 on the first step
   if (a.n_steps + a.n_megno > 0 && is_finite(P.k) && P.k > 0.0) {
     const double mu_macro = P.k * (fabs(a.dt) / P.theta_imp) * (fabs(a.dt) / P.theta_imp);
@@ -535,8 +569,7 @@ __global__ void __launch_bounds__(128, (N <= 4 ? 4 : 2)) hamsoft_run_kernel(HsAr
   bool have_first = false, cos_nan = false, th_nan = false;
   int n_samp = 0, next_sample = 0;
   for (int step = 0; step < a.n_steps; ++step) {
-#pragma unroll 1
-    for (int k = 0; k < n_sub; ++k) hs_strang<N>(s, P, G, h, lane);
+    macro_step();
     if (a.sample_interval > 0 && step == next_sample) {   // diagnostics.py:241-285
       next_sample += a.sample_interval;
       double cx = 0.0, cy = 0.0, Lt = 0.0, Li[N];
@@ -594,8 +627,7 @@ __global__ void __launch_bounds__(128, (N <= 4 ? 4 : 2)) hamsoft_run_kernel(HsAr
     double tt = 0.0, accum = 0.0;
     const double dt = a.dt;
     for (int step = 0; step < a.n_megno; ++step) {
-#pragma unroll 1
-      for (int k = 0; k < n_sub; ++k) hs_strang<N>(s, P, G, h, lane);
+      macro_step();
       SysState<N> t;
       double dax[N], day[N];
 #pragma unroll
@@ -627,7 +659,7 @@ __global__ void __launch_bounds__(128, (N <= 4 ? 4 : 2)) hamsoft_run_kernel(HsAr
     t_end = tt;
   }
 
-  if (lane != 0) return;
+  if ((lane & (LPS - 1)) != 0 || !live) return;
   bool finite = is_finite(s.eps) && is_finite(s.pi);
 #pragma unroll
   for (int i = 0; i < N; ++i)
@@ -840,7 +872,7 @@ int hamsoft_run(const double* m, double* q, double* v, double G, int B, int N, u
   (void)perm;
   HsArgs a{m, q, v, G, B, flags, dt, n_steps, sample_interval, n_megno, n_sub, raw_dr, raw_dv, eps_pi, hs, dyn, status};
   const int blocks = (B + 3) / 4;
-  NB_HS_DISPATCH(N, (hamsoft_run_kernel<NN><<<blocks, 128, 0, st>>>(a)));
+  NB_HS_DISPATCH(N, (hamsoft_run_kernel<NN><<<hs_run_blocks<NN>(a.B), 128, 0, st>>>(a)));
   NB_CUDA_CHECK(cudaGetLastError());
   return NB_OK;
 }

@@ -143,3 +143,33 @@ def test_hamsoft_barrier_policies_vs_golden():
             assert abs(ep[1] - ref[1]) <= 1e-5 * max(abs(ref[1]), 1e-6), (key, mark, ep, ref)
             if not disabled:
                 assert hsv[P["eps_min"]] <= ep[0] <= hsv[P["eps_max"]]
+
+
+def test_hamsoft_two_systems_per_warp_for_small_n():
+    """N <= 3: 4 N + 1 <= 16 evaluations, so two systems share a warp (half-warp shuffles, the pair runs to the larger
+    sub-step count).  An odd batch with mixed n_sub must give every system exactly what it gets alone."""
+    from nbodysimproject_b200 import hamsoft as H
+    from nbodysimproject_b200.simulation import SimConfig
+    rng = np.random.RandomState(11)
+    for N in (2, 3):
+        B = 7
+        m = rng.uniform(0.5, 3.0, (B, N))
+        q = rng.randn(B, N, 2) * rng.uniform(0.15, 1.0, (B, 1, 1))
+        v = rng.randn(B, N, 2) * 0.4
+        v -= (m[:, :, None] * v).sum(1, keepdims=True) / m.sum(1)[:, None, None]
+        hs, s0 = H.default_params(SimConfig(), 0.05, 0.005, B)
+        b = H.HamSoftBucket(m, q, v, hs, np.stack([s0, np.zeros(B)], 1), 1.0)
+        b.setup(True, 0.01)
+        nsub = b.n_sub.cpu().numpy().copy()
+        rr, rv = rng.randn(B, N, 2), rng.randn(B, N, 2)
+        dyn = b.run(0.01, 6, 2, 3, rr, rv, flags=3, want_dyn=True).cpu().numpy()
+        qa, ea = b.bk.q.cpu().numpy(), b.eps_pi.cpu().numpy()
+        if N == 3:
+            assert len(np.unique(nsub)) > 1                    # the pairs really mix sub-step counts
+        for i in range(B):
+            b1 = H.HamSoftBucket(m[i:i + 1], q[i:i + 1], v[i:i + 1], hs[i:i + 1], np.array([[s0[i], 0.0]]), 1.0)
+            b1.setup(True, 0.01)
+            d1 = b1.run(0.01, 6, 2, 3, rr[i:i + 1], rv[i:i + 1], flags=3, want_dyn=True).cpu().numpy()
+            assert np.array_equal(b1.bk.q.cpu().numpy()[0], qa[i]), (N, i)
+            assert np.array_equal(b1.eps_pi.cpu().numpy()[0], ea[i]), (N, i)
+            assert np.array_equal(d1[0], dyn[i], equal_nan=True), (N, i)
