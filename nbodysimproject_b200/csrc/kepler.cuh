@@ -84,27 +84,36 @@ __device__ __forceinline__ int kepler_reference(double& rx, double& ry, double& 
     chi = sqrt_mu * sd(fabs(alpha.v)) * dt;
   else
     chi = sqrt_mu * dt / r0;
-  double prev1 = __longlong_as_double(0x7ff8000000000000LL), prev2 = prev1;
+  // x2 = the iterate two steps back.  (The reference also keeps prev1/prev2, but its second exit test
+  // `chi_new == prev2` compares with the current chi again, kepler_solver.py:71-77, so it only ever exits on
+  // chi_new == chi; an exact 2-cycle therefore runs to the 64-iteration cap -- 4 % of all planetary solves.)
+  double x2 = __longlong_as_double(0x7ff8000000000000LL);
   sd c0, c1, c2, c3;
   int it = 0;
   double last_step = 0.0;
+  const sd k1 = r0 * vr0 / sqrt_mu, k2 = sd(1.0) - alpha * r0, k3 = sqrt_mu * dt;     // loop invariants, same rounding
   for (; it < 64;) {
     ++it;
     const sd z = alpha * chi * chi;
     cfunc_reference(z.v, c0, c1, c2, c3);
-    const sd f = r0 * vr0 / sqrt_mu * chi * chi * c1 + (sd(1.0) - alpha * r0) * chi * chi * chi * c2 + r0 * chi -
-                 sqrt_mu * dt;
-    const sd fp = r0 * vr0 / sqrt_mu * chi * (sd(1.0) - alpha * chi * chi * c2) +
-                  (sd(1.0) - alpha * r0) * chi * chi * c1 + r0;
+    const sd f = k1 * chi * chi * c1 + k2 * chi * chi * chi * c2 + r0 * chi - k3;
+    const sd fp = k1 * chi * (sd(1.0) - alpha * chi * chi * c2) + k2 * chi * chi * c1 + r0;
     if (fp.v == 0.0) break;
     const sd chi_new = chi - f / fp;
-    prev2 = prev1;
-    prev1 = chi_new.v;
     last_step = fabs(chi_new.v - chi.v);
-    if (chi_new.v == chi.v || chi_new.v == prev2) {
+    if (chi_new.v == chi.v) {
       chi = chi_new;
       break;
     }
+    // Exact-cycle shortcut (bit-identical result): the Newton map is a pure function of chi, so chi_new == x2 means the
+    // iterates alternate between chi_new and chi for the rest of the reference's 64 iterations; its final iterate is
+    // the one with the parity of 64.  Detected after ~8 iterations instead of running all 64 in lock-step per warp.
+    if (chi_new.v == x2) {
+      if (((64 - it) & 1) == 0) chi = chi_new;
+      it = 64;
+      break;
+    }
+    x2 = chi.v;
     chi = chi_new;
   }
   // the reference's exit test is exact equality, so running into the 64-iteration cap while hovering within a
