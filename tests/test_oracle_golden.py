@@ -243,3 +243,83 @@ def test_adaptive_softening_oracle_vs_golden():
                 assert relerr(sim.v, g[key + f"v{t}"]) < 1e-9 + 10 * sq, (key, t)
         assert len(sim.history) == int(g[key + "history_len"])
         assert np.allclose(sim.history[-64:], g[key + "history_tail"], rtol=1e-10 + 100.0 * float(sens[-1, 1]))
+
+
+def _kepler_shortcut(r, v, mu, dt):
+    """Host mirror of the device Newton loop in csrc/kepler.cuh (exact 2-cycle shortcut); must give the reference's
+    final iterate bit for bit."""
+    import math
+    from oracle import nbody_oracle as O
+    r = np.asarray(r, dtype=float); v = np.asarray(v, dtype=float)
+    r0 = float(math.hypot(r[0], r[1]))
+    vr0 = float(np.dot(r, v) / r0)
+    alpha = 2 / r0 - float(np.dot(v, v)) / mu
+    sm = math.sqrt(mu)
+    chi = sm * abs(alpha) * dt if abs(alpha) > 1e-12 else sm * dt / r0
+    x2 = math.nan
+    it = 0
+    while it < 64:
+        it += 1
+        z = alpha * chi * chi
+        c0, c1, c2, c3 = O.kepler_cfunc(z)
+        f = r0 * vr0 / sm * chi * chi * c1 + (1 - alpha * r0) * chi * chi * chi * c2 + r0 * chi - sm * dt
+        fp = r0 * vr0 / sm * chi * (1 - alpha * chi * chi * c2) + (1 - alpha * r0) * chi * chi * c1 + r0
+        if fp == 0:
+            break
+        cn = chi - f / fp
+        if cn == chi:
+            chi = cn
+            break
+        if cn == x2:
+            if ((64 - it) & 1) == 0:
+                chi = cn
+            it = 64
+            break
+        x2 = chi
+        chi = cn
+    return chi, it
+
+
+def test_kepler_cycle_shortcut_is_bit_identical():
+    """The reference's Newton loop only exits on chi_new == chi, so exact 2-cycles run to the 64-iteration cap; the
+    device loop stops at the first repeat and picks the iterate with the parity of 64.  Same chi, bit for bit, on the
+    golden Kepler cases and on planetary solves (where 4 % of the solves are such cycles)."""
+    import math
+    from oracle import nbody_oracle as O
+    sys_path_bench = __import__("bench")
+    g = load_golden("kepler.npz")
+    cases = [(g["r"][i], g["v"][i], float(g["mu"][i]), float(g["dt"][i])) for i in range(len(g["mu"]))]
+    inp = sys_path_bench._c4_inputs(90, 3)
+    for N, (m, q, v, eps) in inp.items():
+        for b in range(m.shape[0]):
+            sim = O.OracleSim(m[b], q[b], v[b], softening=0.0, integrator_mode="whfast")
+            jp, jv = sim.to_jacobi()
+            cum = sim.m[0]
+            for i in range(1, sim.n):
+                mu = sim.G * (cum + sim.m[i]); cum += sim.m[i]
+                cases.append((jp[i].copy(), jv[i].copy(), float(mu), 0.0314))
+    n_cap = 0
+    for r, v, mu, dt in cases:
+        if math.hypot(r[0], r[1]) < 1e-14:
+            continue
+        chi_s, it_s = _kepler_shortcut(r, v, mu, dt)
+        # the reference loop, instrumented only to expose its final iterate
+        r0 = float(math.hypot(r[0], r[1])); vr0 = float(np.dot(r, v) / r0)
+        alpha = 2 / r0 - float(np.dot(v, v)) / mu; sm = math.sqrt(mu)
+        chi = sm * abs(alpha) * dt if abs(alpha) > 1e-12 else sm * dt / r0
+        it = 0
+        for _ in range(64):
+            it += 1
+            c0, c1, c2, c3 = O.kepler_cfunc(alpha * chi * chi)
+            f = r0 * vr0 / sm * chi * chi * c1 + (1 - alpha * r0) * chi * chi * chi * c2 + r0 * chi - sm * dt
+            fp = r0 * vr0 / sm * chi * (1 - alpha * chi * chi * c2) + (1 - alpha * r0) * chi * chi * c1 + r0
+            if fp == 0:
+                break
+            cn = chi - f / fp
+            if cn == chi:
+                chi = cn
+                break
+            chi = cn
+        assert chi_s == chi and it_s == it, (r, v, mu, dt, chi_s, chi, it_s, it)
+        n_cap += it == 64
+    assert n_cap >= 5          # the sample really contains capped solves
