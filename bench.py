@@ -169,8 +169,21 @@ def run_cpu(n_jobs: int, cores: int, seed: int = 777):
     return done / dt, dt
 
 
+def cpu_pairs_per_s(n: int = 4096, reps: int = 3):
+    """CPU baseline for the large-N metric: the oracle's dense gravitational_force (forces.py:63-75 restated) at the
+    largest N whose (N,N,2) fp64 temporaries fit comfortably; pairs/s on one core (the reference is single-threaded)."""
+    from oracle import nbody_oracle as O
+    from nbodysimproject_b200.largen import make_disc
+    m, q, _ = make_disc(n, seed=5)
+    O.accelerations(q, m, 1e-3, 1.0)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        O.accelerations(q, m, 1e-3, 1.0)
+    dt = (time.perf_counter() - t0) / reps
+    return float(n) * float(n) / dt, dt
+
+
 def impl_reference_largen(args):
-    from nbodysimproject_b200.largen import cpu_pairs_per_s
     n = 4096
     times = []
     for it in range(args.warmup + args.steps):
@@ -669,6 +682,11 @@ def bench_largen(args, torch, dist, world, rank, local, dev):
         sampler = ClockSampler(local)
         sampler.start()
     line = run(args, world, rank, local, dev, sampler)
+    if rank == 0 and line is not None and world == 1 and not args.no_cpu:
+        rate, dtc = cpu_pairs_per_s(4096, 5)
+        line["cpu_baseline"] = {"value": rate, "unit": "pair-interactions/s", "cores": 1, "kind": "port",
+                                "sample": f"oracle dense gravitational_force at N=4096 ({dtc*1e3:.0f} ms per call; the "
+                                          "(N,N,2) fp64 temporaries make N=2^20 impossible on the CPU path: 17.6 TB)"}
     if rank == 0 and line is not None:
         print(json.dumps(line))
     if world > 1:

@@ -526,19 +526,6 @@ def make_disc(n: int, seed: int = 0):
     return m, q, v
 
 
-def cpu_pairs_per_s(n: int = 4096, reps: int = 3):
-    """CPU baseline for the large-N metric: the oracle's dense gravitational_force (forces.py:63-75 restated) at the
-    largest N whose (N,N,2) fp64 temporaries fit comfortably; pairs/s on one core (the reference is single-threaded)."""
-    from oracle import nbody_oracle as O
-    m, q, _ = make_disc(n, seed=5)
-    O.accelerations(q, m, 1e-3, 1.0)
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        O.accelerations(q, m, 1e-3, 1.0)
-    dt = (time.perf_counter() - t0) / reps
-    return float(n) * float(n) / dt, dt
-
-
 def measure_force(sim, steps: int, warmup: int = 3):
     """CUDA-event time of `steps` x (in-place position all-gather + one force evaluation); returns seconds (this rank)."""
     torch = sim.torch
@@ -619,12 +606,7 @@ def bench_largen(args, world, rank, local, dev, sampler=None):
         return None
     pairs = float(n) * float(n) * args.steps
     peak32 = L.peak_flops(1, local)
-    cpu = None
-    if world == 1 and not getattr(args, "no_cpu", False):
-        rate, dtc = cpu_pairs_per_s(4096, 5)
-        cpu = {"value": rate, "unit": "pair-interactions/s", "cores": 1, "kind": "port",
-               "sample": f"oracle dense gravitational_force at N=4096 ({dtc*1e3:.0f} ms per call; the (N,N,2) fp64 "
-                         "temporaries make N=2^20 impossible on the CPU path: 17.6 TB)"}
+    cpu = None          # filled in by bench.py (the only place allowed to time the oracle)
     line = {
         "metric": "pair-interactions/s at N=2^20", "value": pairs / t, "unit": "pair-interactions/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t / args.steps,

@@ -42,3 +42,15 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(_lib.NBodyB200Error):
         from nbodysimproject_b200 import ensemble
         ensemble.pair_batched([[[0.0, 0.0], [1.0, 0.0]]], [[1.0, 1.0]], 0.0)
+
+
+def test_product_path_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package (nor the C sources) may import or call it."""
+    import glob
+    pkg = os.path.join(ROOT, "nbodysimproject_b200")
+    files = glob.glob(os.path.join(pkg, "*.py")) + glob.glob(os.path.join(pkg, "csrc", "*.cu*"))
+    assert len(files) > 15
+    for f in files:
+        src = open(f).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+        assert "oracle." not in src and "import oracle" not in src, f
