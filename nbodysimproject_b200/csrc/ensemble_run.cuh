@@ -168,15 +168,17 @@ __device__ __forceinline__ int substep(SysState<N>& s, const double* m, double G
     const double w1 = 1.0 / (2.0 - cbrt2);
     const double w2 = -cbrt2 / (2.0 - cbrt2);
     const double ha = w1 * h, hb = w2 * h;
+    // the closing half kick of one Verlet kernel and the opening half kick of the next use the same acceleration:
+    // v += (ha/2) a ; v += (hb/2) a  is issued as one fma with (ha + hb)/2 (differs from the reference's two
+    // roundings by <= 1 ulp of the kick; 4N FP64 operations fewer per sub-step)
+    const double hab = 0.5 * ha + 0.5 * hb;
     kick<N>(s, 0.5 * ha);
     drift<N>(s, ha);
     pair_pass<N, false, GUARD>(s, nullptr, nullptr, nullptr, nullptr);
-    kick<N>(s, 0.5 * ha);
-    kick<N>(s, 0.5 * hb);
+    kick<N>(s, hab);
     drift<N>(s, hb);
     pair_pass<N, false, GUARD>(s, nullptr, nullptr, nullptr, nullptr);
-    kick<N>(s, 0.5 * hb);
-    kick<N>(s, 0.5 * ha);
+    kick<N>(s, hab);
     drift<N>(s, ha);
     pair_pass<N, TANGENT, GUARD>(s, drx, dry, dax, day);
     kick<N>(s, 0.5 * ha);

@@ -41,9 +41,15 @@ __device__ __forceinline__ void pair_pass(SysState<N>& s, const double* __restri
       const double dx = s.x[i] - s.x[j];
       const double dy = s.y[i] - s.y[j];
       const double r2 = fma(dx, dx, fma(dy, dy, s.eps2));
-      const double w = rsqrt_f64<GUARD>(r2);
-      const double w2 = w * w;
-      const double w3 = w2 * w;
+      double w2, w3;
+      if (TANGENT) {
+        const double w = rsqrt_f64<GUARD>(r2);
+        w2 = w * w;
+        w3 = w2 * w;
+      } else {
+        w2 = 0.0;
+        w3 = rsqrt3_f64<GUARD>(r2);      // rho^-3 directly: 16 instead of 17 FP64 operations per unordered pair
+      }
       const double cj = s.gm[j] * w3;
       const double ci = s.gm[i] * w3;
       s.ax[i] = fma(-cj, dx, s.ax[i]);
