@@ -445,7 +445,9 @@ int sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* ws,
   static const float speedup[9] = {1.f, 1.f, 1.f, 1.f, 1.8f, 2.1f, 3.0f, 3.5f, 4.5f};
   static const int per_sm[9] = {384, 384, 640, 512, 512, 384, 384, 256, 256};
   const int n = (N >= 2 && N <= 8) ? N : 0;
-  sort_scan_kernel<<<1, 32, 0, st>>>(ws, g_heavy_kappa, 148 * per_sm[n], speedup[n], g_heavy_fixed);
+  static float sp_scale = -1.f;
+  if (sp_scale < 0.f) sp_scale = getenv("NB_HEAVY_SPEEDUP_SCALE") ? (float)atof(getenv("NB_HEAVY_SPEEDUP_SCALE")) : 1.0f;
+  sort_scan_kernel<<<1, 32, 0, st>>>(ws, g_heavy_kappa, 148 * per_sm[n], speedup[n] * sp_scale, g_heavy_fixed);
   sort_scatter_kernel<<<blocks, threads, 0, st>>>(n_sub, B, ws, perm);
   NB_CUDA_CHECK(cudaGetLastError());
   return NB_OK;
