@@ -148,9 +148,9 @@ int nb_hamsoft_probe_f64(const double* m, const double* q, const double* v, doub
 
 /* counting sort of systems by n_sub (descending) -> perm[B]; workspace: 128 int32 on the device;
  * on return workspace[64] = number of systems in the "heavy" head of perm (n_sub > workspace[65]) that the run
- * kernels map for latency instead of throughput.  The threshold is chosen per batch, >= 4, from N (bodies per
- * system, 0 = unknown), the largest n_sub present and sum(n_sub): a system is heavy only when its own sequential
- * sub-step chain would otherwise set the run time of the launch. */
+ * kernels map for latency instead of throughput.  The threshold depends on N only (bodies per system, 0 = unknown;
+ * max(4, 50 / measured chain speed-up of the latency mapping)), never on the batch, so a system is integrated by the
+ * same arithmetic however the ensemble is sharded. */
 int nb_sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* workspace, void* stream);
 /* override the heavy threshold (process-wide; tests and tuning): -1 = automatic (default), 0..63 = fixed */
 int nb_ensemble_set_heavy_nsub(int threshold);

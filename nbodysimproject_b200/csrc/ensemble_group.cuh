@@ -39,9 +39,15 @@ __device__ __forceinline__ void group_accel(const GroupCtx<N>& c, int b, double 
     const double yj = __shfl_sync(0xffffffffu, y, src);
     const double dx = x - xj, dy = y - yj;
     const double r2 = fma(dx, dx, fma(dy, dy, c.eps2));
-    const double w = rsqrt_f64<GUARD>(r2);
-    const double w2 = w * w;
-    const double w3 = w2 * w;
+    double w2, w3;                                   // same arithmetic as pair_small.cuh: bit-identical accelerations
+    if (TANGENT) {
+      const double w = rsqrt_f64<GUARD>(r2);
+      w2 = w * w;
+      w3 = w2 * w;
+    } else {
+      w2 = 0.0;
+      w3 = rsqrt3_f64<GUARD>(r2);
+    }
     const double cj = c.gmk[t] * w3;
     ax = fma(-cj, dx, ax);
     ay = fma(-cj, dy, ay);
@@ -80,15 +86,14 @@ __device__ __forceinline__ void group_substep(const GroupCtx<N>& c, int b, doubl
     const double cbrt2 = 1.2599210498948731648;
     const double w1 = 1.0 / (2.0 - cbrt2), w2 = -cbrt2 / (2.0 - cbrt2);
     const double ha = w1 * h, hb = w2 * h;
+    const double hab = 0.5 * ha + 0.5 * hb;          // merged adjacent half kicks, exactly as ensemble_run.cuh substep<>
     vx = fma(0.5 * ha, ax, vx); vy = fma(0.5 * ha, ay, vy);
     x = fma(ha, vx, x); y = fma(ha, vy, y);
     group_accel<N, false, GUARD>(c, b, x, y, ax, ay, 0.0, 0.0, dum1, dum2);
-    vx = fma(0.5 * ha, ax, vx); vy = fma(0.5 * ha, ay, vy);
-    vx = fma(0.5 * hb, ax, vx); vy = fma(0.5 * hb, ay, vy);
+    vx = fma(hab, ax, vx); vy = fma(hab, ay, vy);
     x = fma(hb, vx, x); y = fma(hb, vy, y);
     group_accel<N, false, GUARD>(c, b, x, y, ax, ay, 0.0, 0.0, dum1, dum2);
-    vx = fma(0.5 * hb, ax, vx); vy = fma(0.5 * hb, ay, vy);
-    vx = fma(0.5 * ha, ax, vx); vy = fma(0.5 * ha, ay, vy);
+    vx = fma(hab, ax, vx); vy = fma(hab, ay, vy);
     x = fma(ha, vx, x); y = fma(ha, vy, y);
     group_accel<N, TANGENT, GUARD>(c, b, x, y, ax, ay, drx, dry, dax, day);
     vx = fma(0.5 * ha, ax, vx); vy = fma(0.5 * ha, ay, vy);

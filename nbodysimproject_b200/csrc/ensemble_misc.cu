@@ -331,26 +331,16 @@ __global__ void sort_hist_kernel(const int32_t* __restrict__ n_sub, int B, int32
   if (threadIdx.x < 64 && sh[threadIdx.x]) atomicAdd(&bins[threadIdx.x], sh[threadIdx.x]);
 }
 // Which systems leave the thread-per-system mapping?  The latency-optimised mappings shorten the sequential
-// chain of a sub-step-heavy system (by the factor `speedup`, measured per N) but spend 2-3.5x the FP64-pipe time
-// per force evaluation, so only systems whose own chain would otherwise set the run time should use them:
-//  (1) a launch cannot finish before the heaviest system does on the fast mapping, i.e. n_sub_max / speedup
-//      thread-mapped sub-steps' worth of time: nothing with n_sub below that gains anything;
-//  (2) W = sum n_sub is the batch's work; W / resident is how many sub-steps per step every resident thread has to
-//      get through, so a thread-mapped system with n_sub <= kappa W / resident finishes with the bulk anyway.
-__global__ void sort_scan_kernel(int32_t* bins, float kappa, int resident, float speedup, int fixed_thr) {
+// chain of a sub-step-heavy system (by the factor `speedup`, measured per N) but spend 2-3.5x the FP64-pipe time per
+// force evaluation, so only systems whose own chain would otherwise set the run time should use them.  A launch
+// cannot finish before a system at the split_n_max cap (50 sub-steps per step) does on the fast mapping, which is as
+// long as 50 / speedup thread-mapped sub-steps: nothing below that gains anything.  The threshold is a function of N
+// alone -- NOT of the batch -- so that a system is integrated by the same arithmetic however the ensemble is
+// sharded over GPUs or batches (the mappings agree to rounding, not to the bit).
+__global__ void sort_scan_kernel(int32_t* bins, float speedup, int fixed_thr) {
   if (threadIdx.x == 0) {                          // descending: bin 63 first
-    long long W = 0;
-    int nmax = 1;
-    for (int b = 0; b < 64; ++b) {
-      W += (long long)max(b, 1) * bins[b];
-      if (bins[b] > 0) nmax = max(b, 1);
-    }
     int thr = fixed_thr;
-    if (thr < 0) {
-      const int t1 = (int)floorf((float)nmax / speedup);
-      const int t2 = (int)ceilf(kappa * (float)W / (float)resident);
-      thr = min(max(max(t1, t2), NB_HEAVY_NSUB), 63);
-    }
+    if (thr < 0) thr = min(max((int)floorf(50.0f / speedup), NB_HEAVY_NSUB), 63);
     int run = 0;
     for (int b = 63; b >= 0; --b) {
       if (b == thr) bins[64] = run;                // number of systems with n_sub > thr (the heavy head of perm)
@@ -419,35 +409,23 @@ int variational_batched(const double* q, const double* m, const double* s2, cons
   return NB_OK;
 }
 
-static float g_heavy_kappa = -1.f;
-static int g_heavy_fixed = -2;
+static int g_heavy_fixed = -1;
 
 int set_heavy_nsub(int thr) {
   if (thr < -1 || thr > 63) { set_error("nb_ensemble_set_heavy_nsub: threshold must be -1 (automatic) or 0..63"); return NB_ERR_ARG; }
-  if (g_heavy_fixed == -2) g_heavy_kappa = getenv("NB_HEAVY_KAPPA") ? (float)atof(getenv("NB_HEAVY_KAPPA")) : 2.0f;
   g_heavy_fixed = thr;
   return NB_OK;
 }
 
 int sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* ws, cudaStream_t st) {
-  if (g_heavy_fixed == -2) {     // tuning knobs: NB_HEAVY_KAPPA (default 2), NB_HEAVY_NSUB_FIXED (default: automatic)
-    const char* e = getenv("NB_HEAVY_KAPPA");
-    g_heavy_kappa = e ? (float)atof(e) : 2.0f;
-    e = getenv("NB_HEAVY_NSUB_FIXED");
-    g_heavy_fixed = e ? atoi(e) : -1;
-  }
   NB_CUDA_CHECK(cudaMemsetAsync(ws, 0, 66 * sizeof(int32_t), st));
   const int threads = 256;
   const int blocks = min((B + threads - 1) / threads, 148 * 8);
   sort_hist_kernel<<<blocks, threads, 0, st>>>(n_sub, B, ws);
-  // measured on B200 (tools/check_thr.py): chain time of an n_sub = 50 system, thread mapping / fast mapping, and
-  // the resident threads per SM of ensemble_main_kernel<N> (register-limited)
+  // measured on B200 (tools/check_thr.py): chain time of an n_sub = 50 system, thread mapping / fast mapping
   static const float speedup[9] = {1.f, 1.f, 1.f, 1.f, 1.8f, 2.1f, 3.0f, 3.5f, 4.5f};
-  static const int per_sm[9] = {384, 384, 640, 512, 512, 384, 384, 256, 256};
   const int n = (N >= 2 && N <= 8) ? N : 0;
-  static float sp_scale = -1.f;
-  if (sp_scale < 0.f) sp_scale = getenv("NB_HEAVY_SPEEDUP_SCALE") ? (float)atof(getenv("NB_HEAVY_SPEEDUP_SCALE")) : 1.0f;
-  sort_scan_kernel<<<1, 32, 0, st>>>(ws, g_heavy_kappa, 148 * per_sm[n], speedup[n] * sp_scale, g_heavy_fixed);
+  sort_scan_kernel<<<1, 32, 0, st>>>(ws, speedup[n], g_heavy_fixed);
   sort_scatter_kernel<<<blocks, threads, 0, st>>>(n_sub, B, ws, perm);
   NB_CUDA_CHECK(cudaGetLastError());
   return NB_OK;

@@ -266,9 +266,10 @@ def test_heavy_substep_mapping_matches_thread_mapping(E, O):
             assert abs(res[True][2][b, L.DYN_COLUMNS.index("MEGNO")] - Y) < 1e-6 * abs(Y)
 
 
-def test_automatic_heavy_threshold_is_batch_dependent_and_result_invariant(E, O):
-    """nb_sort_by_nsub picks the heavy threshold from N, max n_sub and sum n_sub; whatever it picks, features agree
-    with a run that forces everything onto the thread mapping (threshold 63) to rounding."""
+def test_heavy_threshold_depends_on_n_only_and_results_are_shard_invariant(E, O):
+    """nb_sort_by_nsub picks the heavy threshold from N alone (max(4, 50 / chain speed-up)), so a system is integrated
+    by the same arithmetic whatever batch it sits in: any split of the batch reproduces the full-batch bits.
+    Against a run with everything on the thread mapping (threshold 63) heavy systems agree to rounding."""
     import nbodysimproject_b200._lib as L
     rng = np.random.RandomState(5)
     N, B = 6, 3000
@@ -277,20 +278,26 @@ def test_automatic_heavy_threshold_is_batch_dependent_and_result_invariant(E, O)
     sep = 10 ** rng.uniform(-2.2, -0.5, B)
     q[:, 1] = q[:, 0] + np.stack([sep, np.zeros(B)], 1)
     v = rng.randn(B, N, 2) * 0.3
-    out = {}
-    for thr in (-1, 63):
+
+    def run(sl, thr=-1):
         L.check(L.load().nb_ensemble_set_heavy_nsub(thr))
-        bk = E.DeviceBucket(m, q, v, 0.3, 1.0, "yoshida4")
+        bk = E.DeviceBucket(m[sl], q[sl], v[sl], 0.3, 1.0, "yoshida4")
         bk.prepare(L.PREP_REMOVE_COM | L.PREP_CTOR_KICK, 0.01, 0.01, 0.01)
         bk.sort()
         dyn = bk.run(0.01, 30, 3, 0, flags=L.RUN_ENERGY | L.RUN_WRITE_STATE)
-        out[thr] = (bk.q.cpu().numpy(), dyn.cpu().numpy(), int(bk._bins[64]), int(bk._bins[65]), bk.n_sub.cpu().numpy())
-    L.check(L.load().nb_ensemble_set_heavy_nsub(-1))
-    n_heavy, thr = out[-1][2], out[-1][3]
-    nsub = out[-1][4]
-    assert out[63][2] == 0 and out[63][3] == 63
-    assert 4 <= thr < 63 and n_heavy == int((nsub > thr).sum()) and n_heavy > 0
-    assert thr >= int(nsub.max() / 3.0)                     # N = 6: measured chain speed-up 3.0
+        L.check(L.load().nb_ensemble_set_heavy_nsub(-1))
+        return bk.q.cpu().numpy(), dyn.cpu().numpy(), int(bk._bins[64]), int(bk._bins[65]), bk.n_sub.cpu().numpy()
+
+    full = run(slice(0, B))
+    nsub, thr = full[4], full[3]
+    assert thr == 16 and full[2] == int((nsub > thr).sum()) and full[2] > 0       # N = 6: floor(50 / 3.0)
+    # shards of very different size and composition: identical bits
+    parts = [run(slice(0, 7)), run(slice(7, 1900)), run(slice(1900, B))]
+    assert all(p[3] == thr for p in parts)
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), full[0])
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), full[1], equal_nan=True)
+    none = run(slice(0, B), 63)
+    assert none[2] == 0 and none[3] == 63
     light = nsub <= thr
-    assert np.array_equal(out[-1][0][light], out[63][0][light])
-    assert relerr(out[-1][0][~light], out[63][0][~light]) < 1e-9
+    assert np.array_equal(full[0][light], none[0][light])
+    assert relerr(full[0][~light], none[0][~light]) < 1e-9
