@@ -703,7 +703,7 @@ def main():
     ap.add_argument("--systems", type=int, default=1 << 20, help="systems per GPU (weak scaling)")
     ap.add_argument("--n", type=int, default=1 << 20, help="particles for --workload largen")
     ap.add_argument("--n-hamsoft", type=int, default=0, dest="n_hamsoft",
-                    help="particles for the ham_soft Strang sub-step timing of --workload largen (default min(n, 2^18))")
+                    help="particles for the ham_soft Strang sub-step timing of --workload largen (default: --n)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-largen", action="store_true", help="skip the secondary large-N force measurement")
     args = ap.parse_args()

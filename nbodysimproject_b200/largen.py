@@ -582,7 +582,7 @@ def bench_largen(args, world, rank, local, dev, sampler=None):
         t_e2e = float(tt[0])
     # full Strang sub-step of the adaptive-epsilon flow (C5 as BASELINE.json words it)
     strang = None
-    n_hs = int(getattr(args, "n_hamsoft", 0) or min(n, 1 << 18))
+    n_hs = int(getattr(args, "n_hamsoft", 0) or n)            # C5 as BASELINE.json words it: the same N = 2^20 particles
     if n_hs > 0:
         mh, qh, vh = make_disc(n_hs, seed=1)
         hs = LargeNHamSoftSimulation(mh, qh, vh, softening=2.0 / math.sqrt(n_hs), initial_dt=1e-3, device=dev)
