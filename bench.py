@@ -305,6 +305,8 @@ def impl_b200(args):
         nonlocal launches_per_step
         cur = torch.cuda.current_stream()
         n = 0
+        # the construction-time kernels of every bucket first (0.3 % of the step), then the runs: nb_ensemble_run_f64
+        # launches each bucket's sub-step-heavy head at high priority, so no head waits behind another bucket's bulk
         for N in Ns:
             bk = devb[N]
             bk.stream.wait_stream(cur)
@@ -313,16 +315,29 @@ def impl_b200(args):
                 bk.v.copy_(bk.v0)
                 bk.prepare(prep_flags, 0.01, 0.01, DT, 50, want_static=True)     # 1 kernel
                 bk.sort()                                                        # 3 kernels
-                bk.dyn = bk.run(DT, N_STEPS, interval, N_MEGNO, bk.rdr, bk.rdv, flags=L.RUN_ENERGY)  # 2+1+1+1
-                n += 9
+        for N in Ns:
+            bk = devb[N]
+            with torch.cuda.stream(bk.stream):
+                bk.dyn = bk.run(DT, N_STEPS, interval, N_MEGNO, bk.rdr, bk.rdv, flags=L.RUN_ENERGY)  # 2+2+1+1 kernels
+                n += 10
         for N in Ns:
             cur.wait_stream(devb[N].stream)
         launches_per_step = n
 
+    def restore_e2e_inputs():
+        # nb_ensemble_analyze_host* returns the kicked velocities in the caller's v (the reference mutates the caller's
+        # sims the same way): put the original inputs back.  Bench scaffolding, outside the timed intervals.
+        for N in Ns:
+            host[N]["v_work"].copy_(host[N]["v"])
+
     def step_e2e():
-        for slot, N in enumerate(Ns):
+        """One end-to-end step: pinned host inputs -> H2D -> kernels -> D2H of both feature tables, all buckets in
+        flight on their own workspace slots; returns the wall time of exactly that."""
+        t0 = time.perf_counter()
+        # largest transfers first: that bucket's H2D is not queued behind everyone else's and its D2H overlaps the
+        # kernels of the buckets issued after it
+        for slot, N in enumerate(sorted(Ns, key=lambda n: -host[n]["m"].numel())):
             hb = host[N]
-            hb["v_work"].copy_(hb["v"])
             B = hb["m"].shape[0]
             L.check(lib.nb_ensemble_analyze_host_async(
                 L.ptr(hb["m"]), L.ptr(hb["q"]), L.ptr(hb["v_work"]), L.ptr(hb["eps"]), 1.0, B, N, L.MODES[MODE],
@@ -331,6 +346,7 @@ def impl_b200(args):
                 "nb_ensemble_analyze_host_async")
         for slot in range(min(len(Ns), 8)):
             L.check(lib.nb_host_sync(slot), "nb_host_sync")
+        return time.perf_counter() - t0
 
     def barrier():
         torch.cuda.synchronize()
@@ -356,13 +372,16 @@ def impl_b200(args):
     t_dev = e0.elapsed_time(e1) * 1e-3
     # ---- e2e: host buffers through the C ABI
     for _ in range(max(1, min(args.warmup, 2))):
+        restore_e2e_inputs()
         step_e2e()
     barrier()
-    t0 = time.perf_counter()
+    t_e2e = 0.0
     for _ in range(args.steps):
-        step_e2e()
+        restore_e2e_inputs()
+        if world > 1:
+            dist.barrier()
+        t_e2e += step_e2e()
     torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
     barrier()
     clocks = sampler.stop(mark0, mark1) if rank == 0 else None
     if world > 1:

@@ -19,7 +19,9 @@ struct RunArgs {
   const int32_t* n_sub;
   const int32_t* perm;
   const int32_t* n_heavy;   // device int: the first *n_heavy entries of perm go to the lane-per-body mapping
-  int group_blocks;         // CTAs [0, group_blocks) of the main/megno kernels run that mapping
+  int group_blocks;         // logical CTAs [0, group_blocks) of the main/megno kernels run that mapping
+  int block0;               // logical index of this launch's CTA 0 (the main kernel may be split into head + rest)
+  int block_count;          // logical CTAs of this launch (0 = all)
   const double* raw_dr;
   const double* raw_dv;
   double* dyn;

@@ -176,6 +176,9 @@ constexpr int NB_HOST_SLOTS = 8;
 struct HostWs {
   int device = -1;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // early D2H of what is final after the prepare kernel (static features, kicked v, n_sub)
+  cudaEvent_t prep_done = nullptr;
+  cudaEvent_t copy_done = nullptr;      // end of the previous call's early D2H: the next call on this slot waits for it
   void* buf = nullptr;
   size_t cap = 0;
 };
@@ -185,15 +188,31 @@ static std::mutex g_ws_mu;
 static int ws_reserve(int slot, int device, size_t bytes) {
   HostWs& w = g_ws[slot];
   if (w.device != device) {
-    if (w.device >= 0) { cudaSetDevice(w.device); if (w.buf) cudaFree(w.buf); if (w.stream) cudaStreamDestroy(w.stream); }
+    if (w.device >= 0) {
+      cudaSetDevice(w.device);
+      if (w.buf) cudaFree(w.buf);
+      if (w.stream) cudaStreamDestroy(w.stream);
+      if (w.copy_stream) cudaStreamDestroy(w.copy_stream);
+      if (w.prep_done) cudaEventDestroy(w.prep_done);
+      if (w.copy_done) cudaEventDestroy(w.copy_done);
+    }
     w = HostWs();
     NB_CUDA_CHECK(cudaSetDevice(device));
-    NB_CUDA_CHECK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    // high priority: everything of a bucket except the bulk of its main kernel (which ensemble_run_classic moves
+    // to a normal-priority side stream) should be dispatched ahead of other buckets' queued bulk CTAs
+    int prio_lo = 0, prio_hi = 0;
+    NB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    NB_CUDA_CHECK(cudaStreamCreateWithPriority(&w.stream, cudaStreamNonBlocking, prio_hi));
+    NB_CUDA_CHECK(cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
+    NB_CUDA_CHECK(cudaEventCreateWithFlags(&w.prep_done, cudaEventDisableTiming));
+    NB_CUDA_CHECK(cudaEventCreateWithFlags(&w.copy_done, cudaEventDisableTiming));
+    NB_CUDA_CHECK(cudaEventRecord(w.copy_done, w.copy_stream));
     w.device = device;
   }
   NB_CUDA_CHECK(cudaSetDevice(device));
   if (w.cap < bytes) {
     NB_CUDA_CHECK(cudaStreamSynchronize(w.stream));
+    NB_CUDA_CHECK(cudaStreamSynchronize(w.copy_stream));
     if (w.buf) cudaFree(w.buf);
     w.buf = nullptr;
     w.cap = 0;
@@ -250,7 +269,7 @@ int nb_ensemble_run_f64(const double* m, double* q, double* v, const double* eps
                        eps_pi, hs_params, dyn_features, status, (cudaStream_t)stream);
   }
   if (!eps) { set_error("nb_ensemble_run_f64: eps is required"); return NB_ERR_ARG; }
-  RunArgs a{m, q, v, eps, G, B, flags, dt, n_steps, sample_interval, n_megno, n_sub, perm, perm ? n_heavy : nullptr, 0, raw_dr, raw_dv, dyn_features, status};
+  RunArgs a{m, q, v, eps, G, B, flags, dt, n_steps, sample_interval, n_megno, n_sub, perm, perm ? n_heavy : nullptr, 0, 0, 0, raw_dr, raw_dv, dyn_features, status};
   return ensemble_run_classic(a, N, mode, (cudaStream_t)stream);
 }
 
@@ -298,7 +317,7 @@ int nb_ensemble_analyze_host_async(const double* m, const double* q, double* v, 
   const size_t sz_m = align256(bn * 8), sz_q = align256(bn * 16), sz_b = align256((size_t)B * 8);
   const size_t sz_dyn = align256((size_t)B * NB_N_DYN * 8), sz_stat = align256((size_t)B * NB_N_STATIC * 8);
   const size_t sz_i = align256((size_t)B * 4);
-  const size_t total = sz_m + 4 * sz_q + sz_b + sz_dyn + sz_stat + 3 * sz_i + 512;
+  const size_t total = sz_m + 5 * sz_q + sz_b + sz_dyn + sz_stat + 3 * sz_i + 512;
   int rc = ws_reserve(slot, device, total);
   if (rc != NB_OK) return rc;
   cudaStream_t st = g_ws[slot].stream;
@@ -308,6 +327,7 @@ int nb_ensemble_analyze_host_async(const double* m, const double* q, double* v, 
   double* d_v = (double*)p; p += sz_q;
   double* d_dr = (double*)p; p += sz_q;
   double* d_dv = (double*)p; p += sz_q;
+  double* d_vk = (double*)p; p += sz_q;      // kicked velocities, frozen for the early D2H while the run advances d_v
   double* d_eps = (double*)p; p += sz_b;
   double* d_dyn = (double*)p; p += sz_dyn;
   double* d_stat = (double*)p; p += sz_stat;
@@ -315,6 +335,7 @@ int nb_ensemble_analyze_host_async(const double* m, const double* q, double* v, 
   int32_t* d_perm = (int32_t*)p; p += sz_i;
   int32_t* d_status = (int32_t*)p; p += sz_i;
   int32_t* d_bins = (int32_t*)p;
+  NB_CUDA_CHECK(cudaStreamWaitEvent(st, g_ws[slot].copy_done, 0));   // the workspace is reused: previous early D2H first
   NB_CUDA_CHECK(cudaMemcpyAsync(d_m, m, bn * 8, cudaMemcpyHostToDevice, st));
   NB_CUDA_CHECK(cudaMemcpyAsync(d_q, q, bn * 16, cudaMemcpyHostToDevice, st));
   NB_CUDA_CHECK(cudaMemcpyAsync(d_v, v, bn * 16, cudaMemcpyHostToDevice, st));
@@ -328,17 +349,25 @@ int nb_ensemble_analyze_host_async(const double* m, const double* q, double* v, 
   PrepArgs pa{d_m, d_q, d_v, d_eps, G, B, mode, pf, kick_dt, sched_dt, dt, split_n_max, nullptr, d_nsub, d_stat};
   rc = ensemble_prepare(pa, N, st);
   if (rc != NB_OK) return rc;
-  if (pf & (NB_PREP_REMOVE_COM | NB_PREP_CTOR_KICK | NB_PREP_SNAPSHOT_KICK))
-    NB_CUDA_CHECK(cudaMemcpyAsync(v, d_v, bn * 16, cudaMemcpyDeviceToHost, st));   // the reference mutates the caller's sims
+  // Everything that is final after the prepare kernel goes back on the copy stream while the run is in flight:
+  // the kicked velocities (the reference mutates the caller's sims), the static features and n_sub -- 60 % of the
+  // D2H bytes, which would otherwise all queue up behind the run together with the dynamic features.
+  cudaStream_t cs = g_ws[slot].copy_stream;
+  const bool kicked = (pf & (NB_PREP_REMOVE_COM | NB_PREP_CTOR_KICK | NB_PREP_SNAPSHOT_KICK)) != 0;
+  if (kicked) NB_CUDA_CHECK(cudaMemcpyAsync(d_vk, d_v, bn * 16, cudaMemcpyDeviceToDevice, st));
+  NB_CUDA_CHECK(cudaEventRecord(g_ws[slot].prep_done, st));
+  NB_CUDA_CHECK(cudaStreamWaitEvent(cs, g_ws[slot].prep_done, 0));
+  if (kicked) NB_CUDA_CHECK(cudaMemcpyAsync(v, d_vk, bn * 16, cudaMemcpyDeviceToHost, cs));
+  if (static_features) NB_CUDA_CHECK(cudaMemcpyAsync(static_features, d_stat, (size_t)B * NB_N_STATIC * 8, cudaMemcpyDeviceToHost, cs));
+  if (n_sub_out) NB_CUDA_CHECK(cudaMemcpyAsync(n_sub_out, d_nsub, (size_t)B * 4, cudaMemcpyDeviceToHost, cs));
+  NB_CUDA_CHECK(cudaEventRecord(g_ws[slot].copy_done, cs));
   rc = sort_by_nsub(d_nsub, B, N, d_perm, d_bins, st);
   if (rc != NB_OK) return rc;
   const int interval = n_steps / 100 > 1 ? n_steps / 100 : 1;
-  RunArgs ra{d_m, d_q, d_v, d_eps, G, B, NB_RUN_ENERGY, dt, n_steps, interval, n_megno, d_nsub, d_perm, d_bins + 64, 0, d_dr, d_dv, d_dyn, d_status};
+  RunArgs ra{d_m, d_q, d_v, d_eps, G, B, NB_RUN_ENERGY, dt, n_steps, interval, n_megno, d_nsub, d_perm, d_bins + 64, 0, 0, 0, d_dr, d_dv, d_dyn, d_status};
   rc = ensemble_run_classic(ra, N, mode, st);
   if (rc != NB_OK) return rc;
   NB_CUDA_CHECK(cudaMemcpyAsync(dyn_features, d_dyn, (size_t)B * NB_N_DYN * 8, cudaMemcpyDeviceToHost, st));
-  if (static_features) NB_CUDA_CHECK(cudaMemcpyAsync(static_features, d_stat, (size_t)B * NB_N_STATIC * 8, cudaMemcpyDeviceToHost, st));
-  if (n_sub_out) NB_CUDA_CHECK(cudaMemcpyAsync(n_sub_out, d_nsub, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   if (status) NB_CUDA_CHECK(cudaMemcpyAsync(status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   return NB_OK;
 }
@@ -348,6 +377,7 @@ int nb_host_sync(int slot) {
   if (g_ws[slot].device < 0) return NB_OK;
   NB_CUDA_CHECK(cudaSetDevice(g_ws[slot].device));
   NB_CUDA_CHECK(cudaStreamSynchronize(g_ws[slot].stream));
+  NB_CUDA_CHECK(cudaStreamSynchronize(g_ws[slot].copy_stream));
   return NB_OK;
 }
 

@@ -102,10 +102,10 @@ __device__ __forceinline__ void group_substep(const GroupCtx<N>& c, int b, doubl
 
 // phase 0: main loop + step_metrics sampling ; phase 1: MEGNO.
 template <int N, int MODE, bool GUARD>
-__device__ __forceinline__ void group_body(const RunArgs& a, int phase, int write_state) {
+__device__ __forceinline__ void group_body(const RunArgs& a, int phase, int write_state, int bid) {
   constexpr int G = 32 / N;
   const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int warp = (bid * (int)blockDim.x + (int)threadIdx.x) >> 5;
   const int n_heavy = min(*a.n_heavy, a.B);
   if (warp * G >= n_heavy) return;                      // warp-uniform exit
   // The warp stays fully converged (full-mask shuffles compile to bare SHFL; partial masks cost a WARPSYNC

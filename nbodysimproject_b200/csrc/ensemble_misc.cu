@@ -1,5 +1,7 @@
 // ensemble_misc.cu -- construction-time kernel, stand-alone pair kernels and the n_sub counting sort.
 #include <cstdlib>
+#include <mutex>
+#include <cstdint>
 #include "ensemble_run.cuh"
 
 namespace nb {
@@ -71,13 +73,62 @@ __global__ void __launch_bounds__(128) finalize_kernel(double* dyn, int B, int h
   f[NB_F_IS_STABLE] = ((ed < 0.01) && (ld < 0.01) && (f[NB_F_COM_MEAN] < 1.0) && (f[NB_F_MEGNO] < 10.0)) ? 1.0 : 0.0;
 }
 
-int ensemble_run_classic(const RunArgs& a, int N, int mode, cudaStream_t st) {
+// ---------------------------------------------------------------------------------------------
+// Heads first.  Each bucket's launch ends in a latency-bound tail: the sub-step-heavy systems at the head of the
+// n_sub-sorted permutation run long sequential chains while the bulk is throughput-bound.  When several buckets are in
+// flight (one stream each) the block scheduler works through the kernels roughly in launch order, so the chains of
+// the buckets launched later START late and finish last (measured: 54.5 ms for the six C3 main kernels, 48.5 ms when
+// every head starts first).  The main kernel is therefore split into a HEAD launch (the latency-mapped CTAs plus the
+// first 5 % of the thread-mapped ones) and a REST launch, and the head -- together with the small energy kernel that
+// must precede it -- runs on a stream of HIGHER priority than the rest: its CTAs are dispatched ahead of every queued
+// bulk CTA of every bucket.  If the caller's stream already has the highest priority (the *_host slots) the rest is
+// demoted to an internal normal-priority stream, otherwise the head is promoted to an internal high-priority one.
+// Internal streams / events are created once per device (the only allocation the device-pointer entry points make).
+// ---------------------------------------------------------------------------------------------
+constexpr int NB_SIDE = 32;   // distinct caller streams served without sharing a side stream (more: hashed)
+struct SidePool {
+  bool init = false;
+  int prio_hi = 0, prio_lo = 0;
+  cudaStream_t hi[NB_SIDE], lo[NB_SIDE];
+  cudaEvent_t ev[NB_SIDE][3];
+  cudaStream_t owner[NB_SIDE];
+  int n_owner = 0;
+};
+static SidePool g_side[16];
+static std::mutex g_side_mu;
+static int g_split_min_b = -1;        // below this a bucket is one launch (nothing to overlap); NB_SPLIT_MIN_B overrides
+
+static int side_pool(int dev, cudaStream_t st, SidePool** out, int* k) {
+  SidePool& p = g_side[dev & 15];
+  if (!p.init) {
+    NB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&p.prio_lo, &p.prio_hi));
+    for (int i = 0; i < NB_SIDE; ++i) {
+      NB_CUDA_CHECK(cudaStreamCreateWithPriority(&p.hi[i], cudaStreamNonBlocking, p.prio_hi));
+      NB_CUDA_CHECK(cudaStreamCreateWithPriority(&p.lo[i], cudaStreamNonBlocking, p.prio_lo));
+      for (int e = 0; e < 3; ++e) NB_CUDA_CHECK(cudaEventCreateWithFlags(&p.ev[i][e], cudaEventDisableTiming));
+    }
+    p.init = true;
+  }
+  int idx = -1;
+  for (int i = 0; i < p.n_owner; ++i) if (p.owner[i] == st) idx = i;
+  if (idx < 0) {
+    idx = p.n_owner < NB_SIDE ? p.n_owner++ : (int)(((uintptr_t)st >> 6) % NB_SIDE);
+    p.owner[idx] = st;
+  }
+  *out = &p;
+  *k = idx;
+  return NB_OK;
+}
+
+int ensemble_run_classic(const RunArgs& a_in, int N, int mode, cudaStream_t st) {
   if (N < NB_MIN_N || N > NB_MAX_N) { set_error("N must be in 2..8"); return NB_ERR_ARG; }
-  auto phase = [&](int ph, int write_state) -> int {
+  RunArgs a = a_in;
+  if (g_split_min_b < 0) g_split_min_b = getenv("NB_SPLIT_MIN_B") ? atoi(getenv("NB_SPLIT_MIN_B")) : 4096;
+  auto phase = [&](int ph, int write_state, const RunArgs& ra, cudaStream_t s) -> int {
     switch (mode) {
-      case NB_MODE_VERLET: return ensemble_run_verlet(a, N, ph, write_state, st);
-      case NB_MODE_YOSHIDA4: return ensemble_run_yoshida4(a, N, ph, write_state, st);
-      case NB_MODE_WHFAST: return ensemble_run_whfast(a, N, ph, write_state, st);
+      case NB_MODE_VERLET: return ensemble_run_verlet(ra, N, ph, write_state, s);
+      case NB_MODE_YOSHIDA4: return ensemble_run_yoshida4(ra, N, ph, write_state, s);
+      case NB_MODE_WHFAST: return ensemble_run_whfast(ra, N, ph, write_state, s);
       default: set_error("nb_ensemble_run_f64: unsupported mode"); return NB_ERR_UNSUPPORTED;
     }
   };
@@ -85,12 +136,52 @@ int ensemble_run_classic(const RunArgs& a, int N, int mode, cudaStream_t st) {
   const bool energy = (a.flags & NB_RUN_ENERGY) != 0 && a.dyn != nullptr;
   const bool megno = a.n_megno > 0;
   const int write = ((a.flags & NB_RUN_WRITE_STATE) || energy || megno) ? 1 : 0;
-  if (energy) energy_kernel<<<blocks, threads, 0, st>>>(a.m, a.q, a.v, a.eps, a.G, a.B, N, a.dyn, 0);
-  int rc = phase(0, write);
-  if (rc != NB_OK) return rc;
+  const bool split = a.perm && a.n_heavy && a.B >= g_split_min_b && a.n_steps > 0 &&
+                     (mode == NB_MODE_VERLET || mode == NB_MODE_YOSHIDA4);
+  int rc;
+  if (!split) {
+    if (energy) energy_kernel<<<blocks, threads, 0, st>>>(a.m, a.q, a.v, a.eps, a.G, a.B, N, a.dyn, 0);
+    rc = phase(0, write, a, st);
+    if (rc != NB_OK) return rc;
+  } else {
+    int total = 0, prefix = 0;
+    if (mode == NB_MODE_YOSHIDA4) main_blocks_n<NB_MODE_YOSHIDA4>(a, N, &total, &prefix);
+    else main_blocks_n<NB_MODE_VERLET>(a, N, &total, &prefix);
+    int head = prefix + (blocks + 19) / 20;
+    if (head > total) head = total;
+    int dev = 0;
+    NB_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_side_mu);
+    SidePool* sp = nullptr;
+    int k = 0;
+    rc = side_pool(dev, st, &sp, &k);
+    if (rc != NB_OK) return rc;
+    int prio = 0;
+    NB_CUDA_CHECK(cudaStreamGetPriority(st, &prio));
+    const bool st_is_high = prio <= sp->prio_hi && sp->prio_hi != sp->prio_lo;
+    cudaStream_t s_head = st_is_high ? st : sp->hi[k];
+    cudaStream_t s_rest = st_is_high ? sp->lo[k] : st;
+    cudaStream_t side = st_is_high ? s_rest : s_head;
+    NB_CUDA_CHECK(cudaEventRecord(sp->ev[k][0], st));              // fork: the side stream joins the caller's order
+    NB_CUDA_CHECK(cudaStreamWaitEvent(side, sp->ev[k][0], 0));
+    if (energy) energy_kernel<<<blocks, threads, 0, s_head>>>(a.m, a.q, a.v, a.eps, a.G, a.B, N, a.dyn, 0);
+    NB_CUDA_CHECK(cudaEventRecord(sp->ev[k][1], s_head));          // E0 is read before anything advances the state
+    NB_CUDA_CHECK(cudaStreamWaitEvent(s_rest, sp->ev[k][1], 0));
+    RunArgs h = a, r = a;
+    h.block0 = 0; h.block_count = head;
+    r.block0 = head; r.block_count = total - head;
+    rc = phase(0, write, h, s_head);
+    if (rc != NB_OK) return rc;
+    if (r.block_count > 0) {
+      rc = phase(0, write, r, s_rest);
+      if (rc != NB_OK) return rc;
+    }
+    NB_CUDA_CHECK(cudaEventRecord(sp->ev[k][2], side));            // join
+    NB_CUDA_CHECK(cudaStreamWaitEvent(st, sp->ev[k][2], 0));
+  }
   if (energy) energy_kernel<<<blocks, threads, 0, st>>>(a.m, a.q, a.v, a.eps, a.G, a.B, N, a.dyn, 1);
   if (megno) {
-    rc = phase(1, (a.flags & NB_RUN_WRITE_STATE) ? 1 : 0);
+    rc = phase(1, (a.flags & NB_RUN_WRITE_STATE) ? 1 : 0, a, st);
     if (rc != NB_OK) return rc;
   }
   if (a.dyn) finalize_kernel<<<blocks, threads, 0, st>>>(a.dyn, a.B, energy ? 1 : 0, megno ? 1 : 0);

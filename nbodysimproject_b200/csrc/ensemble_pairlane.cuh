@@ -40,11 +40,11 @@ __device__ __forceinline__ int pl_pair_index(int N, int a, int b) {   // a < b
 }
 
 template <int N, int MODE, bool GUARD>
-__device__ __forceinline__ void pairlane_main(const RunArgs& a, int write_state, double* smem) {
+__device__ __forceinline__ void pairlane_main(const RunArgs& a, int write_state, double* smem, int bid) {
   constexpr int P = PairLane<N>::P, S = PairLane<N>::S;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int warp = (bid * (int)blockDim.x + (int)threadIdx.x) >> 5;
   const int n_heavy = min(*a.n_heavy, a.B);
   if (warp * S >= n_heavy) return;                 // warp-uniform exit
   // spare lanes and empty slots shadow a live (system, pair): they compute and publish identical values and

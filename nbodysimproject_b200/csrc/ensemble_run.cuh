@@ -249,17 +249,18 @@ __host__ __device__ constexpr bool use_pairlane() { return N >= 5 && MODE != NB_
 // ---------------------------------------------------------------------------------------------
 template <int N, int MODE, bool GUARD, bool EXACT>
 __global__ void __launch_bounds__(128) ensemble_main_kernel(RunArgs a, int write_state) {
-  if (MODE != NB_MODE_WHFAST && (int)blockIdx.x < a.group_blocks) {   // latency-optimised mappings for the n_sub-heavy head
+  const int bid = (int)blockIdx.x + a.block0;                          // logical CTA (the launch may be split head / rest)
+  if (MODE != NB_MODE_WHFAST && bid < a.group_blocks) {                // latency-optimised mappings for the n_sub-heavy head
     if constexpr (use_pairlane<N, MODE>()) {
       __shared__ __align__(16) double pl_smem[PairLane<N>::SMEM_DOUBLES];
-      pairlane_main<N, MODE, GUARD>(a, write_state, pl_smem);          // one pair per lane (N >= 5)
+      pairlane_main<N, MODE, GUARD>(a, write_state, pl_smem, bid);     // one pair per lane (N >= 5)
     } else {
-      group_body<N, MODE == NB_MODE_WHFAST ? NB_MODE_VERLET : MODE, GUARD>(a, 0, write_state);   // one body per lane
+      group_body<N, MODE == NB_MODE_WHFAST ? NB_MODE_VERLET : MODE, GUARD>(a, 0, write_state, bid);   // one body per lane
     }
     return;
   }
   const int nh = (a.group_blocks > 0) ? min(*a.n_heavy, a.B) : 0;
-  const int t = ((int)blockIdx.x - a.group_blocks) * blockDim.x + threadIdx.x;
+  const int t = (bid - a.group_blocks) * blockDim.x + threadIdx.x;
   if (t >= a.B - nh) return;
   const int sys = a.perm ? a.perm[t + nh] : t;
   SysState<N> s;
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(128) ensemble_main_kernel(RunArgs a, int write
 template <int N, int MODE, bool GUARD, bool EXACT>
 __global__ void __launch_bounds__(128) ensemble_megno_kernel(RunArgs a, int write_state) {
   if (MODE != NB_MODE_WHFAST && (int)blockIdx.x < a.group_blocks) {   // lane-per-body mapping for the n_sub-heavy head
-    group_body<N, MODE == NB_MODE_WHFAST ? NB_MODE_VERLET : MODE, GUARD>(a, 1, write_state);
+    group_body<N, MODE == NB_MODE_WHFAST ? NB_MODE_VERLET : MODE, GUARD>(a, 1, write_state, (int)blockIdx.x);
     return;
   }
   const int nh = (a.group_blocks > 0) ? min(*a.n_heavy, a.B) : 0;
@@ -428,7 +429,10 @@ static int launch_run_mode(const RunArgs& a_in, int phase, int write_state, cuda
   a.group_blocks = (MODE != NB_MODE_WHFAST && a.n_heavy && a.perm)
                        ? ((phase == 0 && use_pairlane<N, MODE>()) ? pairlane_blocks_for<N>(a.B) : group_blocks_for<N>(a.B))
                        : 0;
-  const int blocks = a.group_blocks + (a.B + threads - 1) / threads;
+  int blocks = a.group_blocks + (a.B + threads - 1) / threads;
+  if (phase == 0 && a.block_count > 0) blocks = min(a.block_count, blocks - a.block0);   // head or rest of a split launch
+  if (phase != 0) { a.block0 = 0; a.block_count = 0; }
+  if (blocks <= 0) return NB_OK;
   const bool exact = MODE == NB_MODE_WHFAST && (a.flags & NB_RUN_KEPLER_EXACT) != 0;
   if (phase == 0) {
     if (exact) ensemble_main_kernel<N, MODE, true, MODE == NB_MODE_WHFAST><<<blocks, threads, 0, st>>>(a, write_state);
@@ -439,6 +443,27 @@ static int launch_run_mode(const RunArgs& a_in, int phase, int write_state, cuda
   }
   NB_CUDA_CHECK(cudaGetLastError());
   return NB_OK;
+}
+
+// logical CTAs of the phase-0 launch and how many of them form the latency-mapped prefix
+template <int N, int MODE>
+static void main_blocks_mode(const RunArgs& a, int* total, int* prefix) {
+  const int g = (MODE != NB_MODE_WHFAST && a.n_heavy && a.perm)
+                    ? (use_pairlane<N, MODE>() ? pairlane_blocks_for<N>(a.B) : group_blocks_for<N>(a.B)) : 0;
+  *prefix = g;
+  *total = g + (a.B + 127) / 128;
+}
+template <int MODE>
+static void main_blocks_n(const RunArgs& a, int N, int* total, int* prefix) {
+  switch (N) {
+    case 2: main_blocks_mode<2, MODE>(a, total, prefix); break;
+    case 3: main_blocks_mode<3, MODE>(a, total, prefix); break;
+    case 4: main_blocks_mode<4, MODE>(a, total, prefix); break;
+    case 5: main_blocks_mode<5, MODE>(a, total, prefix); break;
+    case 6: main_blocks_mode<6, MODE>(a, total, prefix); break;
+    case 7: main_blocks_mode<7, MODE>(a, total, prefix); break;
+    default: main_blocks_mode<8, MODE>(a, total, prefix); break;
+  }
 }
 
 template <int MODE>
