@@ -7,8 +7,11 @@
  *
  * Conventions
  *   - plain pointers + sizes, no torch types.  `*_f64` / `*_f32` entry points take DEVICE pointers
- *     (caller-owned, e.g. torch tensors) and a cudaStream_t passed as `void*`; they never allocate,
- *     never synchronise and are safe to call concurrently on distinct streams.
+ *     (caller-owned, e.g. torch tensors) and a cudaStream_t passed as `void*`; they never synchronise, never
+ *     allocate device memory and are safe to call concurrently on distinct streams.  (nb_ensemble_run_f64 creates a
+ *     per-device pool of internal priority streams and events on first use: it launches the sub-step-heavy head of
+ *     a large batch at higher priority than the bulk and joins both back into the caller's stream before returning
+ *     control of it, so stream-ordered semantics are unchanged.)
  *   - `*_host` entry points take HOST pointers and do H2D -> kernels -> D2H themselves (they own a
  *     cached per-device workspace); they return after the result is in the host buffers.
  *   - arrays use the reference's own layouts: m[B][N], q[B][N][2], v[B][N][2] row-major fp64
