@@ -242,43 +242,124 @@ __device__ __forceinline__ double hs_fd_step(double x) {
 // eps*(q) and its gradient, cooperatively over the warp: lane 0 evaluates the unperturbed configuration,
 // lane 1+2c+s the coordinate c = 2 i + a perturbed by +h (s = 0) or -h (s = 1).  Every lane returns the full
 // gradient.  hamsoft_eps_model.py:94-234.
-// lanes per system: 4 N + 1 evaluations fit a half warp for N <= 3, so two systems share a warp there
+// Lanes per system.  4 N + 1 evaluations fit a half warp for N <= 3, so two systems share a warp there.  For N = 4
+// (17) and N = 8 (33) the odd one out -- the UNPERTURBED evaluation -- is computed cooperatively instead (one body per
+// lane, Jacobi sweeps exchanged by shuffles; same arithmetic per body, so the same bits as the serial solve at 1/N of
+// its cost): the 4 N perturbed evaluations then fit a half warp (N = 4: two systems per warp) or one pass (N = 8).
 template <int N>
-struct HsLanes { static constexpr int LPS = (4 * N + 1 <= 16) ? 16 : 32; };
+struct HsLanes {
+  static constexpr bool COOP = (N == 4 || N == 8);
+  static constexpr int NE = COOP ? 4 * N : 4 * N + 1;        // evaluations spread one per lane
+  static constexpr int LPS = (NE <= 16) ? 16 : 32;
+};
+
+// eps_target of the unperturbed configuration, cooperatively over the lanes [base, base + LPS) of one system
+// (hamsoft_eps_model.py:316-400 + :240-289).  All lanes of the group hold the same x, y, m.  Warp-uniform control flow:
+// the sweep loop always runs 8 times and a converged group simply stops updating (the two systems of a warp may
+// converge at different sweeps, and the shuffles need the whole warp).
+template <int N>
+__device__ __forceinline__ double hs_eps_target_coop(const double* x, const double* y, const double* m, double eps_cur,
+                                                     const HsPar& P, int lane, int base) {
+  constexpr int LPS = HsLanes<N>::LPS;
+  const int i = lane < N ? lane : 0;                        // spare lanes shadow body 0
+  double xi = x[0], yi = y[0], mi = m[0];
+#pragma unroll
+  for (int k = 1; k < N; ++k) if (k == i) { xi = x[k]; yi = y[k]; mi = m[k]; }
+  double lo = P.eps_min, hi = P.eps_max;
+  if (hi < lo) { const double t = lo; lo = hi; hi = t; }
+  const double flo = fmax(lo, 1.0e-12), cap = fmax(flo, hi);
+  double h0 = eps_cur;
+  if (!is_finite(h0) || h0 <= 0.0) h0 = 1.0;
+  h0 = fmin(fmax(h0, flo), cap);
+  double r2[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    // the serial solver stores r^2 of the pair (min, max): same value, the squares do not see the sign
+    const double dx = (i < j) ? xi - x[j] : x[j] - xi, dy = (i < j) ? yi - y[j] : y[j] - yi;
+    r2[j] = dx * dx + dy * dy;
+  }
+  double hcur = h0;
+  bool done = false;
+#pragma unroll 1
+  for (int it = 0; it < 8; ++it) {
+    const double hj = fmax(hcur, 1.0e-12);
+    const double h2 = hj * hj;
+    const double c = 1.0 / (NB_PI * h2);
+    const double nih2 = -1.0 / h2;
+    double S = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const double term = m[j] * (c * exp(r2[j] * nih2));
+      if (j != i) S += term;
+    }
+    const double Si = fmax(S, 1.0e-30);
+    double v = P.eta * sqrt(mi / Si);
+    if (!is_finite(v) || v <= 0.0) v = hcur;
+    if (v < flo) v = flo;
+    else if (v > cap) v = cap;
+    double rel = fabs(v - hcur) / fmax(hcur, 1.0e-12);
+#pragma unroll
+    for (int off = LPS / 2; off > 0; off >>= 1) rel = fmax(rel, __shfl_xor_sync(0xffffffffu, rel, off));
+    if (!done) hcur = v;
+    if (rel < 1.0e-6) done = true;                          // group-uniform
+  }
+  double h[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) h[k] = __shfl_sync(0xffffffffu, hcur, base + k);
+  double tmax = -h[0] / P.alpha;
+#pragma unroll
+  for (int k = 1; k < N; ++k) tmax = fmax(tmax, -h[k] / P.alpha);
+  double sum = 0.0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) sum += exp(-h[k] / P.alpha - tmax);
+  double es;
+  if (sum <= 0.0 || !is_finite(sum)) es = P.s0;
+  else es = -P.alpha * (tmax + log(sum));
+  if (P.policy == 0) {
+    double l2 = P.eps_min, h2b = P.eps_max;
+    if (h2b < l2) { const double t = l2; l2 = h2b; h2b = t; }
+    if (es < l2) es = l2;
+    else if (es > h2b) es = h2b;
+  }
+  return es;
+}
 
 template <int N>
 __device__ __forceinline__ double hs_eps_star_and_grad(const double* x, const double* y, const double* m,
                                                        double eps_cur, const HsPar& P, int lane_full, double* gx,
                                                        double* gy, bool& used_fallback) {
-  constexpr int NE = 4 * N + 1;
+  constexpr bool COOP = HsLanes<N>::COOP;
+  constexpr int NE = HsLanes<N>::NE;
   constexpr int LPS = HsLanes<N>::LPS;
+  constexpr int OFF = COOP ? 0 : 1;           // evaluation index of the first perturbed configuration
   const int lane = lane_full & (LPS - 1);     // lane within this system's group
   const int base = lane_full - lane;          // first lane of the group
   double f[2] = {0.0, 0.0};
 #pragma unroll
   for (int pass = 0; pass < (NE + LPS - 1) / LPS; ++pass) {
     const int e = lane + LPS * pass;          // evaluation index
-    const int ee = e < NE ? e : 0;            // idle lanes redo the unperturbed one
-    const int c = (ee - 1) >> 1;              // perturbed coordinate (ee >= 1)
-    const double sgn = ((ee - 1) & 1) ? -1.0 : 1.0;
+    const int ee = e < NE ? e : 0;            // idle lanes redo evaluation 0
+    const bool pert = COOP || ee >= 1;        // without COOP evaluation 0 is the unperturbed configuration
+    const int c = (ee - OFF) >> 1;            // perturbed coordinate
+    const double sgn = ((ee - OFF) & 1) ? -1.0 : 1.0;
     double px[N], py[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       px[i] = x[i];
       py[i] = y[i];
-      if (ee >= 1 && c == 2 * i) px[i] = x[i] + sgn * hs_fd_step(x[i]);
-      if (ee >= 1 && c == 2 * i + 1) py[i] = y[i] + sgn * hs_fd_step(y[i]);
+      if (pert && c == 2 * i) px[i] = x[i] + sgn * hs_fd_step(x[i]);
+      if (pert && c == 2 * i + 1) py[i] = y[i] + sgn * hs_fd_step(y[i]);
     }
     f[pass] = hs_eps_target<N>(px, py, m, eps_cur, P);
   }
-  const double es = __shfl_sync(0xffffffffu, f[0], base);
+  const double es = COOP ? hs_eps_target_coop<N>(x, y, m, eps_cur, P, lane, base) : __shfl_sync(0xffffffffu, f[0], base);
   double gmax2 = 0.0;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       const int c = 2 * i + a;
-      const int ep = 1 + 2 * c, em = 2 + 2 * c;
+      const int ep = OFF + 2 * c, em = OFF + 1 + 2 * c;
       const double fp = ep < LPS ? __shfl_sync(0xffffffffu, f[0], base + (ep & (LPS - 1)))
                                  : __shfl_sync(0xffffffffu, f[1], base + (ep & (LPS - 1)));
       const double fm = em < LPS ? __shfl_sync(0xffffffffu, f[0], base + (em & (LPS - 1)))

@@ -146,12 +146,13 @@ def test_hamsoft_barrier_policies_vs_golden():
 
 
 def test_hamsoft_two_systems_per_warp_for_small_n():
-    """N <= 3: 4 N + 1 <= 16 evaluations, so two systems share a warp (half-warp shuffles, the pair runs to the larger
-    sub-step count).  An odd batch with mixed n_sub must give every system exactly what it gets alone."""
+    """N <= 4: the finite-difference evaluations fit a half warp (N = 4 with the unperturbed solve done cooperatively),
+    so two systems share a warp (half-warp shuffles, the pair runs to the larger sub-step count).  An odd batch with
+    mixed n_sub must give every system exactly what it gets alone."""
     from nbodysimproject_b200 import hamsoft as H
     from nbodysimproject_b200.simulation import SimConfig
     rng = np.random.RandomState(11)
-    for N in (2, 3):
+    for N in (2, 3, 4):
         B = 7
         m = rng.uniform(0.5, 3.0, (B, N))
         q = rng.randn(B, N, 2) * rng.uniform(0.15, 1.0, (B, 1, 1))
@@ -164,7 +165,7 @@ def test_hamsoft_two_systems_per_warp_for_small_n():
         rr, rv = rng.randn(B, N, 2), rng.randn(B, N, 2)
         dyn = b.run(0.01, 6, 2, 3, rr, rv, flags=3, want_dyn=True).cpu().numpy()
         qa, ea = b.bk.q.cpu().numpy(), b.eps_pi.cpu().numpy()
-        if N == 3:
+        if N >= 3:
             assert len(np.unique(nsub)) > 1                    # the pairs really mix sub-step counts
         for i in range(B):
             b1 = H.HamSoftBucket(m[i:i + 1], q[i:i + 1], v[i:i + 1], hs[i:i + 1], np.array([[s0[i], 0.0]]), 1.0)

@@ -23,3 +23,18 @@ for rep in range(3):
     e0.record(); hb.run(0.01, steps); e1.record(); torch.cuda.synchronize()
 t = e0.elapsed_time(e1) * 1e-3
 print(f"hamsoft N=3 B={B} steps={steps}: {t*1e3:.2f} ms, {B*steps/t:.3e} system-steps/s")
+
+# generic N: random compact systems
+for N in (4, 8):
+    rng = np.random.RandomState(1)
+    Bn = B // 4
+    m = rng.uniform(0.5, 3.0, (Bn, N)); q = rng.randn(Bn, N, 2) * 0.8; v = rng.randn(Bn, N, 2) * 0.4
+    v -= (m[:, :, None] * v).sum(1, keepdims=True) / m.sum(1)[:, None, None]
+    hs, s0 = H.default_params(object(), 0.05, 0.005, Bn)
+    hb = H.HamSoftBucket(m, q, v, hs, np.stack([s0, np.zeros(Bn)], 1), 1.0)
+    hb.setup(calibrate=True, freeze_dt=0.01)
+    hb.n_sub[:] = 1
+    for rep in range(2):
+        e0.record(); hb.run(0.01, steps); e1.record(); torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3
+    print(f"hamsoft N={N} B={Bn} steps={steps} (n_sub forced to 1): {t*1e3:.2f} ms, {Bn*steps/t:.3e} system-substeps/s")
