@@ -263,6 +263,11 @@ def impl_b200(args):
 
     if args.workload == "largen":
         return bench_largen(args, torch, dist, world, rank, local, dev)
+    if args.workload == "c2":
+        bench_c2(args, torch, dist, world, rank, local, dev)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload in ("c4", "c1"):
         bench_secondary(args, torch, dist, world, rank, local, dev)
         if world > 1:
@@ -694,6 +699,69 @@ def bench_secondary(args, torch, dist, world, rank, local, dev):
     print(json.dumps(line))
 
 
+def _c2_sims(mode):
+    from nbodysimproject_b200.generators import InitialConditionGenerator, set_global_seed
+    set_global_seed(42)
+    gen = InitialConditionGenerator()
+    return [gen.create_simulation(3 + (i % 3), integrator_mode=mode) for i in range(10)]
+
+
+def _cpu_c2(job):
+    from oracle import nbody_oracle as O
+    m, q, v, soft = job
+    sim = O.OracleSim(m, q, v, softening=soft, integrator_mode="verlet")
+    rr, rv = np.random.default_rng(0).standard_normal((2, len(m), 2))
+    O.run_stability_analysis(sim, 1000, 0.01, "full", rr, rv)
+    return 1050
+
+
+def bench_c2(args, torch, dist, world, rank, local, dev):
+    """--workload c2 (BASELINE.json configs[1]): the quick_test cohort (10 systems, N = 3, 4, 5 cycling) analysed through
+    the PUBLIC PYTHON API -- NBodySimulation objects in, DataFrame out -- as the BASELINE wording has it (verlet, 1000
+    steps, 'full' mode with MEGNO).  Ten tiny systems are launch-latency-bound: this line measures the API overhead a
+    reference user sees, not the kernels."""
+    import io
+    import contextlib
+    from nbodysimproject_b200.stability import BatchStabilityAnalyzer
+    if rank != 0:
+        return
+
+    def step():
+        sims = _c2_sims("verlet")
+        np.random.seed(7)
+        with contextlib.redirect_stdout(io.StringIO()):
+            return BatchStabilityAnalyzer(n_steps=1000, dt=0.01, mode="full").analyze_batch(sims, show_progress=False)
+
+    for _ in range(args.warmup):
+        df = step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        df = step()
+    torch.cuda.synchronize()
+    t = time.perf_counter() - t0
+    sys_steps = 10 * 1050 * args.steps
+    cpu = None
+    if not args.no_cpu:
+        sims = _c2_sims("verlet")
+        jobs = [(s._mass.copy(), s._pos.copy(), s._vel.copy(), float(s.manager.s0)) for s in sims]
+        cores = min(os.cpu_count() or 1, len(jobs))
+        rate, dtc = _cpu_pool(_cpu_c2, jobs, cores)
+        cpu = {"value": rate, "unit": "system-steps/s", "cores": cores, "kind": "port",
+               "sample": f"the same 10 systems, oracle run_stability_analysis in {cores} processes, {dtc:.1f} s"}
+    print(json.dumps({
+        "metric": "system-steps/s", "value": sys_steps / t, "unit": "system-steps/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 MLTrainingPipeline.quick_test cohort (BASELINE.json configs[1]): 10 systems N=3,4,5, verlet, "
+                               "1000 steps + MEGNO, mode full, through NBodySimulation / BatchStabilityAnalyzer (includes "
+                               "building the 10 simulation objects and the DataFrame)",
+                   "columns": int(df.shape[1])},
+        "e2e": {"value": sys_steps / t, "unit": "system-steps/s", "h2d_bytes_per_step": int(10 * 4 * 5 * 8 * 3),
+                "d2h_bytes_per_step": int(10 * 47 * 8), "api": "BatchStabilityAnalyzer.analyze_batch"},
+        "gpu_launches": None, "roofline": None, "cpu_baseline": cpu}))
+
+
 def bench_largen(args, torch, dist, world, rank, local, dev):
     from nbodysimproject_b200.largen import bench_largen as run
     sampler = None
@@ -718,7 +786,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None, help="timed steps (default 20; 5 for c4 / c1 / largen)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="ensemble", choices=["ensemble", "largen", "c4", "c1"])
+    ap.add_argument("--workload", default="ensemble", choices=["ensemble", "largen", "c4", "c1", "c2"])
     ap.add_argument("--systems", type=int, default=1 << 20, help="systems per GPU (weak scaling)")
     ap.add_argument("--n", type=int, default=1 << 20, help="particles for --workload largen")
     ap.add_argument("--n-hamsoft", type=int, default=0, dest="n_hamsoft",
