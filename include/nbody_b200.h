@@ -136,6 +136,17 @@ int nb_ensemble_run_adaptive_f64(const double* m, double* q, double* v, double* 
                                  int barrier_exponent, double* energy_delta, double* eps_hist, int32_t* status,
                                  void* stream);
 
+/* ---- StabilityAnalyzer.run_stability_analysis (stability_analyzer.py:69-259) for adaptive-softening copies: E0,
+ *      n_steps adaptive macro steps with step_metrics sampling, E1, n_megno tangent-map steps, drifts and is_stable.
+ *      eps[B] = the softening the restored copy starts from (the original's sim._epsilon, simulation.py:473-482; in/out);
+ *      eps_energy[B] = the CONSTANT epsilon of the reference's energy diagnostics (diagnostics.py:474);
+ *      the variational equations use the current manager.step_s2 (tangent_map.py:21-59). */
+int nb_ensemble_analyze_adaptive_f64(const double* m, double* q, double* v, double* eps, const double* eps_energy,
+                                     const double* soft_par, double G, int B, int N, int mode, double dt, int n_steps,
+                                     int sample_interval, int n_megno, const int32_t* n_sub, const double* raw_dr,
+                                     const double* raw_dv, double k_wall, int barrier_exponent, double* energy_delta,
+                                     double* dyn_features, int32_t* status, void* stream);
+
 /* ---- a11/a14 ham_soft construction-time calibration, one thread per system, in place on hs_params / eps_pi:
  *      flags bit0: EpsilonModel.calibrate_from_initial_conditions (hamsoft_eps_model.py:645-729: alpha_run,
  *                  eps_min, eps0) + _calibrate_mu_from_timescales (hamiltonian_softening_integrator.py:251-296);

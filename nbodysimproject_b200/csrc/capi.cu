@@ -29,6 +29,11 @@ int sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* ws,
 int set_heavy_nsub(int thr);
 int generate_ensemble(int cohort, int N, int B, uint64_t seed, uint64_t first, double* m, double* q, double* v, double* eps,
                       cudaStream_t st);
+int ensemble_analyze_adaptive(const double* m, double* q, double* v, double* eps, const double* eps_energy,
+                              const double* soft_par, double G, int B, int N, int mode, double dt, int n_steps,
+                              int sample_interval, int n_megno, const int32_t* n_sub, const double* raw_dr,
+                              const double* raw_dv, double k_wall, int n_exp, double* e_delta, double* dyn, int32_t* status,
+                              cudaStream_t st);
 int mlp_classify(const double* dyn, const double* stat, const int32_t* idx, int F, const float* mean,
                  const float* inv_scale, const float* w1, const float* b1, const float* w2, const float* b2,
                  const float* w3, float b3, float threshold, int B, float* prob, int32_t* label, cudaStream_t st);
@@ -295,6 +300,16 @@ int nb_ensemble_run_adaptive_f64(const double* m, double* q, double* v, double* 
                                  void* stream) {
   return ensemble_run_adaptive(m, q, v, eps, soft_par, G, B, N, mode, dt, n_steps, n_sub, k_wall, barrier_exponent,
                                energy_delta, eps_hist, status, (cudaStream_t)stream);
+}
+
+int nb_ensemble_analyze_adaptive_f64(const double* m, double* q, double* v, double* eps, const double* eps_energy,
+                                     const double* soft_par, double G, int B, int N, int mode, double dt, int n_steps,
+                                     int sample_interval, int n_megno, const int32_t* n_sub, const double* raw_dr,
+                                     const double* raw_dv, double k_wall, int barrier_exponent, double* energy_delta,
+                                     double* dyn_features, int32_t* status, void* stream) {
+  return ensemble_analyze_adaptive(m, q, v, eps, eps_energy, soft_par, G, B, N, mode, dt, n_steps, sample_interval, n_megno,
+                                   n_sub, raw_dr, raw_dv, k_wall, barrier_exponent, energy_delta, dyn_features, status,
+                                   (cudaStream_t)stream);
 }
 
 int nb_sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* workspace, void* stream) {

@@ -28,6 +28,13 @@ struct AdaptArgs {
   double* e_delta;          // [B] softening_energy_delta, in/out
   double* eps_hist;         // [B][n_steps] softening after each macro step (optional)
   int32_t* status;
+  // analysis (run_stability_analysis on an adaptive copy): step_metrics sampling and the MEGNO phase
+  int sample_interval;
+  double* dyn;              // [B][NB_N_DYN] or null
+  const double* eps_energy; // [B] sim._epsilon: the constant epsilon the reference's diagnostics use (diagnostics.py:474)
+  int n_megno;
+  const double* raw_dr;
+  const double* raw_dv;
 };
 
 __device__ __forceinline__ double barrier_energy_dev(double eps, double a, double b, double k_wall, int n) {  // barrier.py:35-63
@@ -40,7 +47,9 @@ __device__ __forceinline__ double barrier_energy_dev(double eps, double a, doubl
   return (k_wall / (double)p) * (lp + rp);
 }
 
-template <int N, int MODE>
+// PHASE 0: n_steps macro steps (+ step_metrics sampling when a.dyn); PHASE 1: n_megno steps with the tangent map
+// (evolution_features.py:34-66; the variational equations use the CURRENT manager.step_s2, tangent_map.py:21-59)
+template <int N, int MODE, int PHASE>
 __global__ void __launch_bounds__(128) ensemble_adaptive_kernel(AdaptArgs a) {
   const int sys = blockIdx.x * blockDim.x + threadIdx.x;
   if (sys >= a.B) return;
@@ -76,7 +85,8 @@ __global__ void __launch_bounds__(128) ensemble_adaptive_kernel(AdaptArgs a) {
     for (int i = 0; i < N; ++i) { s.vx[i] = fma(h2, s.ax[i], s.vx[i]); s.vy[i] = fma(h2, s.ay[i], s.vy[i]); }
   };
 
-  for (int step = 0; step < a.n_steps; ++step) {
+  // one macro step: n_sub sub-steps, each followed by the softening refresh
+  auto macro_step = [&]() {
     double pending = 0.0;                                   // begin_step
 #pragma unroll 1
     for (int k = 0; k < n_sub; ++k) {
@@ -121,7 +131,119 @@ __global__ void __launch_bounds__(128) ensemble_adaptive_kernel(AdaptArgs a) {
       soft = eps_new;
       if (pending != 0.0) { e_delta += pending; pending = 0.0; }          // commit_substep
     }
-    if (a.eps_hist) a.eps_hist[(size_t)sys * a.n_steps + step] = soft;
+  };
+
+  if (PHASE == 0) {
+    double com_sum = 0.0, com_max = -1.0, var_sum = 0.0, var_max = -1.0, cos_sum = 0.0, cos_min = 2.0, th_sum = 0.0;
+    double Lfirst = 0.0;
+    bool have_first = false, cos_nan = false;
+    int n_samp = 0, next_sample = 0;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const double eps_d = a.eps_energy ? a.eps_energy[sys] : soft;
+    const double theta_eps = (eps_d != 0.0) ? atan2(0.0, eps_d) : nan;   // diagnostics.py:246-249 with pi = 0
+    const int interval = a.dyn ? a.sample_interval : 0;
+    for (int step = 0; step < a.n_steps; ++step) {
+      macro_step();
+      if (a.eps_hist) a.eps_hist[(size_t)sys * a.n_steps + step] = soft;
+      if (interval > 0 && step == next_sample) {           // diagnostics.py:241-285
+        next_sample += interval;
+        double cx = 0.0, cy = 0.0, Lt = 0.0, Li[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          cx += m[i] * s.x[i];
+          cy += m[i] * s.y[i];
+          Li[i] = m[i] * (s.x[i] * s.vy[i] - s.y[i] * s.vx[i]);
+          Lt += Li[i];
+        }
+        const double com = sqrt(cx * cx + cy * cy);
+        const double mean = Lt / N;
+        double var = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) var += (Li[i] - mean) * (Li[i] - mean);
+        var /= N;
+        if (!have_first) { Lfirst = Lt; have_first = true; }
+        double c;
+        if (Lfirst != 0.0 && Lt != 0.0) c = (Lt * Lfirst) / (fabs(Lt) * fabs(Lfirst));
+        else { c = 0.0; cos_nan = true; }
+        com_sum += com; com_max = fmax(com_max, com);
+        var_sum += var; var_max = fmax(var_max, var);
+        cos_sum += c; cos_min = fmin(cos_min, c);
+        th_sum += theta_eps;
+        ++n_samp;
+      }
+    }
+    if (a.dyn) {
+      double* f = a.dyn + (size_t)sys * NB_N_DYN;
+      const double inv = n_samp > 0 ? 1.0 / (double)n_samp : nan;
+      f[NB_F_COM_MEAN] = n_samp > 0 ? com_sum * inv : nan;
+      f[NB_F_COM_MAX] = n_samp > 0 ? com_max : nan;
+      f[NB_F_JEPS_MEAN] = n_samp > 0 ? 0.0 : nan;
+      f[NB_F_JEPS_STD] = n_samp > 0 ? 0.0 : nan;
+      f[NB_F_THETA_MEAN] = n_samp > 0 ? th_sum * inv : nan;
+      f[NB_F_THETA_STD] = n_samp > 0 ? ((eps_d != 0.0) ? 0.0 : nan) : nan;
+      f[NB_F_COS_MEAN] = (n_samp > 0 && !cos_nan) ? cos_sum * inv : nan;
+      f[NB_F_COS_MIN] = (n_samp > 0 && !cos_nan) ? cos_min : nan;
+      f[NB_F_VARL_MEAN] = n_samp > 0 ? var_sum * inv : nan;
+      f[NB_F_VARL_MAX] = n_samp > 0 ? var_max : nan;
+      f[NB_F_TIDAL_MEAN] = n_samp > 0 ? 0.0 : nan;
+      f[NB_F_TIDAL_MAX] = n_samp > 0 ? 0.0 : nan;
+    }
+  } else {
+    double drx[N], dry[N], dvx[N], dvy[N], dax[N], day[N];
+    {
+      double M = 0.0, cx = 0.0, cy = 0.0, ux = 0.0, uy = 0.0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        drx[i] = a.raw_dr[((size_t)sys * N + i) * 2 + 0]; dry[i] = a.raw_dr[((size_t)sys * N + i) * 2 + 1];
+        dvx[i] = a.raw_dv[((size_t)sys * N + i) * 2 + 0]; dvy[i] = a.raw_dv[((size_t)sys * N + i) * 2 + 1];
+        M += m[i];
+        cx += m[i] * drx[i]; cy += m[i] * dry[i]; ux += m[i] * dvx[i]; uy += m[i] * dvy[i];
+      }
+      cx /= M; cy /= M; ux /= M; uy /= M;
+      double nr = 0.0, nv = 0.0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        drx[i] -= cx; dry[i] -= cy; dvx[i] -= ux; dvy[i] -= uy;
+        nr += drx[i] * drx[i] + dry[i] * dry[i];
+        nv += dvx[i] * dvx[i] + dvy[i] * dvy[i];
+      }
+      nr = sqrt(nr); nv = sqrt(nv);
+#pragma unroll
+      for (int i = 0; i < N; ++i) { drx[i] /= nr; dry[i] /= nr; dvx[i] /= nv; dvy[i] /= nv; }
+    }
+    double tt = 0.0, accum = 0.0;
+    const double dt = a.dt;
+    for (int step = 0; step < a.n_megno; ++step) {
+      macro_step();
+#pragma unroll
+      for (int i = 0; i < N; ++i) { drx[i] = fma(dvx[i], dt, drx[i]); dry[i] = fma(dvy[i], dt, dry[i]); }
+      s.eps2 = soft * soft;                                 // manager.step_s2 AFTER the step's last refresh
+      pair_pass<N, true, true>(s, drx, dry, dax, day);
+      double nr = 0.0, nv = 0.0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        dvx[i] = fma(dax[i], dt, dvx[i]);
+        dvy[i] = fma(day[i], dt, dvy[i]);
+        nr += drx[i] * drx[i] + dry[i] * dry[i];
+      }
+      tt += dt;
+      nr = sqrt(nr);
+      if (nr < 1e-12) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) { drx[i] /= nr; dry[i] /= nr; dvx[i] /= nr; dvy[i] /= nr; }
+        nr = 1.0;
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) nv += dvx[i] * dvx[i] + dvy[i] * dvy[i];
+      accum += (sqrt(nv) / nr) * tt * dt;
+    }
+    if (a.dyn && a.n_megno > 0) {
+      double* f = a.dyn + (size_t)sys * NB_N_DYN;
+      const double megno = 2.0 * accum / tt;
+      f[NB_F_MEGNO] = megno;
+      f[NB_F_LYAP_TIME] = (megno == 0.0) ? __longlong_as_double(0x7ff0000000000000LL) : tt / fabs(megno);
+      f[NB_F_T_END] = tt;
+    }
   }
   bool finite = true;
 #pragma unroll
@@ -134,23 +256,39 @@ __global__ void __launch_bounds__(128) ensemble_adaptive_kernel(AdaptArgs a) {
   }
   a.eps[sys] = soft;
   if (a.e_delta) a.e_delta[sys] = e_delta;
-  if (a.status) a.status[sys] = finite ? 0 : NB_STATUS_NONFINITE;
+  if (a.status) {
+    const int st = finite ? 0 : NB_STATUS_NONFINITE;
+    if (PHASE == 0) a.status[sys] = st; else a.status[sys] |= st;
+  }
 }
 
-template <int MODE>
+template <int MODE, int PHASE>
 static int launch_adaptive(const AdaptArgs& a, int N, cudaStream_t st) {
   const int threads = 128, blocks = (a.B + threads - 1) / threads;
   switch (N) {
-    case 2: ensemble_adaptive_kernel<2, MODE><<<blocks, threads, 0, st>>>(a); break;
-    case 3: ensemble_adaptive_kernel<3, MODE><<<blocks, threads, 0, st>>>(a); break;
-    case 4: ensemble_adaptive_kernel<4, MODE><<<blocks, threads, 0, st>>>(a); break;
-    case 5: ensemble_adaptive_kernel<5, MODE><<<blocks, threads, 0, st>>>(a); break;
-    case 6: ensemble_adaptive_kernel<6, MODE><<<blocks, threads, 0, st>>>(a); break;
-    case 7: ensemble_adaptive_kernel<7, MODE><<<blocks, threads, 0, st>>>(a); break;
-    case 8: ensemble_adaptive_kernel<8, MODE><<<blocks, threads, 0, st>>>(a); break;
+    case 2: ensemble_adaptive_kernel<2, MODE, PHASE><<<blocks, threads, 0, st>>>(a); break;
+    case 3: ensemble_adaptive_kernel<3, MODE, PHASE><<<blocks, threads, 0, st>>>(a); break;
+    case 4: ensemble_adaptive_kernel<4, MODE, PHASE><<<blocks, threads, 0, st>>>(a); break;
+    case 5: ensemble_adaptive_kernel<5, MODE, PHASE><<<blocks, threads, 0, st>>>(a); break;
+    case 6: ensemble_adaptive_kernel<6, MODE, PHASE><<<blocks, threads, 0, st>>>(a); break;
+    case 7: ensemble_adaptive_kernel<7, MODE, PHASE><<<blocks, threads, 0, st>>>(a); break;
+    case 8: ensemble_adaptive_kernel<8, MODE, PHASE><<<blocks, threads, 0, st>>>(a); break;
     default: set_error("N must be in 2..8"); return NB_ERR_ARG;
   }
   NB_CUDA_CHECK(cudaGetLastError());
+  return NB_OK;
+}
+
+int launch_energy(const double* m, const double* q, const double* v, const double* eps, double G, int B, int N, double* dyn,
+                  int slot, cudaStream_t st);
+int launch_finalize(double* dyn, int B, int have_energy, int have_megno, cudaStream_t st);
+
+static int check_adaptive_mode(int mode) {
+  if (mode != NB_MODE_VERLET && mode != NB_MODE_YOSHIDA4) {
+    set_error("adaptive softening exists for verlet and yoshida4 (the reference turns whfast into verlet, "
+              "simulation.py:103-107; ham_soft has its own epsilon flow)");
+    return NB_ERR_UNSUPPORTED;
+  }
   return NB_OK;
 }
 
@@ -161,14 +299,42 @@ int ensemble_run_adaptive(const double* m, double* q, double* v, double* eps, co
     set_error("nb_ensemble_run_adaptive_f64: bad arguments");
     return NB_ERR_ARG;
   }
-  if (mode != NB_MODE_VERLET && mode != NB_MODE_YOSHIDA4) {
-    set_error("nb_ensemble_run_adaptive_f64: adaptive softening exists for verlet and yoshida4 (the reference turns whfast "
-              "into verlet, simulation.py:103-107; ham_soft has its own epsilon flow)");
-    return NB_ERR_UNSUPPORTED;
-  }
+  int rc = check_adaptive_mode(mode);
+  if (rc != NB_OK) return rc;
   if (B == 0) return NB_OK;
-  AdaptArgs a{m, q, v, eps, soft_par, G, B, dt, n_steps, n_sub, k_wall, n_exp, e_delta, eps_hist, status};
-  return mode == NB_MODE_YOSHIDA4 ? launch_adaptive<NB_MODE_YOSHIDA4>(a, N, st) : launch_adaptive<NB_MODE_VERLET>(a, N, st);
+  AdaptArgs a{m, q, v, eps, soft_par, G, B, dt, n_steps, n_sub, k_wall, n_exp, e_delta, eps_hist, status,
+              0, nullptr, nullptr, 0, nullptr, nullptr};
+  return mode == NB_MODE_YOSHIDA4 ? launch_adaptive<NB_MODE_YOSHIDA4, 0>(a, N, st) : launch_adaptive<NB_MODE_VERLET, 0>(a, N, st);
+}
+
+// run_stability_analysis (stability_analyzer.py:69-259) for adaptive-softening copies: E0 -> main loop with sampling
+// -> E1 -> MEGNO -> drifts / is_stable, the energies with the constant eps_energy (diagnostics.py:474)
+int ensemble_analyze_adaptive(const double* m, double* q, double* v, double* eps, const double* eps_energy,
+                              const double* soft_par, double G, int B, int N, int mode, double dt, int n_steps,
+                              int sample_interval, int n_megno, const int32_t* n_sub, const double* raw_dr,
+                              const double* raw_dv, double k_wall, int n_exp, double* e_delta, double* dyn, int32_t* status,
+                              cudaStream_t st) {
+  if (!m || !q || !v || !eps || !eps_energy || !soft_par || !dyn || B < 0 || n_steps < 0 || n_megno < 0 ||
+      (n_megno > 0 && (!raw_dr || !raw_dv))) {
+    set_error("nb_ensemble_analyze_adaptive_f64: bad arguments");
+    return NB_ERR_ARG;
+  }
+  int rc = check_adaptive_mode(mode);
+  if (rc != NB_OK) return rc;
+  if (B == 0) return NB_OK;
+  AdaptArgs a{m, q, v, eps, soft_par, G, B, dt, n_steps, n_sub, k_wall, n_exp, e_delta, nullptr, status,
+              sample_interval, dyn, eps_energy, n_megno, raw_dr, raw_dv};
+  rc = launch_energy(m, q, v, eps_energy, G, B, N, dyn, 0, st);
+  if (rc != NB_OK) return rc;
+  rc = mode == NB_MODE_YOSHIDA4 ? launch_adaptive<NB_MODE_YOSHIDA4, 0>(a, N, st) : launch_adaptive<NB_MODE_VERLET, 0>(a, N, st);
+  if (rc != NB_OK) return rc;
+  rc = launch_energy(m, q, v, eps_energy, G, B, N, dyn, 1, st);
+  if (rc != NB_OK) return rc;
+  if (n_megno > 0) {
+    rc = mode == NB_MODE_YOSHIDA4 ? launch_adaptive<NB_MODE_YOSHIDA4, 1>(a, N, st) : launch_adaptive<NB_MODE_VERLET, 1>(a, N, st);
+    if (rc != NB_OK) return rc;
+  }
+  return launch_finalize(dyn, B, 1, n_megno > 0 ? 1 : 0, st);
 }
 
 }  // namespace nb

@@ -73,6 +73,19 @@ __global__ void __launch_bounds__(128) finalize_kernel(double* dyn, int B, int h
   f[NB_F_IS_STABLE] = ((ed < 0.01) && (ld < 0.01) && (f[NB_F_COM_MEAN] < 1.0) && (f[NB_F_MEGNO] < 10.0)) ? 1.0 : 0.0;
 }
 
+// launchers for the other translation units (ensemble_adaptive.cu)
+int launch_energy(const double* m, const double* q, const double* v, const double* eps, double G, int B, int N, double* dyn,
+                  int slot, cudaStream_t st) {
+  energy_kernel<<<(B + 127) / 128, 128, 0, st>>>(m, q, v, eps, G, B, N, dyn, slot);
+  NB_CUDA_CHECK(cudaGetLastError());
+  return NB_OK;
+}
+int launch_finalize(double* dyn, int B, int have_energy, int have_megno, cudaStream_t st) {
+  finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(dyn, B, have_energy, have_megno);
+  NB_CUDA_CHECK(cudaGetLastError());
+  return NB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Heads first.  Each bucket's launch ends in a latency-bound tail: the sub-step-heavy systems at the head of the
 // n_sub-sorted permutation run long sequential chains while the bulk is throughput-bound.  When several buckets are in

@@ -188,12 +188,9 @@ def analyze_simulations(sims, n_steps: int, dt: float, mode: str, via: str = "de
         if s.n_bodies < 2:
             rows[i] = {"is_stable": float("nan"), "mode": mode}
             continue
-        if getattr(s, "_adaptive_softening", False) and _mode_of(s) != "ham_soft":
-            raise L.NBodyB200Error("stability analysis of classic adaptive-softening simulations is not built: the "
-                                   "adaptive path covers NBodySimulation.step / nb_ensemble_run_adaptive_f64 "
-                                   "(SURVEY.md section 8f item 1); analyse with fixed softening or ham_soft")
-        buckets.setdefault((s.n_bodies, _mode_of(s), float(s.G), str(s.device)), []).append(i)
-    for (N, imode, G, _dev), idx in buckets.items():
+        adaptive = bool(getattr(s, "_adaptive_softening", False)) and _mode_of(s) != "ham_soft"
+        buckets.setdefault((s.n_bodies, _mode_of(s), float(s.G), str(s.device), adaptive), []).append(i)
+    for (N, imode, G, _dev, adaptive), idx in buckets.items():
         group = [sims[i] for i in idx]
         m = np.stack([s._mass for s in group])
         q = np.stack([s._pos for s in group])
@@ -203,6 +200,10 @@ def analyze_simulations(sims, n_steps: int, dt: float, mode: str, via: str = "de
         rv = np.stack([draws[i][1] for i in idx]) if n_megno > 0 else None
         if imode == "ham_soft":
             dyn, stat, status = _analyze_hamsoft(group, m, q, v, G, n_steps, dt, mode, interval, n_megno, rr, rv)
+        elif adaptive:
+            dyn, stat, status, vk = _analyze_adaptive(group, m, q, v, G, imode, n_steps, dt, mode, interval, n_megno, rr, rv)
+            for k, s in enumerate(group):
+                s._vel[...] = vk[k]                      # snapshot() mutates the caller's sim
         else:
             eps = np.array([s._force_eps() for s in group])
             # snapshot(): one more corrector half kick with the last |dt| stepped (simulation.py:319-326)
@@ -263,6 +264,49 @@ def _analyze_minimal(m, q, v, eps, G, imode, n_steps, dt, top, group):
     bk.sort()
     dyn = bk.run(dt, n_steps, 0, 0, flags=L.RUN_ENERGY).cpu().numpy()
     return dyn, None, bk.status.cpu().numpy(), vk
+
+
+def _analyze_adaptive(group, m, q, v, G, imode, n_steps, dt, mode, interval, n_megno, rr, rv):
+    """run_stability_analysis on classic adaptive-softening sims.  snapshot() kicks the original with the CURRENT
+    softening; restore() rebuilds an adaptive copy whose manager restarts from the original's `_epsilon` (the constructor
+    softening, simulation.py:473-482); the energies use that constant epsilon (diagnostics.py:474)."""
+    torch = L.require_cuda()
+    B, N = m.shape
+    dev = group[0].device
+    dyn = np.empty((B, L.N_DYN)); status = np.zeros(B, dtype=np.int32); vk = np.empty_like(v)
+    stat = np.empty((B, L.N_STATIC)) if mode == "full" else None
+    top = np.array([abs(float(s._integrator._top_dt or s.cfg.initial_dt)) for s in group])
+    eps_force = np.array([s._force_eps() for s in group])
+    eps_attr = np.array([float(s._epsilon) for s in group])
+    hist0 = np.array([list(s.manager._history)[0] for s in group])
+    min_soft = np.array([float(s._min_softening) for s in group])
+    par = np.stack([np.maximum(hist0, min_soft), min_soft, np.array([float(s._softening_scale) for s in group])], 1)
+    for t in np.unique(top):
+        sel = np.where(top == t)[0]
+        bk = E.DeviceBucket(m[sel], q[sel], v[sel], eps_force[sel], G, imode, dev)
+        bk.prepare(L.PREP_SNAPSHOT_KICK, float(t), float(group[0].cfg.initial_dt), dt, int(group[0].cfg.split_n_max),
+                   want_static=(mode == "full"))
+        vk[sel] = bk.v.cpu().numpy()
+        eps_d = E._to_dev(eps_attr[sel], torch.float64, bk.device).clone()
+        eps_e = E._to_dev(eps_attr[sel], torch.float64, bk.device)
+        par_d = E._to_dev(par[sel], torch.float64, bk.device)
+        e_d = torch.zeros((len(sel),), dtype=torch.float64, device=bk.device)
+        dyn_d = torch.empty((len(sel), L.N_DYN), dtype=torch.float64, device=bk.device)
+        rdr = E._to_dev(rr[sel], torch.float64, bk.device) if n_megno > 0 else None
+        rdv = E._to_dev(rv[sel], torch.float64, bk.device) if n_megno > 0 else None
+        cfg = group[0].cfg
+        with torch.cuda.device(bk.device):
+            L.check(L.load().nb_ensemble_analyze_adaptive_f64(
+                L.ptr(bk.m), L.ptr(bk.q), L.ptr(bk.v), L.ptr(eps_d), L.ptr(eps_e), L.ptr(par_d), float(G), len(sel), N,
+                L.MODES[imode], float(dt), int(n_steps), int(interval if mode != "minimal" else 0), int(n_megno),
+                L.ptr(bk.n_sub), L.ptr(rdr), L.ptr(rdv), float(getattr(cfg, "k_wall", 1.0e9)),
+                int(getattr(cfg, "barrier_exponent", 5)), L.ptr(e_d), L.ptr(dyn_d), L.ptr(bk.status), L.stream_ptr()),
+                "nb_ensemble_analyze_adaptive_f64")
+        dyn[sel] = dyn_d.cpu().numpy()
+        status[sel] = bk.status.cpu().numpy()
+        if stat is not None:
+            stat[sel] = bk.static.cpu().numpy()
+    return dyn, stat, status, vk
 
 
 def _analyze_hamsoft(group, m, q, v, G, n_steps, dt, mode, interval, n_megno, rr, rv):

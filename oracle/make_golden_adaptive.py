@@ -93,5 +93,67 @@ def main():
     np.savez_compressed(os.path.join(OUT, "adaptive_softening.npz"), **out)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "features" not in sys.argv:
     main()
+
+
+def gen_features():
+    """StabilityAnalyzer('full') rows of adaptive-softening simulations (stepped 5 times first, so that manager.s differs
+    from the constructor value the restored copy falls back to, simulation.py:473-482), tangent draws recorded, plus the
+    reference's own sensitivity under the equivalent-arithmetic force routine.  -> tests/golden/features_adaptive.npz"""
+    import contextlib
+    import io
+    import minbody.simulation as simmod
+    out, names = {}, []
+    n_steps = 60
+    for name, (m, p, v, soft) in systems().items():
+        for mode in ("verlet", "yoshida4"):
+            rows = []
+            draws = []
+            for alt in (False, True):
+                orig_force = simmod.gravitational_force
+                if alt:
+                    simmod.gravitational_force = _alt_force
+                try:
+                    with quiet():
+                        sim = mb.NBodySimulation(masses=m, positions=p, velocities=v, softening=soft, integrator_mode=mode,
+                                                 adaptive_softening=True)
+                        for _ in range(5):
+                            sim.step(0.01)
+                    orig = np.random.randn
+                    if not alt:
+                        def rec(*shape):
+                            a = orig(*shape)
+                            draws.append(a.copy())
+                            return a
+                        np.random.seed(3)
+                        np.random.randn = rec
+                    else:
+                        it = iter([d.copy() for d in draws])
+                        np.random.randn = lambda *shape: next(it)
+                    try:
+                        with quiet():
+                            rows.append(mb.StabilityAnalyzer(sim, n_steps=n_steps, dt=0.01, mode="full").run_stability_analysis())
+                    finally:
+                        np.random.randn = orig
+                finally:
+                    simmod.gravitational_force = orig_force
+            key = f"{name}__{mode}_"
+            names.append(key)
+            out[key + "m"] = m; out[key + "q"] = p; out[key + "v"] = v; out[key + "soft"] = soft
+            out[key + "raw_r"] = draws[0]; out[key + "raw_v"] = draws[1]
+            for c, val in rows[0].items():
+                if isinstance(val, (str, bool, np.bool_)):
+                    continue
+                out[key + "f__" + c] = float(val)
+                d = abs(float(val) - float(rows[1][c]))
+                out[key + "sens__" + c] = d if np.isfinite(d) else 0.0
+            print(key, {k: rows[0][k] for k in ("energy_drift", "MEGNO")}, "sens MEGNO", out[key + "sens__MEGNO"])
+    out["names"] = np.array(names)
+    out["n_steps"] = n_steps
+    out["pre_steps"] = 5
+    np.savez_compressed(os.path.join(OUT, "features_adaptive.npz"), **out)
+
+
+if __name__ == "__main__" and "features" in sys.argv:
+    gen_features()

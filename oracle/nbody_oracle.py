@@ -317,6 +317,7 @@ class OracleSim:
                 mode = "verlet"
         self.s0 = float(max(softening, self.min_softening))         # softening_manager.py:48
         self.s = self.s0
+        self.eps_attr = self.s0        # sim._epsilon: set once in the constructor (simulation.py:116), never by the classic refresh
         self.step_s2 = self.s * self.s
         self.max_softening = 10.0 * self.s0
         if self.s > 0.0 and mode == "whfast":                       # :119-120
@@ -550,11 +551,18 @@ class OracleSim:
                       min_softening=(0.1 * self.history[0] if self.history[0] > 0 else 0.0),
                       integrator_mode=self.mode, skip_init_corrector=True, skip_cm_recenter=True,
                       initial_dt=self.initial_dt, split_n_max=self.split_n_max,
-                      corrector_order=self.corrector_order)
-        c.s = self.s
-        c.step_s2 = self.step_s2
+                      corrector_order=self.corrector_order, adaptive_softening=self.adaptive_softening,
+                      adaptive_timestep=self.adaptive_timestep, softening_scale=self.softening_scale,
+                      k_wall=self.k_wall, barrier_exponent=self.barrier_exponent)
+        # simulation.py:473-482: after the state is restored the manager is reset to the ORIGINAL sim's `_epsilon`
+        # (update_continuous), which for classic modes is the constructor softening -- an adaptive copy therefore
+        # restarts its softening from s0 while keeping the restored history
+        c.s = self.eps_attr
+        c.step_s2 = c.s * c.s
+        c.eps_attr = self.eps_attr
         c.history = list(self.history)
         c.top_dt = self.top_dt
+        c.softening_energy_delta = self.softening_energy_delta
         return c
 
 
@@ -748,12 +756,12 @@ def run_stability_analysis(sim, n_steps=1000, dt=0.01, mode="core", raw_r=None, 
     classic integrator modes.  `sim` is mutated by the snapshot kick exactly like the reference."""
     n_steps = max(1, int(n_steps))
     c = sim.snapshot_restore()
-    eps = c.s
+    eps = c.eps_attr              # diagnostics.py:474: eps = sim._epsilon, constant for classic modes
     E0 = extended_hamiltonian_classic(c.m, c.q, c.v, eps, c.G)
     if mode == "minimal":
         for _ in range(n_steps):
             c.step(dt)
-        E1 = extended_hamiltonian_classic(c.m, c.q, c.v, c.s, c.G)
+        E1 = extended_hamiltonian_classic(c.m, c.q, c.v, c.eps_attr, c.G)
         d = _drift(E0, E1)
         return {"is_stable": float(d < 0.01), "energy_drift": d, "mode": "minimal"}
     L0 = angular_momentum(c.m, c.q, c.v)
@@ -763,10 +771,10 @@ def run_stability_analysis(sim, n_steps=1000, dt=0.01, mode="core", raw_r=None, 
     for i in range(n_steps):
         c.step(dt)
         if i % interval == 0:
-            met, Lfirst = step_metrics_classic(c.m, c.q, c.v, c.s, Lfirst)
+            met, Lfirst = step_metrics_classic(c.m, c.q, c.v, c.eps_attr, Lfirst)
             for k in samples:
                 samples[k].append(met[k])
-    E1 = extended_hamiltonian_classic(c.m, c.q, c.v, c.s, c.G)
+    E1 = extended_hamiltonian_classic(c.m, c.q, c.v, c.eps_attr, c.G)
     L1 = angular_momentum(c.m, c.q, c.v)
     if mode == "full":
         n_samp = min(50, n_steps // 2)

@@ -74,10 +74,33 @@ def test_step_many_equals_repeated_steps_and_batch_vs_oracle():
     assert a.manager.history == b2.manager.history
 
 
-def test_analysis_of_adaptive_sims_fails_loudly():
+def test_stability_analysis_of_adaptive_sims_vs_golden():
+    """StabilityAnalyzer('full') on adaptive-softening sims against the live reference's rows
+    (oracle/make_golden_adaptive.py features): tolerance 1e-8 + 100 x the reference's own sensitivity per column."""
     import nbodysimproject_b200 as nb
-    from nbodysimproject_b200._lib import NBodyB200Error
-    sim = nb.NBodySimulation(masses=[1.0, 0.5, 0.1], positions=[[0, 0], [1, 0], [2, 0.0]],
-                             velocities=[[0, 0], [0, 1], [0, 0.5]], integrator_mode="verlet", adaptive_softening=True)
-    with pytest.raises(NBodyB200Error):
-        nb.StabilityAnalyzer(sim, n_steps=10, dt=0.01, mode="core").run_stability_analysis()
+    g = load_golden("features_adaptive.npz")
+    n_steps, pre = int(g["n_steps"]), int(g["pre_steps"])
+    cols = ["energy_drift", "angular_momentum_drift", "com_drift_mean", "com_drift_max", "cos_theta_mean", "cos_theta_min",
+            "ang_mom_var_mean", "ang_mom_var_max", "MEGNO", "lyapunov_time", "initial_softening_mean",
+            "initial_softening_std", "initial_total_energy", "initial_min_separation", "initial_virial_ratio", "is_stable"]
+    for key in g["names"]:
+        key = str(key)
+        mode = key.split("__")[1].rstrip("_")
+        sim = nb.NBodySimulation(masses=g[key + "m"], positions=g[key + "q"], velocities=g[key + "v"],
+                                 softening=float(g[key + "soft"]), integrator_mode=mode, adaptive_softening=True)
+        for _ in range(pre):
+            sim.step(0.01)
+        draws = [g[key + "raw_r"], g[key + "raw_v"]]
+        it = iter(draws)
+        orig = np.random.randn
+        np.random.randn = lambda *shape: next(it).copy()
+        try:
+            row = nb.StabilityAnalyzer(sim, n_steps=n_steps, dt=0.01, mode="full").run_stability_analysis()
+        finally:
+            np.random.randn = orig
+        for c in cols:
+            ref, sens = float(g[key + "f__" + c]), float(g[key + "sens__" + c])
+            if c == "angular_momentum_drift":          # |L1 - L0| / |L0| of ~1e-15: rounding noise on both sides
+                assert abs(row[c] - ref) < 1e-12, (key, c, row[c], ref)
+                continue
+            assert abs(row[c] - ref) <= 1e-8 * max(abs(ref), 1e-12) + 100 * sens, (key, c, row[c], ref)

@@ -323,3 +323,26 @@ def test_kepler_cycle_shortcut_is_bit_identical():
         assert chi_s == chi and it_s == it, (r, v, mu, dt, chi_s, chi, it_s, it)
         n_cap += it == 64
     assert n_cap >= 5          # the sample really contains capped solves
+
+
+def test_adaptive_analysis_oracle_vs_golden():
+    """run_stability_analysis on adaptive-softening sims (oracle/make_golden_adaptive.py features): the restored copy
+    restarts its softening from the original's constructor epsilon (simulation.py:473-482), the energies use that
+    constant epsilon (diagnostics.py:474), the tangent map the current one."""
+    from oracle import nbody_oracle as O
+    g = load_golden("features_adaptive.npz")
+    n_steps, pre = int(g["n_steps"]), int(g["pre_steps"])
+    cols = ["energy_drift", "angular_momentum_drift", "com_drift_mean", "com_drift_max", "cos_theta_mean", "cos_theta_min",
+            "ang_mom_var_mean", "ang_mom_var_max", "MEGNO", "lyapunov_time", "initial_softening_mean",
+            "initial_softening_std", "initial_total_energy", "initial_min_separation", "is_stable"]
+    for key in g["names"]:
+        key = str(key)
+        mode = key.split("__")[1].rstrip("_")
+        sim = O.OracleSim(g[key + "m"], g[key + "q"], g[key + "v"], softening=float(g[key + "soft"]),
+                          integrator_mode=mode, adaptive_softening=True)
+        for _ in range(pre):
+            sim.step(0.01)
+        row = O.run_stability_analysis(sim, n_steps, 0.01, "full", g[key + "raw_r"], g[key + "raw_v"])
+        for c in cols:
+            ref, sens = float(g[key + "f__" + c]), float(g[key + "sens__" + c])
+            assert abs(row[c] - ref) <= 1e-9 * max(abs(ref), 1e-12) + 100 * sens, (key, c, row[c], ref)
