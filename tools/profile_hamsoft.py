@@ -25,7 +25,7 @@ t = e0.elapsed_time(e1) * 1e-3
 print(f"hamsoft N=3 B={B} steps={steps}: {t*1e3:.2f} ms, {B*steps/t:.3e} system-steps/s")
 
 # generic N: random compact systems
-for N in (4, 8):
+for N in (4, 6, 8):
     rng = np.random.RandomState(1)
     Bn = B // 4
     m = rng.uniform(0.5, 3.0, (Bn, N)); q = rng.randn(Bn, N, 2) * 0.8; v = rng.randn(Bn, N, 2) * 0.4
