@@ -216,7 +216,7 @@ int nb_largeN_kick_drift_f32(float* xym_local, float* vel, const float* acc, int
 int nb_largeN_pass_f32(int kind, const float* xym, const float* jaux, int n_total, int i0, int ni,
                        const float* iparam, float eps, double* out, void* stream);
 
-/* kernel variant of nb_largeN_accel_f32 (tuning / A-B tests only; process-wide): -1 default (9 without, 10 with sums);
+/* kernel variant of nb_largeN_accel_f32 (tuning / A-B tests only; process-wide): -1 default (= 10);
  * 0..7 scalar-fp32 kernel (bit0: TMA staging, bits1-2: 4/2/1 i-particles per thread);
  * 8 packed f32x2 over j-pairs, 4 i per thread; 9 same with 8 i per thread, 2 CTAs/SM; 10 same with 2 i per thread */
 int nb_largeN_set_variant(int variant);

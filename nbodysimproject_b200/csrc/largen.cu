@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(LN_TPB, MINB) largeN_accel_x2_kernel(LargeNArg
       const float4* py = reinterpret_cast<const float4*>(sy[buf]);
       const float4* pm = reinterpret_cast<const float4*>(sm[buf]);
       if (!diag) {
-#pragma unroll 2
+#pragma unroll 4
         for (int j4 = 0; j4 < cnt4 / 4; ++j4) {
           const float4 X = px[j4], Y = py[j4], M = pm[j4];
 #pragma unroll
@@ -406,10 +406,9 @@ int largeN_accel(const float* xym, int n_total, int i0, int ni, float eps, float
     const char* e = getenv("NB_LARGEN_VARIANT");
     g_ln_variant = e ? atoi(e) : -1;
   }
-  // default (-1): 8 i-particles per thread (2 CTAs/SM) for the plain force pass, 2 per thread when the scalar sums are
-  // fused (their extra accumulators spill at 64 registers with 4 or 8): measured 3.16e12 / 2.70e12 pairs/s
-  const bool scal_req = sums != nullptr;
-  const int variant = g_ln_variant >= 0 ? g_ln_variant : (scal_req ? 10 : 9);
+  // default (-1): 2 i-particles per thread, 4 CTAs/SM, 16 j-particles per unrolled iteration: measured 3.25e12 pairs/s
+  // (4 or 8 i per thread: 3.13-3.17e12; with the fused scalar sums their extra accumulators spill at 64 registers)
+  const int variant = g_ln_variant >= 0 ? g_ln_variant : 10;
   const bool v2 = variant >= 8;
   const int v2_ipt = variant == 9 ? 8 : (variant == 10 ? 2 : 4);
   const int v2_minb = variant == 9 ? 2 : 4;
