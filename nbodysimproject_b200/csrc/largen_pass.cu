@@ -19,7 +19,7 @@
 namespace nb {
 
 constexpr int LP_TILE = 512;
-constexpr int LP_IPT = 4;
+constexpr int LP_IPT = 2;
 
 enum { LP_DENSITY = 0, LP_EPSGRAD = 1, LP_UNITGRAD = 2, LP_TAUMIN = 3 };
 
@@ -34,7 +34,7 @@ struct PassArgs {
 };
 
 template <int KIND>
-__global__ void __launch_bounds__(LN_TPB, 2) largeN_pass_kernel(PassArgs a) {
+__global__ void __launch_bounds__(LN_TPB, 4) largeN_pass_kernel(PassArgs a) {
   constexpr bool AUX = (KIND == LP_EPSGRAD);
   constexpr int NROW = AUX ? 5 : 3;
   __shared__ __align__(128) float4 raw[2][LP_TILE];
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(LN_TPB, 2) largeN_pass_kernel(PassArgs a) {
       const float4* pk = reinterpret_cast<const float4*>(rows[buf][NROW - 2]);
       const float4* pa = reinterpret_cast<const float4*>(rows[buf][NROW - 1]);
       const float2 eps2v = make_float2(a.eps2, a.eps2);
-#pragma unroll 2
+#pragma unroll 4
       for (int j4 = 0; j4 < cnt4 / 4; ++j4) {
         const float4 X = px[j4], Y = py[j4], M = pm[j4];
         float4 K = make_float4(0.f, 0.f, 0.f, 0.f), A = K;
@@ -259,7 +259,7 @@ int largeN_pass(int kind, const float* xym, const float* jaux, int n_total, int 
     NB_CUDA_CHECK(cudaGetDevice(&dev));
     NB_CUDA_CHECK(cudaDeviceGetAttribute(&g_pass_sm, cudaDevAttrMultiProcessorCount, dev));
   }
-  const LargeNChunks c = largeN_chunks(n_total, ni, LP_IPT, LP_TILE, g_pass_sm * 2, kind == LP_TAUMIN);
+  const LargeNChunks c = largeN_chunks(n_total, ni, LP_IPT, LP_TILE, g_pass_sm * 4, kind == LP_TAUMIN);
   PassArgs a;
   a.xym = reinterpret_cast<const float4*>(xym);
   a.jaux = reinterpret_cast<const float2*>(jaux);
