@@ -264,7 +264,7 @@ class LargeNHamSoftSimulation(LargeNSimulation):
         a = self._alpha()
         t = -h / a
         tmax = float(self._allmax(t.max()))
-        ex = torch_exp(self.torch, t - tmax)
+        ex = self.torch.exp(t - tmax)
         den = float(self._allsum(ex.sum()))
         return a, tmax, ex, den
 
@@ -503,14 +503,6 @@ class LargeNHamSoftSimulation(LargeNSimulation):
             p = self.n_exp - 1
             H += (self.k_wall / p) * (max(0.0, a - self.eps) ** p + max(0.0, self.eps - b) ** p)
         return H
-
-
-def torch_exp(torch, t):
-    return torch.exp(t)
-
-
-def torch_sum(t):
-    return float(t.sum())
 
 
 def make_disc(n: int, seed: int = 0):
