@@ -301,3 +301,31 @@ def test_heavy_threshold_depends_on_n_only_and_results_are_shard_invariant(E, O)
     light = nsub <= thr
     assert np.array_equal(full[0][light], none[0][light])
     assert relerr(full[0][~light], none[0][~light]) < 1e-9
+
+
+def test_head_rest_split_launch_is_invisible(E, O):
+    """B >= 4096: nb_ensemble_run_f64 launches the main kernel as a high-priority HEAD and a REST on different streams.
+    The split must not change a single bit: the same systems run in chunks below the split size give identical tables."""
+    import nbodysimproject_b200._lib as L
+    rng = np.random.RandomState(21)
+    for N, mode in ((3, "yoshida4"), (5, "verlet"), (8, "yoshida4")):
+        B = 9000 + N            # not a multiple of the CTA size; head boundary inside the thread-mapped range
+        m = rng.uniform(0.5, 5.0, (B, N))
+        q = rng.randn(B, N, 2) * 1.5
+        sep = 10 ** rng.uniform(-2.0, 0.0, B)
+        q[:, 1] = q[:, 0] + np.stack([sep, np.zeros(B)], 1)
+        v = rng.randn(B, N, 2) * 0.3
+        rr, rv = rng.randn(B, N, 2), rng.randn(B, N, 2)
+
+        def run(sl):
+            bk = E.DeviceBucket(m[sl], q[sl], v[sl], 0.2, 1.0, mode)
+            bk.prepare(L.PREP_REMOVE_COM | L.PREP_CTOR_KICK, 0.01, 0.01, 0.01, want_static=True)
+            bk.sort()
+            dyn = bk.run(0.01, 20, 2, 5, rr[sl], rv[sl], flags=L.RUN_ENERGY | L.RUN_WRITE_STATE)
+            return bk.q.cpu().numpy(), dyn.cpu().numpy(), bk.status.cpu().numpy()
+
+        full = run(slice(0, B))
+        parts = [run(slice(0, 3000)), run(slice(3000, 6500)), run(slice(6500, B))]
+        assert np.array_equal(np.concatenate([p[0] for p in parts]), full[0]), (N, mode)
+        assert np.array_equal(np.concatenate([p[1] for p in parts]), full[1], equal_nan=True), (N, mode)
+        assert np.array_equal(np.concatenate([p[2] for p in parts]), full[2])
