@@ -526,13 +526,34 @@ __device__ __forceinline__ void hs_v_half(HsState<N>& s, const HsPar& P, double 
 
 template <int N>
 __device__ __forceinline__ void hs_strang(HsState<N>& s, const HsPar& P, double G, double h, int lane) {
+  // S(h/2) V(h/2) T(h) V(h/2) S(h/2).  Written as a two-trip loop so that the S half-flow (the eps* model: by far the
+  // largest piece of code) is instantiated ONCE; the unrolled form made the kernel stall on instruction fetch
+  // (ncu: no_instruction 1.8 warps per issue slot at N = 3).
   hs_fold(s.eps, s.pi, P);                       // hamsoft_stepper.py:261-264
-  hs_s_half<N>(s, P, h, lane);
-  hs_v_half<N>(s, P, G, h);
+  if constexpr (N >= 8) {                        // N = 8 is register-bound: the rolled form spills more than it saves
+    hs_s_half<N>(s, P, h, lane);
+    hs_v_half<N>(s, P, G, h);
 #pragma unroll
-  for (int i = 0; i < N; ++i) { s.x[i] = fma(h, s.vx[i], s.x[i]); s.y[i] = fma(h, s.vy[i], s.y[i]); }
-  hs_v_half<N>(s, P, G, h);
-  hs_s_half<N>(s, P, h, lane);
+    for (int i = 0; i < N; ++i) { s.x[i] = fma(h, s.vx[i], s.x[i]); s.y[i] = fma(h, s.vy[i], s.y[i]); }
+    hs_v_half<N>(s, P, G, h);
+    hs_s_half<N>(s, P, h, lane);
+    hs_fold(s.eps, s.pi, P);
+    return;
+  }
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    hs_s_half<N>(s, P, h, lane);
+    if (half == 0) {
+#pragma unroll 1
+      for (int kick = 0; kick < 2; ++kick) {
+        hs_v_half<N>(s, P, G, h);
+        if (kick == 0) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) { s.x[i] = fma(h, s.vx[i], s.x[i]); s.y[i] = fma(h, s.vy[i], s.y[i]); }
+        }
+      }
+    }
+  }
   hs_fold(s.eps, s.pi, P);                       // hamsoft_stepper.py:300-303
 }
 
@@ -642,50 +663,30 @@ __global__ void __launch_bounds__(128, (N <= 4 ? 4 : 2)) hamsoft_run_kernel(HsAr
     for (int i = 0; i < N; ++i) L += s.m[i] * (s.x[i] * s.vy[i] - s.y[i] * s.vx[i]);
   };
   double E0 = nan, L0 = nan, E1 = nan, L1 = nan;
-  if (want_energy) energy(E0, L0);
 
   double com_sum = 0.0, com_max = -1.0, var_sum = 0.0, var_max = -1.0, cos_sum = 0.0, cos_min = 2.0;
   Welford wj{0.0, 0.0, 0}, wt{0.0, 0.0, 0};
   double Lfirst = 0.0;
   bool have_first = false, cos_nan = false, th_nan = false;
   int n_samp = 0, next_sample = 0;
-  for (int step = 0; step < a.n_steps; ++step) {
-    macro_step();
-    if (a.sample_interval > 0 && step == next_sample) {   // diagnostics.py:241-285
-      next_sample += a.sample_interval;
-      double cx = 0.0, cy = 0.0, Lt = 0.0, Li[N];
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        cx += s.m[i] * s.x[i]; cy += s.m[i] * s.y[i];
-        Li[i] = s.m[i] * (s.x[i] * s.vy[i] - s.y[i] * s.vx[i]);
-        Lt += Li[i];
-      }
-      const double mean = Lt / N;
-      double var = 0.0;
-#pragma unroll
-      for (int i = 0; i < N; ++i) var += (Li[i] - mean) * (Li[i] - mean);
-      var /= N;
-      const double com = sqrt(cx * cx + cy * cy);
-      if (!have_first) { Lfirst = Lt; have_first = true; }
-      double c;
-      if (Lfirst != 0.0 && Lt != 0.0) c = (Lt * Lfirst) / (fabs(Lt) * fabs(Lfirst));
-      else { c = 0.0; cos_nan = true; }
-      com_sum += com; com_max = fmax(com_max, com);
-      var_sum += var; var_max = fmax(var_max, var);
-      cos_sum += c; cos_min = fmin(cos_min, c);
-      wj.add(s.eps * s.pi / P.mu);
-      if (P.mu * s.eps != 0.0 || s.pi != 0.0) wt.add(atan2(s.pi, P.mu * s.eps));
-      else th_nan = true;
-      ++n_samp;
-    }
-  }
-  if (want_energy) energy(E1, L1);
-
   // MEGNO (evolution_features.py:34-66); the tangent map uses the post-step epsilon^2 (softening_manager.py:359-366)
   double megno = 2.0, lyap = inf, t_end = 0.0;
-  if (a.n_megno > 0) {
-    double drx[N], dry[N], dvx[N], dvy[N];
-    {
+  double drx[N], dry[N], dvx[N], dvy[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) { drx[i] = 0.0; dry[i] = 0.0; dvx[i] = 0.0; dvy[i] = 0.0; }
+  double tt = 0.0, accum = 0.0;
+  const double dt = a.dt;
+  const int n_total = a.n_steps + a.n_megno;
+  // ONE loop over the main steps and the MEGNO steps, so that the macro step (and the energy evaluation) is
+  // instantiated once: step < n_steps samples step_metrics, step >= n_steps advances the tangent vectors
+  for (int step = 0; step <= n_total; ++step) {
+    if (want_energy && (step == 0 || step == a.n_steps)) {
+      double E, Lz;
+      energy(E, Lz);
+      if (step == 0) { E0 = E; L0 = Lz; }
+      if (step == a.n_steps) { E1 = E; L1 = Lz; }
+    }
+    if (step == a.n_steps && a.n_megno > 0) {
       double M = 0.0, cx = 0.0, cy = 0.0, ux = 0.0, uy = 0.0;
 #pragma unroll
       for (int i = 0; i < N; ++i) {
@@ -705,10 +706,37 @@ __global__ void __launch_bounds__(128, (N <= 4 ? 4 : 2)) hamsoft_run_kernel(HsAr
 #pragma unroll
       for (int i = 0; i < N; ++i) { drx[i] /= nr; dry[i] /= nr; dvx[i] /= nv; dvy[i] /= nv; }
     }
-    double tt = 0.0, accum = 0.0;
-    const double dt = a.dt;
-    for (int step = 0; step < a.n_megno; ++step) {
-      macro_step();
+    if (step == n_total) break;
+    macro_step();
+    if (step < a.n_steps) {
+      if (a.sample_interval > 0 && step == next_sample) {   // diagnostics.py:241-285
+        next_sample += a.sample_interval;
+        double cx = 0.0, cy = 0.0, Lt = 0.0, Li[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          cx += s.m[i] * s.x[i]; cy += s.m[i] * s.y[i];
+          Li[i] = s.m[i] * (s.x[i] * s.vy[i] - s.y[i] * s.vx[i]);
+          Lt += Li[i];
+        }
+        const double mean = Lt / N;
+        double var = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) var += (Li[i] - mean) * (Li[i] - mean);
+        var /= N;
+        const double com = sqrt(cx * cx + cy * cy);
+        if (!have_first) { Lfirst = Lt; have_first = true; }
+        double c;
+        if (Lfirst != 0.0 && Lt != 0.0) c = (Lt * Lfirst) / (fabs(Lt) * fabs(Lfirst));
+        else { c = 0.0; cos_nan = true; }
+        com_sum += com; com_max = fmax(com_max, com);
+        var_sum += var; var_max = fmax(var_max, var);
+        cos_sum += c; cos_min = fmin(cos_min, c);
+        wj.add(s.eps * s.pi / P.mu);
+        if (P.mu * s.eps != 0.0 || s.pi != 0.0) wt.add(atan2(s.pi, P.mu * s.eps));
+        else th_nan = true;
+        ++n_samp;
+      }
+    } else {
       SysState<N> t;
       double dax[N], day[N];
 #pragma unroll
@@ -735,6 +763,8 @@ __global__ void __launch_bounds__(128, (N <= 4 ? 4 : 2)) hamsoft_run_kernel(HsAr
       for (int i = 0; i < N; ++i) nv += dvx[i] * dvx[i] + dvy[i] * dvy[i];
       accum += (sqrt(nv) / nr) * tt * dt;
     }
+  }
+  if (a.n_megno > 0) {
     megno = 2.0 * accum / tt;
     lyap = (megno == 0.0) ? inf : tt / fabs(megno);
     t_end = tt;
