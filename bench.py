@@ -110,6 +110,41 @@ class ClockSampler:
                 "samples": len(sm), "window": note}
 
 
+_ORIG_AFFINITY = None
+
+
+def restore_affinity():
+    """The CPU baseline leg uses every host core again."""
+    if _ORIG_AFFINITY is not None:
+        try:
+            os.sched_setaffinity(0, _ORIG_AFFINITY)
+        except Exception:
+            pass
+
+
+def bind_to_gpu_numa_node(index: int):
+    """Pin this rank to the CPU cores next to its GPU (NVML's ideal CPU affinity) BEFORE any pinned host buffer is
+    allocated, so the staging memory of the e2e leg lands on the GPU's own NUMA node: with 8 ranks on one box the host
+    side of the PCIe transfers is otherwise the bottleneck.  Best effort; returns the number of cores or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            global _ORIG_AFFINITY
+            _ORIG_AFFINITY = allowed
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def make_inputs(n_systems: int, seed: int):
     """Diverse cohort (ml_training_pipeline.py:44-122 extended to N <= 8) + per-system tangent draws."""
     from nbodysimproject_b200.generators import EnsembleInputs
@@ -257,6 +292,7 @@ def impl_b200(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = L.load()
@@ -485,6 +521,7 @@ def impl_b200(args):
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        restore_affinity()
         cores = os.cpu_count() or 1
         n_jobs = max(cores, 8) * 96          # ~10-15 s of CPU work on the box's cores
         rate, dt_cpu = run_cpu(n_jobs, cores)
@@ -502,7 +539,7 @@ def impl_b200(args):
                                    "40% random N=3-8 / 30% hierarchical triples / 20% polygons / 10% close encounters, "
                                    "yoshida4 dt=0.01, 1000 steps + 50 tangent-map MEGNO steps, mode full",
                        "systems_per_gpu": B_total, "buckets": {str(N): int(devb[N].B) for N in Ns},
-                       "sharding": "by system, no collective", "l2_note": "inputs re-read from HBM each step "
+                       "sharding": "by system, no collective", "cpu_cores_bound_to_gpu_numa_node": numa, "l2_note": "inputs re-read from HBM each step "
                        f"({h2d / 1e6:.0f} MB per GPU > 126 MB L2)"},
             "e2e": {"value": sys_steps / t_e2e, "unit": "system-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps,
@@ -562,6 +599,7 @@ def _cpu_c1(job):
 
 def _cpu_pool(fn, jobs, cores):
     import multiprocessing as mp
+    restore_affinity()
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(cores) as pool:
         done = sum(pool.map(fn, jobs, chunksize=1))
@@ -770,6 +808,7 @@ def bench_largen(args, torch, dist, world, rank, local, dev):
         sampler.start()
     line = run(args, world, rank, local, dev, sampler)
     if rank == 0 and line is not None and world == 1 and not args.no_cpu:
+        restore_affinity()
         rate, dtc = cpu_pairs_per_s(4096, 5)
         line["cpu_baseline"] = {"value": rate, "unit": "pair-interactions/s", "cores": 1, "kind": "port",
                                 "sample": f"oracle dense gravitational_force at N=4096 ({dtc*1e3:.0f} ms per call; the "
