@@ -12,7 +12,7 @@ for N, (m, q, v, soft, cohort) in sorted(buckets.items()):
     ns = bk.n_sub.cpu().numpy()
     print("N", N, "B", bk.B, "W", int(ns.sum()), "n_heavy", int(bk._bins[64]), "thr", int(bk._bins[65]),
           "hist>4:", int((ns > 4).sum()), ">10:", int((ns > 10).sum()), ">=50:", int((ns >= 50).sum()),
-          "env", os.environ.get("NB_HEAVY_KAPPA"), os.environ.get("NB_HEAVY_NSUB_FIXED"))
+          flush=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     q0, v0 = bk.q.clone(), bk.v.clone()
     for rep in range(2):
