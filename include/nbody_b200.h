@@ -81,7 +81,7 @@ enum {
  * one row of hs_params[B][NB_HS_NPARAM] */
 enum {
   NB_HS_K_SOFT = 0, NB_HS_MU_SOFT, NB_HS_EPS_MIN, NB_HS_EPS_MAX, NB_HS_ALPHA_RUN, NB_HS_K_WALL,
-  NB_HS_BARRIER_N, NB_HS_ETA, NB_HS_J_MAX_CAP, NB_HS_LAMBDA, NB_HS_POLICY /*0 soft, 2 none (1 = reflection: not built)*/,
+  NB_HS_BARRIER_N, NB_HS_ETA, NB_HS_J_MAX_CAP, NB_HS_LAMBDA, NB_HS_POLICY /*0 soft barrier, 1 reflection (fold), 2 none*/,
   NB_HS_THETA_IMP, NB_HS_THETA_CAP, NB_HS_CHI_PI, NB_HS_OMEGA_SPR0, NB_HS_S0,
   NB_HS_NPARAM
 };
