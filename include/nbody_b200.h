@@ -125,6 +125,17 @@ int nb_ensemble_run_f64(const double* m, double* q, double* v, const double* eps
                         double* eps_pi, const double* hs_params,
                         double* dyn_features, int32_t* status, void* stream);
 
+/* the same call with counted work for the roofline figures: work[B][2] (may be NULL) receives, per system,
+ *      whfast  : {Newton iterations summed over all Kepler solves, number of Kepler solves}   (kepler_solver.py:48-91)
+ *      ham_soft: {Jacobi sweeps of _solve_hi summed over the 4N+1 evaluations of every S half-flow, number of S half-flows}
+ *                (hamsoft_eps_model.py:316-400); verlet / yoshida4 leave it untouched (their work is n_sub x n_steps) */
+int nb_ensemble_run_counted_f64(const double* m, double* q, double* v, const double* eps, double G, int B, int N,
+                                int mode, unsigned flags, double dt, int n_steps, int sample_interval, int n_megno,
+                                const int32_t* n_sub, const int32_t* perm, const int32_t* n_heavy,
+                                const double* raw_dr, const double* raw_dv,
+                                double* eps_pi, const double* hs_params,
+                                double* dyn_features, int32_t* status, double* work, void* stream);
+
 /* ---- classic ADAPTIVE softening (adaptive_softening=True with verlet / yoshida4): n_steps macro steps in which the
  *      softening is re-derived from the minimum separation after every sub-step (integrator.py:126-136, 204-225;
  *      SofteningManager.softening_from_min_sep / refresh_softening / _compute_energy_correction,

@@ -42,7 +42,7 @@ N_HS = len(HS_PARAMS)
 
 EXPORTS = [
     "nb_last_error", "nb_version", "nb_pair_batched_f64", "nb_variational_batched_f64",
-    "nb_ensemble_prepare_f64", "nb_ensemble_run_f64", "nb_sort_by_nsub", "nb_ensemble_set_heavy_nsub",
+    "nb_ensemble_prepare_f64", "nb_ensemble_run_f64", "nb_ensemble_run_counted_f64", "nb_sort_by_nsub", "nb_ensemble_set_heavy_nsub",
     "nb_ensemble_run_adaptive_f64", "nb_ensemble_analyze_adaptive_f64", "nb_ensemble_analyze_host",
     "nb_ensemble_analyze_host_async", "nb_host_sync", "nb_hamsoft_setup_f64", "nb_hamsoft_probe_f64",
     "nb_largeN_accel_f32", "nb_largeN_kick_drift_f32", "nb_largeN_set_variant", "nb_largeN_pass_f32", "nb_mlp_classify_f32", "nb_generate_ensemble_f64",
@@ -74,6 +74,7 @@ def load():
     lib.nb_variational_batched_f64.argtypes = [p, p, p, p, d, i, i, p, p]
     lib.nb_ensemble_prepare_f64.argtypes = [p, p, p, p, d, i, i, i, u, d, d, d, i, p, p, p, p]
     lib.nb_ensemble_run_f64.argtypes = [p, p, p, p, d, i, i, i, u, d, i, i, i, p, p, p, p, p, p, p, p, p, p]
+    lib.nb_ensemble_run_counted_f64.argtypes = [p, p, p, p, d, i, i, i, u, d, i, i, i, p, p, p, p, p, p, p, p, p, p, p]
     lib.nb_sort_by_nsub.argtypes = [p, i, i, p, p, p]
     lib.nb_ensemble_set_heavy_nsub.argtypes = [i]
     lib.nb_ensemble_run_adaptive_f64.argtypes = [p, p, p, p, p, d, i, i, i, d, i, p, d, i, p, p, p, p]

@@ -26,6 +26,7 @@ struct RunArgs {
   const double* raw_dv;
   double* dyn;
   int32_t* status;
+  double* work;             // optional [B][2] counted work: whfast {Newton iterations, Kepler solves}; ham_soft {Jacobi sweeps, S half-flows}
 };
 
 struct PrepArgs {

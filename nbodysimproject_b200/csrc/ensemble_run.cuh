@@ -45,7 +45,7 @@ __device__ __forceinline__ void drift(SysState<N>& s, double h) {
 
 // whfast_scheme.py:22-37 + simulation.py:487-534: pseudo-Jacobi Kepler drift.  `m` are plain masses.
 template <int N, bool EXACT>
-__device__ __forceinline__ int kepler_drift(SysState<N>& s, const double* m, double G, double tau) {
+__device__ __forceinline__ int kepler_drift(SysState<N>& s, const double* m, double G, double tau, int& iters) {
   double jx[N], jy[N], jvx[N], jvy[N];
   int worst = 0;
   {
@@ -75,6 +75,7 @@ __device__ __forceinline__ int kepler_drift(SysState<N>& s, const double* m, dou
       double rx = jx[i], ry = jy[i], ux = jvx[i], uy = jvy[i];
       const int it = EXACT ? kepler_exact(rx, ry, ux, uy, mu, tau) : kepler_reference(rx, ry, ux, uy, mu, tau);
       worst = max(worst, it);
+      iters += min(it, 64);
       jx[i] = rx; jy[i] = ry; jvx[i] = ux; jvy[i] = uy;
     }
   }
@@ -155,7 +156,7 @@ __device__ __forceinline__ void wh_interaction_accel(const SysState<N>& s, const
 // force evaluation is fused with the variational acceleration (classic modes).
 template <int N, int MODE, bool GUARD, bool EXACT, bool TANGENT>
 __device__ __forceinline__ int substep(SysState<N>& s, const double* m, double G, double h, const double* drx,
-                                       const double* dry, double* dax, double* day) {
+                                       const double* dry, double* dax, double* day, int& iters) {
   int kep = 0;
   if (MODE == NB_MODE_VERLET) {
     const double h2 = 0.5 * h;
@@ -183,7 +184,7 @@ __device__ __forceinline__ int substep(SysState<N>& s, const double* m, double G
     pair_pass<N, TANGENT, GUARD>(s, drx, dry, dax, day);
     kick<N>(s, 0.5 * ha);
   } else {  // NB_MODE_WHFAST: Kepler(h/2) . full-force kick(h) . Kepler(h/2)   whfast_scheme.py:71-93
-    kep = kepler_drift<N, EXACT>(s, m, G, 0.5 * h);
+    kep = kepler_drift<N, EXACT>(s, m, G, 0.5 * h, iters);
     if (EXACT) {
       // physically correct Wisdom-Holman: kick with the INTERACTION acceleration only (the star-planet Kepler
       // terms are already in the drift); the reference kicks with the full force (whfast_scheme.py:85-88)
@@ -195,7 +196,7 @@ __device__ __forceinline__ int substep(SysState<N>& s, const double* m, double G
       pair_pass<N, false, GUARD>(s, nullptr, nullptr, nullptr, nullptr);
     }
     kick<N>(s, h);
-    kep = max(kep, kepler_drift<N, EXACT>(s, m, G, 0.5 * h));
+    kep = max(kep, kepler_drift<N, EXACT>(s, m, G, 0.5 * h, iters));
     if (TANGENT) pair_pass<N, true, GUARD>(s, drx, dry, dax, day);
   }
   return kep;
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(128) ensemble_main_kernel(RunArgs a, int write
   const double eps = a.eps[sys];
   const int n_sub = a.n_sub ? max(1, a.n_sub[sys]) : 1;
   const double h = a.dt / (double)n_sub;
-  int kep_worst = 0;
+  int kep_worst = 0, kep_iters = 0;
   if (MODE != NB_MODE_WHFAST) pair_pass<N, false, GUARD>(s, nullptr, nullptr, nullptr, nullptr);   // FSAL start
 
   double com_sum = 0.0, com_max = -1.0, var_sum = 0.0, var_max = -1.0, cos_sum = 0.0, cos_min = 2.0, th_sum = 0.0;
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(128) ensemble_main_kernel(RunArgs a, int write
   for (int step = 0; step < a.n_steps; ++step) {
 #pragma unroll 1
     for (int k = 0; k < n_sub; ++k)
-      kep_worst = max(kep_worst, substep<N, MODE, GUARD, EXACT, false>(s, m, G, h, nullptr, nullptr, nullptr, nullptr));
+      kep_worst = max(kep_worst, substep<N, MODE, GUARD, EXACT, false>(s, m, G, h, nullptr, nullptr, nullptr, nullptr, kep_iters));
     if (interval > 0 && step == next_sample) {       // diagnostics.py:241-285
       next_sample += interval;
       double cx = 0.0, cy = 0.0, Lt = 0.0, Li[N];
@@ -314,6 +315,10 @@ __global__ void __launch_bounds__(128) ensemble_main_kernel(RunArgs a, int write
   int st = store_state<N>(a, sys, s, write_state != 0);
   if (MODE == NB_MODE_WHFAST && kep_worst > 64) st |= NB_STATUS_KEPLER_NOCONV;
   if (a.status) a.status[sys] = st;
+  if (MODE == NB_MODE_WHFAST && a.work) {   // counted work for the roofline (mean Newton iterations)
+    a.work[2 * (size_t)sys] = (double)kep_iters;
+    a.work[2 * (size_t)sys + 1] = 2.0 * (N - 1) * (double)n_sub * (double)a.n_steps;
+  }
   if (a.dyn) {
     double* f = a.dyn + (size_t)sys * NB_N_DYN;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(128) ensemble_megno_kernel(RunArgs a, int writ
   const double G = a.G;
   const int n_sub = a.n_sub ? max(1, a.n_sub[sys]) : 1;
   const double h = a.dt / (double)n_sub;
-  int kep_worst = 0;
+  int kep_worst = 0, kep_iters = 0;
   if (MODE != NB_MODE_WHFAST) pair_pass<N, false, GUARD>(s, nullptr, nullptr, nullptr, nullptr);
 
   double drx[N], dry[N], dvx[N], dvy[N], dax[N], day[N];
@@ -385,11 +390,11 @@ __global__ void __launch_bounds__(128) ensemble_megno_kernel(RunArgs a, int writ
   for (int step = 0; step < a.n_megno; ++step) {
 #pragma unroll 1
     for (int k = 0; k < n_sub - 1; ++k)
-      kep_worst = max(kep_worst, substep<N, MODE, GUARD, EXACT, false>(s, m, G, h, nullptr, nullptr, nullptr, nullptr));
+      kep_worst = max(kep_worst, substep<N, MODE, GUARD, EXACT, false>(s, m, G, h, nullptr, nullptr, nullptr, nullptr, kep_iters));
     // delta_r += delta_v dt does not depend on the step, so it can precede the fused last evaluation
 #pragma unroll
     for (int i = 0; i < N; ++i) { drx[i] = fma(dvx[i], dt, drx[i]); dry[i] = fma(dvy[i], dt, dry[i]); }
-    kep_worst = max(kep_worst, substep<N, MODE, GUARD, EXACT, true>(s, m, G, h, drx, dry, dax, day));
+    kep_worst = max(kep_worst, substep<N, MODE, GUARD, EXACT, true>(s, m, G, h, drx, dry, dax, day, kep_iters));
     double nr = 0.0, nv = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {

@@ -145,103 +145,126 @@ __device__ __forceinline__ double hs_eps_target(const double* qx, const double* 
   return es;
 }
 
-// hamsoft_eps_model.py:451-556 analytic SPH gradient
+// =================================================================================================
+// Group-cooperative run path.  A "group" = the LPS (16 or 32) lanes that serve one system.  The system's state lives
+// ONCE in shared memory (HsSh); a lane keeps in registers only what its current phase needs:
+//   * eps* model  : lane e holds ONE finite-difference evaluation (pair distances r2[NP] + smoothing lengths h[N]),
+//                   nothing else is live across the Jacobi sweeps -> no local-memory spill
+//   * every other flow (gradient assembly, J cap, V half kick, T drift, tangent map): lane i < N owns BODY i,
+//                   sums / maxima over bodies are xor-butterflies inside the group
+// Round 1 kept a full replica of the state, the parameters, the sampling accumulators and the tangent vectors in the
+// registers of every lane (61 live doubles at N = 3 against a 128-register cap): 0.8-1.7 KB of spill per thread,
+// 410 MB of DRAM writes per launch, FP64 pipe 34 % busy.
+// Two systems may share a warp (LPS = 16): every shuffle names its source lane inside the group and the butterflies use
+// offsets < LPS, so full-mask intrinsics stay legal; a system that has fewer sub-steps than its neighbour executes the
+// excess with its writes predicated off (`act`).
+// =================================================================================================
+#define HS_NACC 22
+enum { HA_COM_SUM = 0, HA_COM_MAX, HA_VAR_SUM, HA_VAR_MAX, HA_COS_SUM, HA_COS_MIN, HA_WJ_MEAN, HA_WJ_M2, HA_WT_MEAN,
+       HA_WT_M2, HA_LFIRST, HA_NSAMP, HA_WJ_N, HA_WT_N, HA_HAVE_FIRST, HA_COS_NAN, HA_TH_NAN, HA_E0, HA_L0, HA_E1, HA_L1 };
+
 template <int N>
-__device__ __noinline__ void hs_production_grad(const double* qx, const double* qy, const double* m, double eps_cur,
-                                                const HsPar& P, double* gx, double* gy) {
-  double h[N];
-  hs_solve_hi<N>(qx, qy, m, eps_cur, P, h);
-  const double flo = fmax(P.eps_min, 1.0e-12);
-  const double hmin = fmax(1.0e-12, 0.1 * flo);
-  double tmax = -h[0] / P.alpha;
-  for (int i = 1; i < N; ++i) tmax = fmax(tmax, -h[i] / P.alpha);
-  double den = 0.0;
-  for (int i = 0; i < N; ++i) den += exp(-h[i] / P.alpha - tmax);
-  for (int i = 0; i < N; ++i) { gx[i] = 0.0; gy[i] = 0.0; }
-  if (den <= 0.0 || !is_finite(den)) return;
-  double Pi[N], w[N];
-  for (int i = 0; i < N; ++i) {
-    w[i] = exp(-h[i] / P.alpha - tmax) / den;
-    const double hj = fmax(h[i], hmin);
-    double S = 0.0, Sd = 0.0;
-    for (int j = 0; j < N; ++j) {
-      if (j == i) continue;
-      const double dx = qx[i] - qx[j], dy = qy[i] - qy[j];
-      const double rr = dx * dx + dy * dy;
-      const double c = 1.0 / (NB_PI * hj * hj);
-      const double W = c * exp(-rr / (hj * hj));
-      S += m[j] * W;
-      Sd += m[j] * (W * (-2.0 / hj + 2.0 * rr / (hj * hj * hj)));
-    }
-    const double Si = fmax(S, 1.0e-30);
-    double Om = 1.0 + hj * Sd / (2.0 * Si);
-    if (!is_finite(Om) || Om == 0.0) Om = 1.0;
-    Pi[i] = -hj / (2.0 * Si * Om);
-  }
-  for (int i = 0; i < N; ++i) {
-    const double hj = fmax(h[i], hmin);
-    const double s_i = -w[i] * Pi[i];
-    for (int j = 0; j < N; ++j) {
-      if (j == i) continue;
-      const double rx = qx[i] - qx[j], ry = qy[i] - qy[j];
-      const double c = 1.0 / (NB_PI * hj * hj);
-      const double W = c * exp(-(rx * rx + ry * ry) / (hj * hj));
-      const double coef = -2.0 * W / (hj * hj);
-      gx[i] += s_i * m[j] * (coef * rx);
-      gy[i] += s_i * m[j] * (coef * ry);
-      gx[j] -= s_i * m[j] * (coef * rx);
-      gy[j] -= s_i * m[j] * (coef * ry);
-    }
-  }
-  for (int i = 0; i < N; ++i) {
-    if (!is_finite(gx[i])) gx[i] = 0.0;
-    if (!is_finite(gy[i])) gy[i] = 0.0;
-  }
-}
+struct HsSh {
+  static constexpr int NP = N * (N - 1) / 2;
+  double m[N], x[N], y[N], vx[N], vy[N];
+  double gx[N], gy[N];          // grad eps* of the current S half-flow
+  double h[N];                  // smoothing lengths of the UNPERTURBED configuration (reused by the analytic fallback)
+  double bx[N], by[N];          // per-body exchange buffer of the analytic fallback
+  double drx[N], dry[N], dvx[N], dvy[N];   // tangent vectors (MEGNO)
+  double rs[NP > 0 ? NP : 1];   // pair separations (median test, legacy gradient)
+  double acc[HS_NACC];          // step_metrics accumulators, touched by the group's lane 0 only
+  HsPar P;
+};
 
-// softening.py:86-131 legacy gradient; only sum(g_use . g_legacy) is needed (sign alignment)
+template <int LPS>
+__device__ __forceinline__ double grp_max(double v) {
+#pragma unroll
+  for (int off = LPS / 2; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+template <int LPS>
+__device__ __forceinline__ double grp_sum(double v) {
+#pragma unroll
+  for (int off = LPS / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+// index of the unordered pair (a < b) in the row-major upper triangle
 template <int N>
-__device__ __noinline__ double hs_legacy_dot(const double* qx, const double* qy, const double* gx, const double* gy,
-                                             double lam) {
-  double D = 0.0;
-  for (int i = 0; i < N; ++i)
-    for (int j = i + 1; j < N; ++j) {
-      const double dx = qx[i] - qx[j], dy = qy[i] - qy[j];
-      const double r = fmax(sqrt(dx * dx + dy * dy), 1.0e-15);
-      D += 1.0 / (r + 1.0e-12);
+__device__ __forceinline__ int hs_pair_index(int a, int b) { return a * N - a * (a + 1) / 2 + (b - a - 1); }
+
+// Jacobi sweeps of hamsoft_eps_model.py:316-400 on register-resident pair distances; returns the sweeps executed.
+// exp(-r^2/h^2) underflows to exactly 0 below -745.13: those pairs (most of them once bodies are a few h apart) skip
+// the exponential altogether -- same bits, and when a whole warp agrees, none of its instructions.
+template <int N>
+__device__ __forceinline__ int hs_solve_regs(const double (&r2)[N * (N - 1) / 2 > 0 ? N * (N - 1) / 2 : 1],
+                                             const double* m, double eps_cur, const HsPar& P, double (&h)[N]) {
+  double lo = P.eps_min, hi = P.eps_max;
+  if (hi < lo) { const double t = lo; lo = hi; hi = t; }
+  const double flo = fmax(lo, 1.0e-12), cap = fmax(flo, hi);
+  double h0 = eps_cur;
+  if (!is_finite(h0) || h0 <= 0.0) h0 = 1.0;
+  h0 = fmin(fmax(h0, flo), cap);
+#pragma unroll
+  for (int i = 0; i < N; ++i) h[i] = h0;
+  const double eta = P.eta;
+  int it = 0;
+#pragma unroll 1
+  while (it < 8) {
+    double changed = 0.0;
+    double hn[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double hj = fmax(h[i], 1.0e-12);
+      const double h2 = hj * hj;
+      const double c = 1.0 / (NB_PI * h2);
+      const double nih2 = -1.0 / h2;
+      double S = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        if (j == i) continue;
+        const int a = i < j ? i : j, b = i < j ? j : i;
+        const double arg = r2[a * N - a * (a + 1) / 2 + (b - a - 1)] * nih2;
+        if (arg > -746.0) S += m[j] * (c * exp(arg));
+      }
+      const double Si = fmax(S, 1.0e-30);
+      double v = eta * sqrt(m[i] / Si);
+      if (!is_finite(v) || v <= 0.0) v = h[i];
+      if (v < flo) v = flo;
+      else if (v > cap) v = cap;
+      const double rel = fabs(v - h[i]) / fmax(h[i], 1.0e-12);
+      changed = fmax(changed, rel);
+      hn[i] = v;
     }
-  if (!is_finite(D) || D <= 0.0) return 0.0;
-  const double cp = lam * ((double)N / (D * D));
-  double dot = 0.0;
-  bool ok = true;
-  for (int i = 0; i < N; ++i) {
-    double sx = 0.0, sy = 0.0;
-    for (int j = 0; j < N; ++j) {
-      if (j == i) continue;
-      const double dx = qx[i] - qx[j], dy = qy[i] - qy[j];
-      const double r = fmax(sqrt(dx * dx + dy * dy), 1.0e-15);
-      const double den = r + 1.0e-12;
-      const double A = 1.0 / (r * den * den);
-      sx += A * dx;
-      sy += A * dy;
-    }
-    const double lx = -cp * sx, ly = -cp * sy;
-    ok = ok && is_finite(lx) && is_finite(ly);
-    dot += gx[i] * lx + gy[i] * ly;
+#pragma unroll
+    for (int i = 0; i < N; ++i) h[i] = hn[i];
+    ++it;
+    if (changed < 1.0e-6) break;
   }
-  return ok ? dot : 0.0;
+  return it;
 }
 
-// FD step of coordinate value x (hamsoft_eps_model.py:136-144)
-__device__ __forceinline__ double hs_fd_step(double x) {
-  double h = 1.0e-5 * fmax(fabs(x), 1.0);
-  if (h < 1.0e-10) h = 1.0e-10;
-  return h;
+// hamsoft_eps_model.py:240-289: soft-min of the h_i with temperature alpha_run (+ clamp under the soft policy)
+template <int N>
+__device__ __forceinline__ double hs_softmin(const double (&h)[N], const HsPar& P) {
+  const double alpha = P.alpha;
+  double tmax = -h[0] / alpha;
+#pragma unroll
+  for (int i = 1; i < N; ++i) tmax = fmax(tmax, -h[i] / alpha);
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) s += exp(-h[i] / alpha - tmax);
+  double es;
+  if (s <= 0.0 || !is_finite(s)) es = P.s0;
+  else es = -alpha * (tmax + log(s));
+  if (P.policy == 0) {
+    double lo = P.eps_min, hi = P.eps_max;
+    if (hi < lo) { const double t = lo; lo = hi; hi = t; }
+    if (es < lo) es = lo;
+    else if (es > hi) es = hi;
+  }
+  return es;
 }
 
-// eps*(q) and its gradient, cooperatively over the warp: lane 0 evaluates the unperturbed configuration,
-// lane 1+2c+s the coordinate c = 2 i + a perturbed by +h (s = 0) or -h (s = 1).  Every lane returns the full
-// gradient.  hamsoft_eps_model.py:94-234.
 // Lanes per system.  4 N + 1 evaluations fit a half warp for N <= 3, so two systems share a warp there.  For N = 4
 // (17) and N = 8 (33) the odd one out -- the UNPERTURBED evaluation -- is computed cooperatively instead (one body per
 // lane, Jacobi sweeps exchanged by shuffles; same arithmetic per body, so the same bits as the serial solve at 1/N of
@@ -249,22 +272,21 @@ __device__ __forceinline__ double hs_fd_step(double x) {
 template <int N>
 struct HsLanes {
   static constexpr bool COOP = (N == 4 || N == 8);
-  static constexpr int NE = COOP ? 4 * N : 4 * N + 1;        // evaluations spread one per lane
+  static constexpr int NE = COOP ? 4 * N : 4 * N + 1;        // evaluations, one per lane
   static constexpr int LPS = (NE <= 16) ? 16 : 32;
+  static_assert(NE <= LPS, "one finite-difference evaluation per lane");
 };
 
-// eps_target of the unperturbed configuration, cooperatively over the lanes [base, base + LPS) of one system
-// (hamsoft_eps_model.py:316-400 + :240-289).  All lanes of the group hold the same x, y, m.  Warp-uniform control flow:
-// the sweep loop always runs 8 times and a converged group simply stops updating (the two systems of a warp may
-// converge at different sweeps, and the shuffles need the whole warp).
+// eps_target of the unperturbed configuration, cooperatively over the lanes of one group (hamsoft_eps_model.py:316-400
+// + :240-289); lane k < N ends up with h_k and publishes it in sh.h.  Warp-uniform control flow: the sweep loop always
+// runs 8 times and a converged group simply stops updating (the two systems of a warp may converge at different sweeps
+// and the shuffles need the whole warp).
 template <int N>
-__device__ __forceinline__ double hs_eps_target_coop(const double* x, const double* y, const double* m, double eps_cur,
-                                                     const HsPar& P, int lane, int base) {
+__device__ __forceinline__ double hs_eps_target_coop(HsSh<N>& sh, double eps_cur, int lane, int base, int& sweeps) {
   constexpr int LPS = HsLanes<N>::LPS;
+  const HsPar& P = sh.P;
   const int i = lane < N ? lane : 0;                        // spare lanes shadow body 0
-  double xi = x[0], yi = y[0], mi = m[0];
-#pragma unroll
-  for (int k = 1; k < N; ++k) if (k == i) { xi = x[k]; yi = y[k]; mi = m[k]; }
+  const double xi = sh.x[i], yi = sh.y[i], mi = sh.m[i];
   double lo = P.eps_min, hi = P.eps_max;
   if (hi < lo) { const double t = lo; lo = hi; hi = t; }
   const double flo = fmax(lo, 1.0e-12), cap = fmax(flo, hi);
@@ -275,11 +297,13 @@ __device__ __forceinline__ double hs_eps_target_coop(const double* x, const doub
 #pragma unroll
   for (int j = 0; j < N; ++j) {
     // the serial solver stores r^2 of the pair (min, max): same value, the squares do not see the sign
-    const double dx = (i < j) ? xi - x[j] : x[j] - xi, dy = (i < j) ? yi - y[j] : y[j] - yi;
+    const double xj = sh.x[j], yj = sh.y[j];
+    const double dx = (i < j) ? xi - xj : xj - xi, dy = (i < j) ? yi - yj : yj - yi;
     r2[j] = dx * dx + dy * dy;
   }
   double hcur = h0;
   bool done = false;
+  int used = 0;
 #pragma unroll 1
   for (int it = 0; it < 8; ++it) {
     const double hj = fmax(hcur, 1.0e-12);
@@ -289,136 +313,227 @@ __device__ __forceinline__ double hs_eps_target_coop(const double* x, const doub
     double S = 0.0;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      const double term = m[j] * (c * exp(r2[j] * nih2));
-      if (j != i) S += term;
+      const double arg = r2[j] * nih2;
+      if (j != i && arg > -746.0) S += sh.m[j] * (c * exp(arg));
     }
     const double Si = fmax(S, 1.0e-30);
     double v = P.eta * sqrt(mi / Si);
     if (!is_finite(v) || v <= 0.0) v = hcur;
     if (v < flo) v = flo;
     else if (v > cap) v = cap;
-    double rel = fabs(v - hcur) / fmax(hcur, 1.0e-12);
-#pragma unroll
-    for (int off = LPS / 2; off > 0; off >>= 1) rel = fmax(rel, __shfl_xor_sync(0xffffffffu, rel, off));
-    if (!done) hcur = v;
+    const double rel = grp_max<LPS>(fabs(v - hcur) / fmax(hcur, 1.0e-12));
+    if (!done) { hcur = v; ++used; }
     if (rel < 1.0e-6) done = true;                          // group-uniform
   }
+  if (lane == 0) sweeps += used;
+  if (lane < N) sh.h[lane] = hcur;
   double h[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) h[k] = __shfl_sync(0xffffffffu, hcur, base + k);
-  double tmax = -h[0] / P.alpha;
-#pragma unroll
-  for (int k = 1; k < N; ++k) tmax = fmax(tmax, -h[k] / P.alpha);
-  double sum = 0.0;
-#pragma unroll
-  for (int k = 0; k < N; ++k) sum += exp(-h[k] / P.alpha - tmax);
-  double es;
-  if (sum <= 0.0 || !is_finite(sum)) es = P.s0;
-  else es = -P.alpha * (tmax + log(sum));
-  if (P.policy == 0) {
-    double l2 = P.eps_min, h2b = P.eps_max;
-    if (h2b < l2) { const double t = l2; l2 = h2b; h2b = t; }
-    if (es < l2) es = l2;
-    else if (es > h2b) es = h2b;
-  }
-  return es;
+  return hs_softmin<N>(h, P);
 }
 
+// FD step of coordinate value x (hamsoft_eps_model.py:136-144)
+__device__ __forceinline__ double hs_fd_step(double x) {
+  double h = 1.0e-5 * fmax(fabs(x), 1.0);
+  if (h < 1.0e-10) h = 1.0e-10;
+  return h;
+}
+
+// hamsoft_eps_model.py:451-556 analytic SPH gradient + softening.py:86-131 sign reference, one body per lane.
+// Runs when ANY group of the warp needs it (warp-uniform branch, so the butterflies inside stay legal); a group
+// commits the result only if it needs it itself.  sh.h holds the smoothing lengths of the unperturbed configuration
+// (the reference calls _solve_hi again with identical inputs).
 template <int N>
-__device__ __forceinline__ double hs_eps_star_and_grad(const double* x, const double* y, const double* m,
-                                                       double eps_cur, const HsPar& P, int lane_full, double* gx,
-                                                       double* gy, bool& used_fallback) {
+__device__ __forceinline__ void hs_fallback_grp(HsSh<N>& sh, int lane, bool commit) {
+  constexpr int LPS = HsLanes<N>::LPS;
+  constexpr int NP = HsSh<N>::NP;
+  const HsPar& P = sh.P;
+  const bool mine = lane < N;
+  const int i = mine ? lane : 0;
+  const double xi = sh.x[i], yi = sh.y[i], mi = sh.m[i];
+  const double flo = fmax(P.eps_min, 1.0e-12);
+  const double hmin = fmax(1.0e-12, 0.1 * flo);
+  const double ti = -sh.h[i] / P.alpha;
+  const double tmax = grp_max<LPS>(ti);
+  const double ei = exp(ti - tmax);
+  __syncwarp();
+  if (mine) sh.bx[i] = ei;
+  __syncwarp();
+  double den = 0.0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) den += sh.bx[k];
+  const bool bad = (den <= 0.0 || !is_finite(den));
+  const double wi = ei / den;
+  const double hj = fmax(sh.h[i], hmin);
+  const double c = 1.0 / (NB_PI * hj * hj);
+  double S = 0.0, Sd = 0.0;
+  double W[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    W[j] = 0.0;
+    if (j == i) continue;
+    const double dx = xi - sh.x[j], dy = yi - sh.y[j];
+    const double rr = dx * dx + dy * dy;
+    const double arg = -rr / (hj * hj);
+    if (arg > -746.0) {
+      W[j] = c * exp(arg);
+      S += sh.m[j] * W[j];
+      Sd += sh.m[j] * (W[j] * (-2.0 / hj + 2.0 * rr / (hj * hj * hj)));
+    }
+  }
+  const double Si = fmax(S, 1.0e-30);
+  double Om = 1.0 + hj * Sd / (2.0 * Si);
+  if (!is_finite(Om) || Om == 0.0) Om = 1.0;
+  const double si = -wi * (-hj / (2.0 * Si * Om));
+  __syncwarp();
+  if (mine) { sh.bx[i] = si; sh.by[i] = hj; }
+  __syncwarp();
+  // the reference scatters s_i m_j coef_i(r_ij) (q_i - q_j) onto i (+) and j (-); gathered per body here
+  double gx = 0.0, gy = 0.0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    if (j == i) continue;
+    const double rx = xi - sh.x[j], ry = yi - sh.y[j];
+    const double coef = -2.0 * W[j] / (hj * hj);
+    gx += si * sh.m[j] * (coef * rx);
+    gy += si * sh.m[j] * (coef * ry);
+  }
+#pragma unroll
+  for (int a = 0; a < N; ++a) {
+    if (a == i) continue;
+    const double ha = sh.by[a], sa = sh.bx[a];
+    const double rx = sh.x[a] - xi, ry = sh.y[a] - yi;
+    const double arg = -(rx * rx + ry * ry) / (ha * ha);
+    if (arg > -746.0) {
+      const double Wa = (1.0 / (NB_PI * ha * ha)) * exp(arg);
+      const double coef = -2.0 * Wa / (ha * ha);
+      gx -= sa * mi * (coef * rx);
+      gy -= sa * mi * (coef * ry);
+    }
+  }
+  if (bad || !is_finite(gx)) gx = 0.0;
+  if (bad || !is_finite(gy)) gy = 0.0;
+  // sign alignment against the legacy gradient: only sum(g_use . g_legacy) matters
+  const double dp = lane < NP ? 1.0 / (fmax(sh.rs[lane < NP ? lane : 0], 1.0e-15) + 1.0e-12) : 0.0;
+  const double D = grp_sum<LPS>(dp);
+  double sg = 1.0;
+  {
+    const double cp = P.lam * ((double)N / (D * D));
+    double sx = 0.0, sy = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      if (j == i) continue;
+      const int a = i < j ? i : j, b = i < j ? j : i;
+      const double r = fmax(sh.rs[hs_pair_index<N>(a, b)], 1.0e-15);
+      const double dn = r + 1.0e-12;
+      const double A = 1.0 / (r * dn * dn);
+      sx += A * (xi - sh.x[j]);
+      sy += A * (yi - sh.y[j]);
+    }
+    const double lx = -cp * sx, ly = -cp * sy;
+    const double nok = grp_max<LPS>((mine && !(is_finite(lx) && is_finite(ly))) ? 1.0 : 0.0);
+    const double dot = grp_sum<LPS>(mine ? gx * lx + gy * ly : 0.0);
+    if (is_finite(D) && D > 0.0 && nok == 0.0 && is_finite(dot) && dot < 0.0) sg = -1.0;
+  }
+  if (commit && mine) { sh.gx[i] = sg * gx; sh.gy[i] = sg * gy; }
+}
+
+// eps*(q) and its gradient (hamsoft_eps_model.py:94-234) for the system in `sh`: lane e of the group evaluates ONE
+// configuration (e = 0: unperturbed unless COOP; then coordinate c = 2 i + a perturbed by +h / -h), body lanes assemble
+// the central differences, and the gradient lands in sh.gx / sh.gy.  Returns eps* on every lane of the group.
+template <int N>
+__device__ __forceinline__ double hs_eps_star_and_grad(HsSh<N>& sh, double eps_cur, int lane_full, bool& used_fallback,
+                                                       int& sweeps) {
   constexpr bool COOP = HsLanes<N>::COOP;
   constexpr int NE = HsLanes<N>::NE;
   constexpr int LPS = HsLanes<N>::LPS;
   constexpr int OFF = COOP ? 0 : 1;           // evaluation index of the first perturbed configuration
+  constexpr int NP = HsSh<N>::NP;
   const int lane = lane_full & (LPS - 1);     // lane within this system's group
   const int base = lane_full - lane;          // first lane of the group
-  double f[2] = {0.0, 0.0};
-#pragma unroll
-  for (int pass = 0; pass < (NE + LPS - 1) / LPS; ++pass) {
-    const int e = lane + LPS * pass;          // evaluation index
-    const int ee = e < NE ? e : 0;            // idle lanes redo evaluation 0
+  const HsPar& P = sh.P;
+  __syncwarp();                               // positions written by the body lanes are visible to every lane
+  double f;
+  {
+    const int ee = lane < NE ? lane : 0;      // idle lanes redo evaluation 0
     const bool pert = COOP || ee >= 1;        // without COOP evaluation 0 is the unperturbed configuration
     const int c = (ee - OFF) >> 1;            // perturbed coordinate
     const double sgn = ((ee - OFF) & 1) ? -1.0 : 1.0;
-    double px[N], py[N];
+    double r2[NP > 0 ? NP : 1];
+    {
+      double px[N], py[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      px[i] = x[i];
-      py[i] = y[i];
-      if (pert && c == 2 * i) px[i] = x[i] + sgn * hs_fd_step(x[i]);
-      if (pert && c == 2 * i + 1) py[i] = y[i] + sgn * hs_fd_step(y[i]);
-    }
-    f[pass] = hs_eps_target<N>(px, py, m, eps_cur, P);
-  }
-  const double es = COOP ? hs_eps_target_coop<N>(x, y, m, eps_cur, P, lane, base) : __shfl_sync(0xffffffffu, f[0], base);
-  double gmax2 = 0.0;
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const int c = 2 * i + a;
-      const int ep = OFF + 2 * c, em = OFF + 1 + 2 * c;
-      const double fp = ep < LPS ? __shfl_sync(0xffffffffu, f[0], base + (ep & (LPS - 1)))
-                                 : __shfl_sync(0xffffffffu, f[1], base + (ep & (LPS - 1)));
-      const double fm = em < LPS ? __shfl_sync(0xffffffffu, f[0], base + (em & (LPS - 1)))
-                                 : __shfl_sync(0xffffffffu, f[1], base + (em & (LPS - 1)));
-      const double h = hs_fd_step(a == 0 ? x[i] : y[i]);
-      double g = (fp - fm) / (2.0 * h);
-      if (!is_finite(g)) g = 0.0;
-      if (a == 0) gx[i] = g; else gy[i] = g;
-    }
-    gmax2 = fmax(gmax2, gx[i] * gx[i] + gy[i] * gy[i]);
-  }
-  const double gmax = sqrt(gmax2);
-  // median pair separation
-  constexpr int NP = N * (N - 1) / 2;
-  double rs[NP > 0 ? NP : 1];
-  {
-    int p = 0;
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int j = i + 1; j < N; ++j) {
-        const double dx = x[i] - x[j], dy = y[i] - y[j];
-        rs[p++] = sqrt(dx * dx + dy * dy);
+      for (int i = 0; i < N; ++i) {
+        px[i] = sh.x[i];
+        py[i] = sh.y[i];
+        if (pert && c == 2 * i) px[i] = px[i] + sgn * hs_fd_step(px[i]);
+        if (pert && c == 2 * i + 1) py[i] = py[i] + sgn * hs_fd_step(py[i]);
       }
-  }
-  double rmed = 0.0;
-  if (NP > 0) {
-    // rank selection without dynamic indexing of a sorted copy
-    double lo_v = 0.0, hi_v = 0.0;
-    const int klo = (NP - 1) / 2, khi = NP / 2;
+      int p = 0;
 #pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      int less = 0, eq = 0;
+      for (int i = 0; i < N; ++i)
 #pragma unroll
-      for (int r = 0; r < NP; ++r) { less += rs[r] < rs[p]; eq += rs[r] == rs[p]; }
-      if (less <= klo && klo < less + eq) lo_v = rs[p];
-      if (less <= khi && khi < less + eq) hi_v = rs[p];
+        for (int j = i + 1; j < N; ++j) {
+          const double dx = px[i] - px[j], dy = py[i] - py[j];
+          r2[p++] = dx * dx + dy * dy;
+        }
     }
-    rmed = 0.5 * (lo_v + hi_v);
+    double h[N];
+    const int used = hs_solve_regs<N>(r2, sh.m, eps_cur, P, h);
+    if (lane < NE) sweeps += used;
+    if (!COOP && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) sh.h[i] = h[i];
+    }
+    f = hs_softmin<N>(h, P);
   }
+  double es;
+  if constexpr (COOP) es = hs_eps_target_coop<N>(sh, eps_cur, lane, base, sweeps);
+  else es = __shfl_sync(0xffffffffu, f, base);
+  // central differences, one body per lane
+  const bool mine = lane < N;
+  const int i = mine ? lane : N - 1;
+  const int src = base + OFF + 4 * i;
+  const double fpx = __shfl_sync(0xffffffffu, f, src), fmx = __shfl_sync(0xffffffffu, f, src + 1);
+  const double fpy = __shfl_sync(0xffffffffu, f, src + 2), fmy = __shfl_sync(0xffffffffu, f, src + 3);
+  const double xi = sh.x[i], yi = sh.y[i];
+  double gx = (fpx - fmx) / (2.0 * hs_fd_step(xi));
+  double gy = (fpy - fmy) / (2.0 * hs_fd_step(yi));
+  if (!is_finite(gx)) gx = 0.0;
+  if (!is_finite(gy)) gy = 0.0;
+  const double gmax = sqrt(grp_max<LPS>(mine ? gx * gx + gy * gy : 0.0));
+  if (mine) { sh.gx[i] = gx; sh.gy[i] = gy; }
+  // median pair separation: one pair per lane, rank selection through shared memory
+  double rsp = 0.0;
+  if (lane < NP) {
+    int pa = 0, pb = 1, idx = 0;
+#pragma unroll
+    for (int a = 0; a < N; ++a)
+#pragma unroll
+      for (int b = a + 1; b < N; ++b) { if (idx == lane) { pa = a; pb = b; } ++idx; }
+    const double dx = sh.x[pa] - sh.x[pb], dy = sh.y[pa] - sh.y[pb];
+    rsp = sqrt(dx * dx + dy * dy);
+    sh.rs[lane] = rsp;
+  }
+  __syncwarp();
+  const double ninf = __longlong_as_double(0xfff0000000000000LL);
+  double lo_c = ninf, hi_c = ninf;
+  if (lane < NP) {
+    constexpr int klo = (NP - 1) / 2, khi = NP / 2;
+    int less = 0, eq = 0;
+#pragma unroll
+    for (int r = 0; r < NP; ++r) { const double v = sh.rs[r]; less += v < rsp; eq += v == rsp; }
+    if (less <= klo && klo < less + eq) lo_c = rsp;
+    if (less <= khi && khi < less + eq) hi_c = rsp;
+  }
+  const double lo_v = grp_max<LPS>(lo_c), hi_v = grp_max<LPS>(hi_c);
+  const double rmed = (lo_v > ninf && hi_v > ninf) ? 0.5 * (lo_v + hi_v) : 0.0;
   used_fallback = (gmax <= 1.0e-12) || (gmax <= 1.0e-9 * rmed);
-  if (used_fallback) {
-    double ax[N], ay[N], cx[N], cy[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) { cx[i] = x[i]; cy[i] = y[i]; }
-    hs_production_grad<N>(cx, cy, m, eps_cur, P, ax, ay);
-    const double dot = hs_legacy_dot<N>(cx, cy, ax, ay, P.lam);
-    const double sg = (is_finite(dot) && dot < 0.0) ? -1.0 : 1.0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) { gx[i] = sg * ax[i]; gy[i] = sg * ay[i]; }
-  }
+  if (__any_sync(0xffffffffu, used_fallback)) hs_fallback_grp<N>(sh, lane, used_fallback);
+  __syncwarp();
   return es;
 }
-
-template <int N>
-struct HsState {
-  double m[N], x[N], y[N], vx[N], vy[N];
-  double eps, pi;
-};
 
 // reflect_and_bounce(eps, pi, h = 0) = reflect_if_needed (hamsoft_barrier_controller.py:27-69, hamsoft_utils.py:105-176)
 __device__ __forceinline__ void hs_fold(double& eps, double& pi, const HsPar& P) {
@@ -433,14 +548,19 @@ __device__ __forceinline__ void hs_fold(double& eps, double& pi, const HsPar& P)
   else { eps = b - (y - R); pi = -pi; }
 }
 
-// S half-flow: hamsoft_stepper.py:47-88 -> spring_oscillation (live definition) hamsoft_flows.py:427-762
+// S half-flow: hamsoft_stepper.py:47-88 -> spring_oscillation (live definition) hamsoft_flows.py:427-762.
+// eps, pi are replicated scalars of the group; momenta are updated by the body lanes.
 template <int N>
-__device__ __forceinline__ void hs_s_half(HsState<N>& s, const HsPar& P, double h, int lane) {
+__device__ __forceinline__ void hs_s_half(HsSh<N>& sh, double& eps, double& pi, double h, int lane_full, bool act,
+                                          int& sweeps) {
+  constexpr int LPS = HsLanes<N>::LPS;
+  const int lane = lane_full & (LPS - 1);
+  const HsPar& P = sh.P;
   const double dt = 0.5 * h;
-  double gx[N], gy[N];
+  double eps0 = eps, pi0 = pi;
+  hs_fold(eps0, pi0, P);                         // hamsoft_stepper.py:107-113
   bool fb;
-  hs_fold(s.eps, s.pi, P);                       // hamsoft_stepper.py:107-113
-  const double es = hs_eps_star_and_grad<N>(s.x, s.y, s.m, s.eps, P, lane, gx, gy, fb);
+  const double es = hs_eps_star_and_grad<N>(sh, eps0, lane_full, fb, sweeps);
   const double k = P.k, mu = P.mu;
   const double om = (k > 0.0 && mu > 0.0) ? sqrt(k / mu) : 0.0;
   const double th = om * dt;
@@ -452,7 +572,6 @@ __device__ __forceinline__ void hs_s_half(HsState<N>& s, const HsPar& P, double 
   } else {
     sincos(th, &sn, &cs);
   }
-  const double eps0 = s.eps, pi0 = s.pi;
   const double kick1 = (P.policy == 0) ? 0.5 * dt * hs_barrier_force(eps0, P) : 0.0;
   const double D0 = eps0 - es;
   const double pin = pi0 + kick1;
@@ -466,95 +585,96 @@ __device__ __forceinline__ void hs_s_half(HsState<N>& s, const HsPar& P, double 
   } else {
     dlt = D0; eta_t = pin; I = 0.0;
   }
-  const double eps_rot = es + dlt;
+  double eps_rot = es + dlt;
   const double kick2 = (P.policy == 0) ? 0.5 * dt * hs_barrier_force(eps_rot, P) : 0.0;
   const double J = k * I;
-  double pmax2 = 0.0, dmax2 = 0.0;
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    const double px = s.m[i] * s.vx[i], py = s.m[i] * s.vy[i];
-    pmax2 = fmax(pmax2, px * px + py * py);
-    const double dx = J * gx[i], dy = J * gy[i];
-    dmax2 = fmax(dmax2, dx * dx + dy * dy);
-  }
+  const bool mine = lane < N;
+  const int i = mine ? lane : 0;
+  const double mi = sh.m[i], vx = sh.vx[i], vy = sh.vy[i], gx = sh.gx[i], gy = sh.gy[i];
+  const double px = mi * vx, py = mi * vy;
+  const double jx = J * gx, jy = J * gy;
+  const double pmax2 = grp_max<LPS>(mine ? px * px + py * py : 0.0);
+  const double dmax2 = grp_max<LPS>(mine ? jx * jx + jy * jy : 0.0);
   const double p_scale = fmax(sqrt(pmax2), 1.0e-12);
   const double dp_inf = sqrt(dmax2);
   const double thr = P.jcap * p_scale;
   const double Ja = (dp_inf > thr && dp_inf > 0.0) ? J * (thr / dp_inf) : J;
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    s.vx[i] = (s.m[i] * s.vx[i] + Ja * gx[i]) / s.m[i];
-    s.vy[i] = (s.m[i] * s.vy[i] + Ja * gy[i]) / s.m[i];
+  if (act && mine) {
+    sh.vx[i] = (mi * vx + Ja * gx) / mi;
+    sh.vy[i] = (mi * vy + Ja * gy) / mi;
   }
-  s.eps = eps_rot;
-  s.pi = eta_t + kick2;
-  hs_fold(s.eps, s.pi, P);                       // hamsoft_stepper.py:72-80
+  double pi_out = eta_t + kick2;
+  hs_fold(eps_rot, pi_out, P);                   // hamsoft_stepper.py:72-80
+  if (act) { eps = eps_rot; pi = pi_out; }
 }
 
-// V half-kick: hamsoft_stepper.py:543-663 + pi_half_kick hamsoft_flows.py:1102-1132
+// V half-kick: hamsoft_stepper.py:543-663 + pi_half_kick hamsoft_flows.py:1102-1132; body i on lane i.  The pair factor
+// G m_lo m_hi rho^-3 is formed identically on both lanes of a pair, so Newton's third law holds to the bit.
 template <int N>
-__device__ __forceinline__ void hs_v_half(HsState<N>& s, const HsPar& P, double G, double h) {
+__device__ __forceinline__ void hs_v_half(HsSh<N>& sh, double eps, double& pi, double G, double h, int lane_full,
+                                          bool act) {
+  constexpr int LPS = HsLanes<N>::LPS;
+  const int lane = lane_full & (LPS - 1);
+  const HsPar& P = sh.P;
   const double hh = 0.5 * h;
-  const double e = s.eps, e2 = e * e;
-  double fx[N], fy[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i) { fx[i] = 0.0; fy[i] = 0.0; }
-  double s3 = 0.0;
+  const double e2 = eps * eps;
+  const bool mine = lane < N;
+  const int i = mine ? lane : 0;
+  __syncwarp();
+  const double xi = sh.x[i], yi = sh.y[i], mi = sh.m[i];
+  double fx = 0.0, fy = 0.0, s3 = 0.0;
   if (G != 0.0) {
 #pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int j = i + 1; j < N; ++j) {
-        const double dx = s.x[i] - s.x[j], dy = s.y[i] - s.y[j];
-        const double w = rsqrt_f64<true>(fma(dx, dx, fma(dy, dy, e2)));
-        const double w3 = w * w * w;
-        const double mm = G * s.m[i] * s.m[j] * w3;          // force magnitude factor
-        fx[i] -= mm * dx; fy[i] -= mm * dy;
-        fx[j] += mm * dx; fy[j] += mm * dy;
-        s3 += s.m[i] * s.m[j] * w3;
-      }
+    for (int j = 0; j < N; ++j) {
+      if (j == i) continue;
+      const double mj = sh.m[j];
+      const double dx = xi - sh.x[j], dy = yi - sh.y[j];
+      const double w = rsqrt_f64<true>(fma(dx, dx, fma(dy, dy, e2)));
+      const double w3 = w * w * w;
+      const double mlo = i < j ? mi : mj, mhi = i < j ? mj : mi;
+      const double mm = G * mlo * mhi * w3;
+      fx -= mm * dx;
+      fy -= mm * dy;
+      if (j > i) s3 += mlo * mhi * w3;
+    }
   }
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    s.vx[i] = (s.m[i] * s.vx[i] + hh * fx[i]) / s.m[i];
-    s.vy[i] = (s.m[i] * s.vy[i] + hh * fy[i]) / s.m[i];
+  if (act && mine) {
+    sh.vx[i] = (mi * sh.vx[i] + hh * fx) / mi;
+    sh.vy[i] = (mi * sh.vy[i] + hh * fy) / mi;
   }
-  const double dU = (e == 0.0 || G == 0.0) ? 0.0 : G * e * s3;
-  const double dB = (P.policy == 0) ? -hs_barrier_force(e, P) : 0.0;
-  s.pi = s.pi - (dU + dB) * hh;
+  const double s3t = grp_sum<LPS>(mine ? s3 : 0.0);
+  const double dU = (eps == 0.0 || G == 0.0) ? 0.0 : G * eps * s3t;
+  const double dB = (P.policy == 0) ? -hs_barrier_force(eps, P) : 0.0;
+  if (act) pi = pi - (dU + dB) * hh;
 }
 
 template <int N>
-__device__ __forceinline__ void hs_strang(HsState<N>& s, const HsPar& P, double G, double h, int lane) {
-  // S(h/2) V(h/2) T(h) V(h/2) S(h/2).  Written as a two-trip loop so that the S half-flow (the eps* model: by far the
-  // largest piece of code) is instantiated ONCE; the unrolled form made the kernel stall on instruction fetch
-  // (ncu: no_instruction 1.8 warps per issue slot at N = 3).
-  hs_fold(s.eps, s.pi, P);                       // hamsoft_stepper.py:261-264
-  if constexpr (N >= 8) {                        // N = 8 is register-bound: the rolled form spills more than it saves
-    hs_s_half<N>(s, P, h, lane);
-    hs_v_half<N>(s, P, G, h);
-#pragma unroll
-    for (int i = 0; i < N; ++i) { s.x[i] = fma(h, s.vx[i], s.x[i]); s.y[i] = fma(h, s.vy[i], s.y[i]); }
-    hs_v_half<N>(s, P, G, h);
-    hs_s_half<N>(s, P, h, lane);
-    hs_fold(s.eps, s.pi, P);
-    return;
+__device__ __forceinline__ void hs_t_drift(HsSh<N>& sh, double h, int lane_full, bool act) {
+  const int lane = lane_full & (HsLanes<N>::LPS - 1);
+  __syncwarp();
+  if (act && lane < N) {
+    sh.x[lane] = fma(h, sh.vx[lane], sh.x[lane]);
+    sh.y[lane] = fma(h, sh.vy[lane], sh.y[lane]);
   }
+}
+
+// S(h/2) V(h/2) T(h) V(h/2) S(h/2), hamsoft_stepper.py:247-308.  Written as a two-trip loop so that the S half-flow
+// (the eps* model: by far the largest piece of code) is instantiated ONCE.
+template <int N>
+__device__ __forceinline__ void hs_strang(HsSh<N>& sh, double& eps, double& pi, double G, double h, int lane, bool act,
+                                          int& sweeps) {
+  const HsPar& P = sh.P;
+  if (act) hs_fold(eps, pi, P);                  // hamsoft_stepper.py:261-264
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
-    hs_s_half<N>(s, P, h, lane);
+    hs_s_half<N>(sh, eps, pi, h, lane, act, sweeps);
     if (half == 0) {
-#pragma unroll 1
-      for (int kick = 0; kick < 2; ++kick) {
-        hs_v_half<N>(s, P, G, h);
-        if (kick == 0) {
-#pragma unroll
-          for (int i = 0; i < N; ++i) { s.x[i] = fma(h, s.vx[i], s.x[i]); s.y[i] = fma(h, s.vy[i], s.y[i]); }
-        }
-      }
+      hs_v_half<N>(sh, eps, pi, G, h, lane, act);
+      hs_t_drift<N>(sh, h, lane, act);
+      hs_v_half<N>(sh, eps, pi, G, h, lane, act);
     }
   }
-  hs_fold(s.eps, s.pi, P);                       // hamsoft_stepper.py:300-303
+  if (act) hs_fold(eps, pi, P);                  // hamsoft_stepper.py:300-303
 }
 
 // diagnostics.py:457-549: T + V (double-double, each rounded to fp64) + pi^2/2mu + k/2 (eps-eps*)^2 + S_bar
@@ -584,18 +704,23 @@ __device__ __noinline__ double hs_energy(const double* m, const double* x, const
   return Tf + Vf + K + Sp + hs_barrier_energy(eps, P);
 }
 
+// eps_target of the system in shared memory, serially on the calling lane (energy taps: twice per run)
+template <int N>
+__device__ __noinline__ double hs_eps_target_sh(const HsSh<N>* sh, double eps_cur) {
+  double x[N], y[N], m[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) { x[i] = sh->x[i]; y[i] = sh->y[i]; m[i] = sh->m[i]; }
+  const HsPar P = sh->P;
+  return hs_eps_target<N>(x, y, m, eps_cur, P);
+}
+
 // ---------------------------------------------------------------------------------------------
-// run kernel: one warp per system
+// run kernel: one group of LPS lanes per system
 // ---------------------------------------------------------------------------------------------
 struct HsArgs {
   const double* m; double* q; double* v; double G; int B; unsigned flags; double dt; int n_steps; int sample_interval;
-  int n_megno; const int32_t* n_sub; const double* raw_dr; const double* raw_dv; double* eps_pi; const double* hs;
-  double* dyn; int32_t* status;
-};
-
-struct Welford {
-  double mean, m2; int n;
-  __device__ __forceinline__ void add(double x) { ++n; const double d = x - mean; mean += d / n; m2 += d * (x - mean); }
+  int n_megno; const int32_t* n_sub; const int32_t* perm; const double* raw_dr; const double* raw_dv; double* eps_pi;
+  const double* hs; double* dyn; int32_t* status; double* work;
 };
 
 template <int N>
@@ -606,209 +731,244 @@ static inline int hs_run_blocks(int B) {
 }
 
 template <int N>
-__global__ void __launch_bounds__(128, (N <= 4 ? 4 : 2)) hamsoft_run_kernel(HsArgs a) {
+__device__ __forceinline__ void hs_load_system(HsSh<N>& sh, const double* m, const double* q, const double* v,
+                                               const double* hs, int sys, int lane) {
+  if (lane < N) {
+    sh.m[lane] = m[(size_t)sys * N + lane];
+    sh.x[lane] = q[((size_t)sys * N + lane) * 2 + 0];
+    sh.y[lane] = q[((size_t)sys * N + lane) * 2 + 1];
+    sh.vx[lane] = v ? v[((size_t)sys * N + lane) * 2 + 0] : 0.0;
+    sh.vy[lane] = v ? v[((size_t)sys * N + lane) * 2 + 1] : 0.0;
+    sh.gx[lane] = 0.0; sh.gy[lane] = 0.0; sh.h[lane] = 0.0;
+    sh.drx[lane] = 0.0; sh.dry[lane] = 0.0; sh.dvx[lane] = 0.0; sh.dvy[lane] = 0.0;
+  }
+  if (lane == 0) {
+    sh.P = hs_load(hs + (size_t)sys * NB_HS_NPARAM);
+#pragma unroll
+    for (int k = 0; k < HS_NACC; ++k) sh.acc[k] = 0.0;
+    sh.acc[HA_COM_MAX] = -1.0; sh.acc[HA_VAR_MAX] = -1.0; sh.acc[HA_COS_MIN] = 2.0;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    sh.acc[HA_E0] = qnan; sh.acc[HA_L0] = qnan; sh.acc[HA_E1] = qnan; sh.acc[HA_L1] = qnan;
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(128, (N <= 4 ? 4 : (N <= 6 ? 3 : 2))) hamsoft_run_kernel(HsArgs a) {
   constexpr int LPS = HsLanes<N>::LPS, SPW = 32 / LPS;   // lanes per system, systems per warp
-  const int lane = threadIdx.x & 31;
+  __shared__ HsSh<N> shs[4 * SPW];
+  const int lane_full = threadIdx.x & 31;
+  const int lane = lane_full & (LPS - 1);
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp * SPW >= a.B) return;                        // warp-uniform
-  // an odd tail slot shadows the warp's first system (same arithmetic, no writes) so the warp stays converged
-  const bool live = warp * SPW + lane / LPS < a.B;
-  const int sys = live ? warp * SPW + lane / LPS : warp * SPW;
-  HsState<N> s;
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    s.m[i] = a.m[(size_t)sys * N + i];
-    s.x[i] = a.q[((size_t)sys * N + i) * 2 + 0];
-    s.y[i] = a.q[((size_t)sys * N + i) * 2 + 1];
-    s.vx[i] = a.v[((size_t)sys * N + i) * 2 + 0];
-    s.vy[i] = a.v[((size_t)sys * N + i) * 2 + 1];
-  }
-  s.eps = a.eps_pi[2 * (size_t)sys];
-  s.pi = a.eps_pi[2 * (size_t)sys + 1];
-  HsPar P = hs_load(a.hs + (size_t)sys * NB_HS_NPARAM);
+  // an odd tail slot shadows the warp's first system (same arithmetic, no global writes) so the warp stays converged
+  const int slot = warp * SPW + lane_full / LPS;
+  const bool live = slot < a.B;
+  const int t = live ? slot : warp * SPW;
+  const int sys = a.perm ? a.perm[t] : t;               // n_sub-sorted: neighbours in a warp have equal sub-step counts
+  HsSh<N>& sh = shs[(threadIdx.x >> 5) * SPW + lane_full / LPS];
+  hs_load_system<N>(sh, a.m, a.q, a.v, a.hs, sys, lane);
+  double eps = a.eps_pi[2 * (size_t)sys];
+  double pi = a.eps_pi[2 * (size_t)sys + 1];
   const double G = a.G;
   const int n_sub = max(1, a.n_sub ? a.n_sub[sys] : 1);
   const int n_sub_warp = SPW > 1 ? __reduce_max_sync(0xffffffffu, n_sub) : n_sub;
   const double h = a.dt / (double)n_sub;
-  // one macro step = n_sub Strang sub-steps; systems sharing a warp run to the larger count and discard the excess
-  auto macro_step = [&]() {
-#pragma unroll 1
-    for (int k = 0; k < n_sub_warp; ++k) {
-      if (SPW > 1) {
-        HsState<N> t = s;
-        hs_strang<N>(t, P, G, h, lane);
-        if (k < n_sub) s = t;
-      } else {
-        hs_strang<N>(s, P, G, h, lane);
-      }
-    }
-  };
+  const double dt = a.dt;
+  __syncwarp();
   // hamiltonian_softening_integrator.py:232-242: mu is raised to k (dt/theta_imp)^2 on the first step
-  if (a.n_steps + a.n_megno > 0 && is_finite(P.k) && P.k > 0.0) {
-    const double mu_macro = P.k * (fabs(a.dt) / P.theta_imp) * (fabs(a.dt) / P.theta_imp);
-    if (P.mu < mu_macro) P.mu = mu_macro;
+  if (lane == 0 && a.n_steps + a.n_megno > 0 && is_finite(sh.P.k) && sh.P.k > 0.0) {
+    const double mu_macro = sh.P.k * (fabs(dt) / sh.P.theta_imp) * (fabs(dt) / sh.P.theta_imp);
+    if (sh.P.mu < mu_macro) sh.P.mu = mu_macro;
   }
+  __syncwarp();
   const bool want_energy = (a.flags & NB_RUN_ENERGY) != 0;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
-
-  auto energy = [&](double& E, double& L) {
-    double cx[N], cy[N], cu[N], cw[N], cm[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) { cx[i] = s.x[i]; cy[i] = s.y[i]; cu[i] = s.vx[i]; cw[i] = s.vy[i]; cm[i] = s.m[i]; }
-    const double es = hs_eps_target<N>(cx, cy, cm, s.eps, P);
-    E = hs_energy<N>(cm, cx, cy, cu, cw, s.eps, s.pi, is_finite(es) ? es : P.s0, P, G);
-    L = 0.0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) L += s.m[i] * (s.x[i] * s.vy[i] - s.y[i] * s.vx[i]);
-  };
-  double E0 = nan, L0 = nan, E1 = nan, L1 = nan;
-
-  double com_sum = 0.0, com_max = -1.0, var_sum = 0.0, var_max = -1.0, cos_sum = 0.0, cos_min = 2.0;
-  Welford wj{0.0, 0.0, 0}, wt{0.0, 0.0, 0};
-  double Lfirst = 0.0;
-  bool have_first = false, cos_nan = false, th_nan = false;
-  int n_samp = 0, next_sample = 0;
+  int sweeps = 0, next_sample = 0;
   // MEGNO (evolution_features.py:34-66); the tangent map uses the post-step epsilon^2 (softening_manager.py:359-366)
-  double megno = 2.0, lyap = inf, t_end = 0.0;
-  double drx[N], dry[N], dvx[N], dvy[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i) { drx[i] = 0.0; dry[i] = 0.0; dvx[i] = 0.0; dvy[i] = 0.0; }
   double tt = 0.0, accum = 0.0;
-  const double dt = a.dt;
   const int n_total = a.n_steps + a.n_megno;
-  // ONE loop over the main steps and the MEGNO steps, so that the macro step (and the energy evaluation) is
-  // instantiated once: step < n_steps samples step_metrics, step >= n_steps advances the tangent vectors
+  const bool mine = lane < N;
+  const int bi = mine ? lane : 0;
+  // ONE loop over the main steps and the MEGNO steps, so that the macro step is instantiated once:
+  // step < n_steps samples step_metrics, step >= n_steps advances the tangent vectors
+#pragma unroll 1
   for (int step = 0; step <= n_total; ++step) {
     if (want_energy && (step == 0 || step == a.n_steps)) {
-      double E, Lz;
-      energy(E, Lz);
-      if (step == 0) { E0 = E; L0 = Lz; }
-      if (step == a.n_steps) { E1 = E; L1 = Lz; }
+      __syncwarp();
+      const double es = hs_eps_target_sh<N>(&sh, eps);
+      const double E = hs_energy<N>(sh.m, sh.x, sh.y, sh.vx, sh.vy, eps, pi, is_finite(es) ? es : sh.P.s0, sh.P, G);
+      double Lz = 0.0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) Lz += sh.m[i] * (sh.x[i] * sh.vy[i] - sh.y[i] * sh.vx[i]);
+      if (lane == 0) {
+        if (step == 0) { sh.acc[HA_E0] = E; sh.acc[HA_L0] = Lz; }
+        if (step == a.n_steps) { sh.acc[HA_E1] = E; sh.acc[HA_L1] = Lz; }
+      }
     }
     if (step == a.n_steps && a.n_megno > 0) {
-      double M = 0.0, cx = 0.0, cy = 0.0, ux = 0.0, uy = 0.0;
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        drx[i] = a.raw_dr[((size_t)sys * N + i) * 2 + 0]; dry[i] = a.raw_dr[((size_t)sys * N + i) * 2 + 1];
-        dvx[i] = a.raw_dv[((size_t)sys * N + i) * 2 + 0]; dvy[i] = a.raw_dv[((size_t)sys * N + i) * 2 + 1];
-        M += s.m[i];
-        cx += s.m[i] * drx[i]; cy += s.m[i] * dry[i]; ux += s.m[i] * dvx[i]; uy += s.m[i] * dvy[i];
+      __syncwarp();
+      if (lane == 0) {
+        double M = 0.0, cx = 0.0, cy = 0.0, ux = 0.0, uy = 0.0;
+        for (int i = 0; i < N; ++i) {
+          const double rx = a.raw_dr[((size_t)sys * N + i) * 2 + 0], ry = a.raw_dr[((size_t)sys * N + i) * 2 + 1];
+          const double wx = a.raw_dv[((size_t)sys * N + i) * 2 + 0], wy = a.raw_dv[((size_t)sys * N + i) * 2 + 1];
+          sh.drx[i] = rx; sh.dry[i] = ry; sh.dvx[i] = wx; sh.dvy[i] = wy;
+          M += sh.m[i];
+          cx += sh.m[i] * rx; cy += sh.m[i] * ry; ux += sh.m[i] * wx; uy += sh.m[i] * wy;
+        }
+        cx /= M; cy /= M; ux /= M; uy /= M;
+        double nr = 0.0, nv = 0.0;
+        for (int i = 0; i < N; ++i) {
+          sh.drx[i] -= cx; sh.dry[i] -= cy; sh.dvx[i] -= ux; sh.dvy[i] -= uy;
+          nr += sh.drx[i] * sh.drx[i] + sh.dry[i] * sh.dry[i]; nv += sh.dvx[i] * sh.dvx[i] + sh.dvy[i] * sh.dvy[i];
+        }
+        nr = sqrt(nr); nv = sqrt(nv);
+        for (int i = 0; i < N; ++i) { sh.drx[i] /= nr; sh.dry[i] /= nr; sh.dvx[i] /= nv; sh.dvy[i] /= nv; }
       }
-      cx /= M; cy /= M; ux /= M; uy /= M;
-      double nr = 0.0, nv = 0.0;
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        drx[i] -= cx; dry[i] -= cy; dvx[i] -= ux; dvy[i] -= uy;
-        nr += drx[i] * drx[i] + dry[i] * dry[i]; nv += dvx[i] * dvx[i] + dvy[i] * dvy[i];
-      }
-      nr = sqrt(nr); nv = sqrt(nv);
-#pragma unroll
-      for (int i = 0; i < N; ++i) { drx[i] /= nr; dry[i] /= nr; dvx[i] /= nv; dvy[i] /= nv; }
+      __syncwarp();
     }
     if (step == n_total) break;
-    macro_step();
+    // one macro step = n_sub Strang sub-steps; systems sharing a warp run to the larger count, excess predicated off
+#pragma unroll 1
+    for (int k = 0; k < n_sub_warp; ++k) hs_strang<N>(sh, eps, pi, G, h, lane_full, k < n_sub, sweeps);
+    __syncwarp();
     if (step < a.n_steps) {
       if (a.sample_interval > 0 && step == next_sample) {   // diagnostics.py:241-285
         next_sample += a.sample_interval;
-        double cx = 0.0, cy = 0.0, Lt = 0.0, Li[N];
+        if (lane == 0) {
+          double* A = sh.acc;
+          double cx = 0.0, cy = 0.0, Lt = 0.0, Li[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          cx += s.m[i] * s.x[i]; cy += s.m[i] * s.y[i];
-          Li[i] = s.m[i] * (s.x[i] * s.vy[i] - s.y[i] * s.vx[i]);
-          Lt += Li[i];
+          for (int i = 0; i < N; ++i) {
+            cx += sh.m[i] * sh.x[i]; cy += sh.m[i] * sh.y[i];
+            Li[i] = sh.m[i] * (sh.x[i] * sh.vy[i] - sh.y[i] * sh.vx[i]);
+            Lt += Li[i];
+          }
+          const double mean = Lt / N;
+          double var = 0.0;
+#pragma unroll
+          for (int i = 0; i < N; ++i) var += (Li[i] - mean) * (Li[i] - mean);
+          var /= N;
+          const double com = sqrt(cx * cx + cy * cy);
+          if (A[HA_HAVE_FIRST] == 0.0) { A[HA_LFIRST] = Lt; A[HA_HAVE_FIRST] = 1.0; }
+          const double Lfirst = A[HA_LFIRST];
+          double c;
+          if (Lfirst != 0.0 && Lt != 0.0) c = (Lt * Lfirst) / (fabs(Lt) * fabs(Lfirst));
+          else { c = 0.0; A[HA_COS_NAN] = 1.0; }
+          A[HA_COM_SUM] += com; A[HA_COM_MAX] = fmax(A[HA_COM_MAX], com);
+          A[HA_VAR_SUM] += var; A[HA_VAR_MAX] = fmax(A[HA_VAR_MAX], var);
+          A[HA_COS_SUM] += c; A[HA_COS_MIN] = fmin(A[HA_COS_MIN], c);
+          const double mu = sh.P.mu;
+          {
+            const double xj = eps * pi / mu;
+            const double n = (A[HA_WJ_N] += 1.0);
+            const double d = xj - A[HA_WJ_MEAN];
+            A[HA_WJ_MEAN] += d / n;
+            A[HA_WJ_M2] += d * (xj - A[HA_WJ_MEAN]);
+          }
+          if (mu * eps != 0.0 || pi != 0.0) {
+            const double xt = atan2(pi, mu * eps);
+            const double n = (A[HA_WT_N] += 1.0);
+            const double d = xt - A[HA_WT_MEAN];
+            A[HA_WT_MEAN] += d / n;
+            A[HA_WT_M2] += d * (xt - A[HA_WT_MEAN]);
+          } else {
+            A[HA_TH_NAN] = 1.0;
+          }
+          A[HA_NSAMP] += 1.0;
         }
-        const double mean = Lt / N;
-        double var = 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) var += (Li[i] - mean) * (Li[i] - mean);
-        var /= N;
-        const double com = sqrt(cx * cx + cy * cy);
-        if (!have_first) { Lfirst = Lt; have_first = true; }
-        double c;
-        if (Lfirst != 0.0 && Lt != 0.0) c = (Lt * Lfirst) / (fabs(Lt) * fabs(Lfirst));
-        else { c = 0.0; cos_nan = true; }
-        com_sum += com; com_max = fmax(com_max, com);
-        var_sum += var; var_max = fmax(var_max, var);
-        cos_sum += c; cos_min = fmin(cos_min, c);
-        wj.add(s.eps * s.pi / P.mu);
-        if (P.mu * s.eps != 0.0 || s.pi != 0.0) wt.add(atan2(s.pi, P.mu * s.eps));
-        else th_nan = true;
-        ++n_samp;
       }
     } else {
-      SysState<N> t;
-      double dax[N], day[N];
+      // tangent map, body i on lane i: dr += dv dt; dv += da(dr) dt  (tangent_map.py:21-59 at the post-step epsilon)
+      double drx = sh.drx[bi], dry = sh.dry[bi];
+      drx = fma(sh.dvx[bi], dt, drx); dry = fma(sh.dvy[bi], dt, dry);
+      __syncwarp();
+      if (mine) { sh.drx[bi] = drx; sh.dry[bi] = dry; }
+      __syncwarp();
+      const double xi = sh.x[bi], yi = sh.y[bi], e2 = eps * eps;
+      double dax = 0.0, day = 0.0;
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-        drx[i] = fma(dvx[i], dt, drx[i]); dry[i] = fma(dvy[i], dt, dry[i]);
-        t.gm[i] = G * s.m[i]; t.x[i] = s.x[i]; t.y[i] = s.y[i];
+      for (int j = 0; j < N; ++j) {
+        if (j == bi) continue;
+        const double dx = xi - sh.x[j], dy = yi - sh.y[j];
+        const double w = rsqrt_f64<true>(fma(dx, dx, fma(dy, dy, e2)));
+        const double w2 = w * w, w3 = w2 * w;
+        const double ex = sh.drx[j] - drx, ey = sh.dry[j] - dry;
+        const double dot = -fma(dx, ex, dy * ey);
+        const double c5 = 3.0 * dot * w2 * w3;
+        const double gmj = G * sh.m[j];
+        dax = fma(gmj, fma(ex, w3, c5 * dx), dax);
+        day = fma(gmj, fma(ey, w3, c5 * dy), day);
       }
-      t.eps2 = s.eps * s.eps;
-      pair_pass<N, true, true>(t, drx, dry, dax, day);
-      double nr = 0.0, nv = 0.0;
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        dvx[i] = fma(dax[i], dt, dvx[i]); dvy[i] = fma(day[i], dt, dvy[i]);
-        nr += drx[i] * drx[i] + dry[i] * dry[i];
-      }
+      double dvx = fma(dax, dt, sh.dvx[bi]), dvy = fma(day, dt, sh.dvy[bi]);
+      double nr = sqrt(grp_sum<LPS>(mine ? drx * drx + dry * dry : 0.0));
       tt += dt;
-      nr = sqrt(nr);
       if (nr < 1e-12) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) { drx[i] /= nr; dry[i] /= nr; dvx[i] /= nr; dvy[i] /= nr; }
+        drx /= nr; dry /= nr; dvx /= nr; dvy /= nr;
         nr = 1.0;
       }
-#pragma unroll
-      for (int i = 0; i < N; ++i) nv += dvx[i] * dvx[i] + dvy[i] * dvy[i];
-      accum += (sqrt(nv) / nr) * tt * dt;
+      const double nv = sqrt(grp_sum<LPS>(mine ? dvx * dvx + dvy * dvy : 0.0));
+      __syncwarp();
+      if (mine) { sh.drx[bi] = drx; sh.dry[bi] = dry; sh.dvx[bi] = dvx; sh.dvy[bi] = dvy; }
+      accum += (nv / nr) * tt * dt;
     }
   }
+  double megno = 2.0, lyap = inf, t_end = 0.0;
   if (a.n_megno > 0) {
     megno = 2.0 * accum / tt;
     lyap = (megno == 0.0) ? inf : tt / fabs(megno);
     t_end = tt;
   }
-
-  if ((lane & (LPS - 1)) != 0 || !live) return;
-  bool finite = is_finite(s.eps) && is_finite(s.pi);
+  const double sweeps_tot = grp_sum<LPS>((double)sweeps);
+  __syncwarp();
+  if (lane != 0 || !live) return;
+  bool finite = is_finite(eps) && is_finite(pi);
 #pragma unroll
   for (int i = 0; i < N; ++i)
-    finite = finite && is_finite(s.x[i]) && is_finite(s.y[i]) && is_finite(s.vx[i]) && is_finite(s.vy[i]);
+    finite = finite && is_finite(sh.x[i]) && is_finite(sh.y[i]) && is_finite(sh.vx[i]) && is_finite(sh.vy[i]);
   int st = finite ? 0 : NB_STATUS_NONFINITE;
   {
-    const double R = P.eps_max - P.eps_min;
-    if (finite && (s.eps < P.eps_min - R || s.eps > P.eps_max + R)) st |= NB_STATUS_EPS_OOB;
+    const double R = sh.P.eps_max - sh.P.eps_min;
+    if (finite && (eps < sh.P.eps_min - R || eps > sh.P.eps_max + R)) st |= NB_STATUS_EPS_OOB;
   }
   if (a.status) a.status[sys] = st;
+  if (a.work) {   // counted work for the roofline: Jacobi sweeps summed over all finite-difference evaluations
+    a.work[2 * (size_t)sys] = sweeps_tot;
+    a.work[2 * (size_t)sys + 1] = 2.0 * (double)n_sub * (double)n_total;   // S half-flows
+  }
   if (a.flags & NB_RUN_WRITE_STATE) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      a.q[((size_t)sys * N + i) * 2 + 0] = s.x[i]; a.q[((size_t)sys * N + i) * 2 + 1] = s.y[i];
-      a.v[((size_t)sys * N + i) * 2 + 0] = s.vx[i]; a.v[((size_t)sys * N + i) * 2 + 1] = s.vy[i];
+      a.q[((size_t)sys * N + i) * 2 + 0] = sh.x[i]; a.q[((size_t)sys * N + i) * 2 + 1] = sh.y[i];
+      a.v[((size_t)sys * N + i) * 2 + 0] = sh.vx[i]; a.v[((size_t)sys * N + i) * 2 + 1] = sh.vy[i];
     }
-    a.eps_pi[2 * (size_t)sys] = s.eps;
-    a.eps_pi[2 * (size_t)sys + 1] = s.pi;
+    a.eps_pi[2 * (size_t)sys] = eps;
+    a.eps_pi[2 * (size_t)sys + 1] = pi;
   }
   if (a.dyn) {
     double* f = a.dyn + (size_t)sys * NB_N_DYN;
+    const double* A = sh.acc;
     auto drift_of = [&](double a0, double a1) {
       if (is_finite(a0) && fabs(a0) > 0.0 && is_finite(a1)) return fabs((a1 - a0) / a0);
       if (is_finite(a0) && is_finite(a1)) return fabs(a1 - a0);
       return inf;
     };
+    const int n_samp = (int)A[HA_NSAMP];
+    const double E0 = A[HA_E0], L0 = A[HA_L0], E1 = A[HA_E1], L1 = A[HA_L1];
+    const bool th_nan = A[HA_TH_NAN] != 0.0, cos_nan = A[HA_COS_NAN] != 0.0;
     const double ed = want_energy ? drift_of(E0, E1) : nan, ld = want_energy ? drift_of(L0, L1) : nan;
     const double inv = n_samp > 0 ? 1.0 / (double)n_samp : nan;
-    const double com_mean = n_samp > 0 ? com_sum * inv : nan;
+    const double com_mean = n_samp > 0 ? A[HA_COM_SUM] * inv : nan;
     f[NB_F_ENERGY_DRIFT] = ed; f[NB_F_ANGMOM_DRIFT] = ld;
-    f[NB_F_COM_MEAN] = com_mean; f[NB_F_COM_MAX] = n_samp > 0 ? com_max : nan;
-    f[NB_F_JEPS_MEAN] = n_samp > 0 ? wj.mean : nan;
-    f[NB_F_JEPS_STD] = n_samp > 0 ? sqrt(wj.m2 / wj.n) : nan;
-    f[NB_F_THETA_MEAN] = (n_samp > 0 && !th_nan) ? wt.mean : nan;
-    f[NB_F_THETA_STD] = (n_samp > 0 && !th_nan) ? sqrt(wt.m2 / wt.n) : nan;
-    f[NB_F_COS_MEAN] = (n_samp > 0 && !cos_nan) ? cos_sum * inv : nan;
-    f[NB_F_COS_MIN] = (n_samp > 0 && !cos_nan) ? cos_min : nan;
-    f[NB_F_VARL_MEAN] = n_samp > 0 ? var_sum * inv : nan; f[NB_F_VARL_MAX] = n_samp > 0 ? var_max : nan;
+    f[NB_F_COM_MEAN] = com_mean; f[NB_F_COM_MAX] = n_samp > 0 ? A[HA_COM_MAX] : nan;
+    f[NB_F_JEPS_MEAN] = n_samp > 0 ? A[HA_WJ_MEAN] : nan;
+    f[NB_F_JEPS_STD] = n_samp > 0 ? sqrt(A[HA_WJ_M2] / A[HA_WJ_N]) : nan;
+    f[NB_F_THETA_MEAN] = (n_samp > 0 && !th_nan) ? A[HA_WT_MEAN] : nan;
+    f[NB_F_THETA_STD] = (n_samp > 0 && !th_nan) ? sqrt(A[HA_WT_M2] / A[HA_WT_N]) : nan;
+    f[NB_F_COS_MEAN] = (n_samp > 0 && !cos_nan) ? A[HA_COS_SUM] * inv : nan;
+    f[NB_F_COS_MIN] = (n_samp > 0 && !cos_nan) ? A[HA_COS_MIN] : nan;
+    f[NB_F_VARL_MEAN] = n_samp > 0 ? A[HA_VAR_SUM] * inv : nan; f[NB_F_VARL_MAX] = n_samp > 0 ? A[HA_VAR_MAX] : nan;
     f[NB_F_TIDAL_MEAN] = n_samp > 0 ? 0.0 : nan; f[NB_F_TIDAL_MAX] = n_samp > 0 ? 0.0 : nan;
     f[NB_F_MEGNO] = megno; f[NB_F_LYAP_TIME] = lyap;
     f[NB_F_IS_STABLE] = ((ed < 0.01) && (ld < 0.01) && (com_mean < 1.0) && (megno < 10.0)) ? 1.0 : 0.0;
@@ -938,30 +1098,29 @@ __global__ void __launch_bounds__(64) hamsoft_setup_kernel(const double* m_, con
   }
 }
 
-// eps*(q), its gradient and H_ext for B systems (parity taps; one warp per system)
+// eps*(q), its gradient and H_ext for B systems (parity taps; one warp per system, same group code as the run kernel)
 template <int N>
 __global__ void __launch_bounds__(128) hamsoft_probe_kernel(const double* m_, const double* q_, const double* v_,
                                                             double G, int B, const double* eps_pi, const double* hs,
-                                                            double* out /*[B][2+2N]: eps*, H, grad*/) {
-  const int lane = threadIdx.x & 31;
+                                                            double* out /*[B][3+2N]: eps*, H, fallback, grad*/) {
+  constexpr int LPS = HsLanes<N>::LPS, SPW = 32 / LPS;
+  __shared__ HsSh<N> shs[4 * SPW];
+  const int lane_full = threadIdx.x & 31;
+  const int lane = lane_full & (LPS - 1);
   const int sys = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (sys >= B) return;
-  double m[N], x[N], y[N], vx[N], vy[N], gx[N], gy[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    m[i] = m_[(size_t)sys * N + i];
-    x[i] = q_[((size_t)sys * N + i) * 2 + 0]; y[i] = q_[((size_t)sys * N + i) * 2 + 1];
-    vx[i] = v_[((size_t)sys * N + i) * 2 + 0]; vy[i] = v_[((size_t)sys * N + i) * 2 + 1];
-  }
-  const HsPar P = hs_load(hs + (size_t)sys * NB_HS_NPARAM);
+  HsSh<N>& sh = shs[(threadIdx.x >> 5) * SPW + lane_full / LPS];   // with LPS = 16 both half warps take the same system
+  hs_load_system<N>(sh, m_, q_, v_, hs, sys, lane);
+  __syncwarp();
   const double eps = eps_pi[2 * (size_t)sys], pi = eps_pi[2 * (size_t)sys + 1];
   bool fb;
-  const double es = hs_eps_star_and_grad<N>(x, y, m, eps, P, lane, gx, gy, fb);
-  const double H = hs_energy<N>(m, x, y, vx, vy, eps, pi, es, P, G);
-  if (lane == 0) {
+  int sweeps = 0;
+  const double es = hs_eps_star_and_grad<N>(sh, eps, lane_full, fb, sweeps);
+  const double H = hs_energy<N>(sh.m, sh.x, sh.y, sh.vx, sh.vy, eps, pi, es, sh.P, G);
+  if (lane_full == 0) {
     double* o = out + (size_t)sys * (3 + 2 * N);
     o[0] = es; o[1] = H; o[2] = fb ? 1.0 : 0.0;
-    for (int i = 0; i < N; ++i) { o[3 + 2 * i] = gx[i]; o[4 + 2 * i] = gy[i]; }
+    for (int i = 0; i < N; ++i) { o[3 + 2 * i] = sh.gx[i]; o[4 + 2 * i] = sh.gy[i]; }
   }
 }
 
@@ -979,10 +1138,10 @@ __global__ void __launch_bounds__(128) hamsoft_probe_kernel(const double* m_, co
 
 int hamsoft_run(const double* m, double* q, double* v, double G, int B, int N, unsigned flags, double dt, int n_steps,
                 int sample_interval, int n_megno, const int32_t* n_sub, const int32_t* perm, const double* raw_dr,
-                const double* raw_dv, double* eps_pi, const double* hs, double* dyn, int32_t* status, cudaStream_t st) {
-  (void)perm;
-  HsArgs a{m, q, v, G, B, flags, dt, n_steps, sample_interval, n_megno, n_sub, raw_dr, raw_dv, eps_pi, hs, dyn, status};
-  const int blocks = (B + 3) / 4;
+                const double* raw_dv, double* eps_pi, const double* hs, double* dyn, int32_t* status, double* work,
+                cudaStream_t st) {
+  HsArgs a{m, q, v, G, B, flags, dt, n_steps, sample_interval, n_megno, n_sub, perm, raw_dr, raw_dv, eps_pi, hs, dyn,
+           status, work};
   NB_HS_DISPATCH(N, (hamsoft_run_kernel<NN><<<hs_run_blocks<NN>(a.B), 128, 0, st>>>(a)));
   NB_CUDA_CHECK(cudaGetLastError());
   return NB_OK;

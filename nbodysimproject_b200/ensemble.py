@@ -139,17 +139,20 @@ class DeviceBucket:
                                              L.stream_ptr()), "nb_sort_by_nsub")
 
     def run(self, dt, n_steps, sample_interval=0, n_megno=0, raw_dr=None, raw_dv=None, flags=0, want_dyn=True,
-            eps_pi=None, hs_params=None):
+            eps_pi=None, hs_params=None, work=None):
+        """`work` (optional float64 [B, 2] device tensor) receives the counted work of the run: whfast {Newton
+        iterations, Kepler solves}, ham_soft {Jacobi sweeps, S half-flows} (nb_ensemble_run_counted_f64)."""
         torch = self.torch
         dyn = torch.empty((self.B, L.N_DYN), dtype=torch.float64, device=self.device) if want_dyn else None
         rdr = _to_dev(raw_dr, torch.float64, self.device) if n_megno > 0 else None
         rdv = _to_dev(raw_dv, torch.float64, self.device) if n_megno > 0 else None
         with torch.cuda.device(self.device):
-            L.check(L.load().nb_ensemble_run_f64(
+            L.check(L.load().nb_ensemble_run_counted_f64(
                 L.ptr(self.m), L.ptr(self.q), L.ptr(self.v), L.ptr(self.eps), self.G, self.B, self.N, self.mode,
                 int(flags), float(dt), int(n_steps), int(sample_interval), int(n_megno), L.ptr(self.n_sub),
-                L.ptr(self.perm), L.ptr(self._bins[64:]) if self.perm is not None else None, L.ptr(rdr), L.ptr(rdv), L.ptr(eps_pi), L.ptr(hs_params), L.ptr(dyn),
-                L.ptr(self.status), L.stream_ptr()), "nb_ensemble_run_f64")
+                L.ptr(self.perm), L.ptr(self._bins[64:]) if self.perm is not None else None, L.ptr(rdr), L.ptr(rdv),
+                L.ptr(eps_pi), L.ptr(hs_params), L.ptr(dyn), L.ptr(self.status), L.ptr(work), L.stream_ptr()),
+                "nb_ensemble_run_counted_f64")
         return dyn
 
 

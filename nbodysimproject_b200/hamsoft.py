@@ -73,10 +73,16 @@ class HamSoftBucket:
         mu = self.hs[:, P["mu_soft"]]
         self.hs[:, P["mu_soft"]] = self.torch.where((k > 0) & (mu < mu_macro), mu_macro, mu)
 
+    def sort(self):
+        """n_sub-sorted launch order: systems that share a warp (N <= 4) then have equal sub-step counts almost always
+        (a warp runs to the larger count of its two systems).  Results do not depend on it."""
+        self.bk.n_sub = self.n_sub
+        self.bk.sort()
+
     def run(self, dt, n_steps, sample_interval=0, n_megno=0, raw_dr=None, raw_dv=None, flags=L.RUN_WRITE_STATE,
-            want_dyn=False):
+            want_dyn=False, work=None):
         dyn = self.bk.run(dt, n_steps, sample_interval, n_megno, raw_dr, raw_dv, flags, want_dyn,
-                          eps_pi=self.eps_pi, hs_params=self.hs)
+                          eps_pi=self.eps_pi, hs_params=self.hs, work=work)
         if n_steps + n_megno > 0:
             self.bump_mu(dt)
         return dyn
