@@ -164,56 +164,125 @@ def flops_main(N, n_sub_sum, n_steps):
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm (oracle port of the reference's Python path)
+# CPU arm: the reference's own Python path when a checkout is importable (baseline/_ref/minbody or $NBODY_REFERENCE;
+# the reference is pure Python, is not pip-installable and does not travel to the GPU box, so normally it is not),
+# else the NumPy oracle port (pinned against the reference's outputs by tests/test_oracle_golden.py).
 # ---------------------------------------------------------------------------------------------
 
+_REAL_REF = None
+
+
+def _real_reference():
+    """Import the unmodified reference package if one is present; returns the module or None."""
+    global _REAL_REF
+    if _REAL_REF is not None:
+        return _REAL_REF or None
+    _REAL_REF = False
+    cands = [os.path.join(ROOT, "baseline", "_ref")]
+    if os.environ.get("NBODY_REFERENCE"):
+        cands.insert(0, os.environ["NBODY_REFERENCE"])
+    for c in cands:
+        if os.path.isdir(os.path.join(c, "minbody")):
+            import types
+            sys.dont_write_bytecode = True
+            sys.modules.setdefault("lightgbm", types.ModuleType("lightgbm"))   # minbody/__init__.py imports its trainer
+            sys.path.insert(0, c)
+            try:
+                import minbody  # noqa: F401
+                _REAL_REF = minbody
+            except Exception:
+                sys.path.remove(c)
+            break
+    return _REAL_REF or None
+
+
 def _cpu_worker(job):
-    from oracle import nbody_oracle as O
     m, q, v, eps, rr, rv = job
+    ref = _real_reference()
+    if ref is not None:
+        # the reference's own path: batch_stability_analyzer.py:62-80 -> stability_analyzer.py:69-259
+        import contextlib
+        import io
+        from minbody.simulation import NBodySimulation
+        from minbody.batch_stability_analyzer import BatchStabilityAnalyzer
+        with contextlib.redirect_stdout(io.StringIO()):
+            sim = NBodySimulation(masses=list(m), positions=[tuple(x) for x in q], velocities=[tuple(x) for x in v],
+                                  softening=float(eps), integrator_mode=MODE)
+            BatchStabilityAnalyzer(n_steps=N_STEPS, dt=DT, mode="full").analyze_batch([sim], show_progress=False)
+        return STEPS_PER_SYSTEM
+    from oracle import nbody_oracle as O
     sim = O.OracleSim(m, q, v, softening=float(eps), integrator_mode=MODE)
     O.run_stability_analysis(sim, N_STEPS, DT, "full", rr, rv)
     return STEPS_PER_SYSTEM
 
 
+def cpu_kind():
+    return "reference" if _real_reference() is not None else "port"
+
+
 def cpu_sample_jobs(n_jobs: int, seed: int):
-    inp = make_inputs(max(64, n_jobs * 4), seed)
+    """A bounded sample WITH THE WORKLOAD'S OWN MIX: the first n_jobs systems of the same diverse generator (46 % of
+    them N = 3: hierarchical triples + a share of the random / polygon / close-encounter cohorts), shuffled so that
+    every worker sees the same mix."""
+    inp = make_inputs(n_jobs, seed)
     jobs = []
-    # round-robin over the N buckets so the sample has the workload's mix
-    keys = sorted(inp)
-    idx = {k: 0 for k in keys}
-    while len(jobs) < n_jobs:
-        for k in keys:
-            d = inp[k]
-            i = idx[k]
-            if i < d["m"].shape[0] and len(jobs) < n_jobs:
-                jobs.append((d["m"][i], d["q"][i], d["v"][i], d["eps"][i], d["raw_dr"][i], d["raw_dv"][i]))
-                idx[k] += 1
-    return jobs
+    for N in sorted(inp):
+        d = inp[N]
+        for i in range(d["m"].shape[0]):
+            jobs.append((d["m"][i], d["q"][i], d["v"][i], d["eps"][i], d["raw_dr"][i], d["raw_dv"][i]))
+    np.random.default_rng(seed).shuffle(jobs)
+    return jobs[:n_jobs]
 
 
-def run_cpu(n_jobs: int, cores: int, seed: int = 777):
-    import multiprocessing as mp
-    jobs = cpu_sample_jobs(n_jobs, seed)
-    t0 = time.perf_counter()
-    if cores > 1:
-        with mp.get_context("fork").Pool(cores) as pool:
-            done = sum(pool.map(_cpu_worker, jobs, chunksize=1))
-    else:
-        done = sum(_cpu_worker(j) for j in jobs)
-    dt = time.perf_counter() - t0
-    return done / dt, dt
+class CpuPool:
+    """Worker processes created ONCE, outside every timed interval."""
+
+    def __init__(self, cores: int):
+        import multiprocessing as mp
+        restore_affinity()
+        self.cores = cores
+        self.pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
+        if self.pool is not None:                      # start-up cost (fork + imports) is paid here
+            self.pool.map(_warm_worker, range(cores))
+
+    def run(self, fn, jobs):
+        t0 = time.perf_counter()
+        if self.pool is not None:
+            done = sum(self.pool.map(fn, jobs, chunksize=max(1, len(jobs) // (4 * self.cores))))
+        else:
+            done = sum(fn(j) for j in jobs)
+        dt = time.perf_counter() - t0
+        return done / dt, dt
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+
+
+def _warm_worker(_):
+    _real_reference()
+    from oracle import nbody_oracle, hamsoft_oracle  # noqa: F401
+    return 0
 
 
 def cpu_pairs_per_s(n: int = 4096, reps: int = 3):
-    """CPU baseline for the large-N metric: the oracle's dense gravitational_force (forces.py:63-75 restated) at the
-    largest N whose (N,N,2) fp64 temporaries fit comfortably; pairs/s on one core (the reference is single-threaded)."""
-    from oracle import nbody_oracle as O
+    """CPU baseline for the large-N metric: dense gravitational_force (forces.py:63-75; the reference's own function
+    when a checkout is importable, else the oracle restatement) at the largest N whose (N,N,2) fp64 temporaries fit
+    comfortably; pairs/s on one core (the reference is single-threaded)."""
     from nbodysimproject_b200.largen import make_disc
     m, q, _ = make_disc(n, seed=5)
-    O.accelerations(q, m, 1e-3, 1.0)
+    ref = _real_reference()
+    if ref is not None:
+        from minbody.forces import gravitational_force
+        fn = lambda: gravitational_force(q, m, eps=1e-3, G=1.0)
+    else:
+        from oracle import nbody_oracle as O
+        fn = lambda: O.accelerations(q, m, 1e-3, 1.0)
+    fn()
     t0 = time.perf_counter()
     for _ in range(reps):
-        O.accelerations(q, m, 1e-3, 1.0)
+        fn()
     dt = (time.perf_counter() - t0) / reps
     return float(n) * float(n) / dt, dt
 
@@ -233,8 +302,8 @@ def impl_reference_largen(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C5 large-N direct sum; CPU path bounded to N=4096 (dense (N,N,2) fp64 temporaries: "
                                "N=2^20 would need 17.6 TB), pairs/s is size-independent for N >= 256"},
-        "cpu_baseline": {"value": value, "unit": "pair-interactions/s", "cores": 1, "kind": "port",
-                         "sample": "oracle dense gravitational_force at N=4096, 3 calls per step"},
+        "cpu_baseline": {"value": value, "unit": "pair-interactions/s", "cores": 1, "kind": cpu_kind(),
+                         "sample": "dense gravitational_force at N=4096, 3 calls per step"},
         "e2e": {"value": value, "unit": "pair-interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
@@ -246,29 +315,36 @@ def impl_reference(args):
     if args.workload == "largen":
         return impl_reference_largen(args)
     cores = os.cpu_count() or 1
-    n_jobs = max(cores, 8) * 4
+    n_jobs = cores * 24                       # >= 24 systems per core and step: the per-process tail stays < 5 %
+    pool = CpuPool(cores)
     times, done = [], 0
     for it in range(args.warmup + args.steps):
-        rate, dt = run_cpu(n_jobs, cores, seed=1000 + it)
+        jobs = cpu_sample_jobs(n_jobs, seed=1000 + it)
+        rate, dt = pool.run(_cpu_worker, jobs)
         if it >= args.warmup:
             times.append(dt)
             done += n_jobs * STEPS_PER_SYSTEM
         if sum(times) > 150:          # keep the whole arm within a few minutes
             break
+    pool.close()
     total = sum(times)
     value = done / total
     k = len(times)
+    kind = cpu_kind()
     line = {
         "impl": "reference", "metric": "system-steps/s (N=3-8 ensembles, MEGNO on)", "value": value,
         "unit": "system-steps/s", "n_gpus": args.gpus, "steps": k, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / max(k, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C3 batch stability ensemble: diverse N=3-8 cohort, yoshida4, 1000+50 MEGNO steps, "
-                               "mode full (bounded CPU sample of the same generator)",
+                               "mode full (bounded CPU sample of the same generator, workload-weighted N mix)",
                    "systems_per_step": n_jobs, "integrator": MODE, "dt": DT},
-        "cpu_baseline": {"value": value, "unit": "system-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_jobs} systems x {STEPS_PER_SYSTEM} steps per bench step, NumPy oracle "
-                                   f"(oracle/nbody_oracle.py) in {cores} worker processes"},
+        "cpu_baseline": {"value": value, "unit": "system-steps/s", "cores": cores, "kind": kind,
+                         "sample": f"{n_jobs} systems x {STEPS_PER_SYSTEM} steps per bench step, "
+                                   + ("the reference's BatchStabilityAnalyzer.analyze_batch" if kind == "reference"
+                                      else "NumPy oracle (oracle/nbody_oracle.py; ~2x faster per core than the reference, "
+                                           "DESIGN.md section 5)")
+                                   + f" in {cores} worker processes created before the timed steps"},
         "e2e": {"value": value, "unit": "system-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -279,11 +355,40 @@ def impl_reference(args):
 # B200 arm
 # ---------------------------------------------------------------------------------------------
 
+NOMINAL_FP64 = 64 * 2 * 148 * 1.965e9 * 1e-12      # 64 DFMA/clk/SM x 148 SMs x 1.965 GHz = 37.2 TFLOP/s
+NOMINAL_FP32 = 128 * 2 * 148 * 1.965e9 * 1e-12     # 128 FFMA/clk/SM                      = 74.5 TFLOP/s
+
+
+def _traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this command
+    (profiles/r2_traffic.json, written by tools/ncu_traffic.py); None when no capture is on file."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            t = json.load(f)
+        return t.get(key)
+    except Exception:
+        return None
+
+
+def _barrier(torch, dist, world):
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+def _allmax(torch, dist, world, dev, *vals):
+    if world == 1:
+        return vals
+    tt = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return tuple(float(x) for x in tt)
+
+
 def impl_b200(args):
     import torch
     import torch.distributed as dist
     from nbodysimproject_b200 import _lib as L
-    from nbodysimproject_b200 import ensemble as E
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -295,25 +400,39 @@ def impl_b200(args):
     numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    lib = L.load()
+    L.load()
+    ctx = dict(torch=torch, dist=dist, world=world, rank=rank, local=local, dev=dev, numa=numa)
 
     if args.workload == "largen":
-        return bench_largen(args, torch, dist, world, rank, local, dev)
-    if args.workload == "c2":
-        bench_c2(args, torch, dist, world, rank, local, dev)
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    if args.workload in ("c4", "c1"):
-        bench_secondary(args, torch, dist, world, rank, local, dev)
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        line = largen_section(args, ctx, steps=args.steps, sampler=sampler, with_hamsoft=True, standalone=True)
+    elif args.workload == "c2":
+        line = bench_c2(args, torch, dist, world, rank, local, dev)
+    elif args.workload in ("c4", "c1"):
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        line = secondary_section(args, ctx, args.workload, steps=args.steps, sampler=sampler, standalone=True)
+    else:
+        line = ensemble_section(args, ctx)
+    if rank == 0 and line is not None:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
+
+def ensemble_section(args, ctx):
+    """Default line: C3 (the configuration BASELINE.json's metric is quoted on) + compact sections for the second half
+    of the metric (large N) and the other configs (C1 ham_soft, C4 whfast), + the cross-rank consistency checks."""
+    torch, dist, world, rank, local, dev = (ctx[k] for k in ("torch", "dist", "world", "rank", "local", "dev"))
+    from nbodysimproject_b200 import _lib as L
+    from nbodysimproject_b200 import ensemble as E
+    lib = L.load()
     B_total = args.systems
     inp = make_inputs(B_total, seed=42 + rank)
     Ns = sorted(inp, reverse=True)   # launch the large-N buckets first: their sequential sub-step tails are the longest
-    # pinned host buffers (e2e) and device-resident copies (value)
     host, devb = {}, {}
     h2d = d2h = 0
     for N in Ns:
@@ -338,14 +457,17 @@ def impl_b200(args):
         bk.rdv = hb["raw_dv"].to(dev)
         bk.stream = torch.cuda.Stream(device=dev)
         devb[N] = bk
+    del inp
     prep_flags = L.PREP_REMOVE_COM | L.PREP_CTOR_KICK | L.PREP_SNAPSHOT_KICK
     interval = max(1, N_STEPS // 100)
     launches_per_step = 0
+    main_events = []            # per timed step: {N: (begin, end)} recorded by the C ABI around the main-phase launches
 
-    def step_device():
+    def step_device(record=False):
         nonlocal launches_per_step
         cur = torch.cuda.current_stream()
         n = 0
+        evs = {}
         # the construction-time kernels of every bucket first (0.3 % of the step), then the runs: nb_ensemble_run_f64
         # launches each bucket's sub-step-heavy head at high priority, so no head waits behind another bucket's bulk
         for N in Ns:
@@ -359,11 +481,17 @@ def impl_b200(args):
         for N in Ns:
             bk = devb[N]
             with torch.cuda.stream(bk.stream):
-                bk.dyn = bk.run(DT, N_STEPS, interval, N_MEGNO, bk.rdr, bk.rdv, flags=L.RUN_ENERGY)  # 2+2+1+1 kernels
+                ev = None
+                if record:
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    evs[N] = ev
+                bk.dyn = bk.run(DT, N_STEPS, interval, N_MEGNO, bk.rdr, bk.rdv, flags=L.RUN_ENERGY, ev_main=ev)  # 2+2+1+1 kernels
                 n += 10
         for N in Ns:
             cur.wait_stream(devb[N].stream)
         launches_per_step = n
+        if record:
+            main_events.append(evs)
 
     def restore_e2e_inputs():
         # nb_ensemble_analyze_host* returns the kicked velocities in the caller's v (the reference mutates the caller's
@@ -389,33 +517,27 @@ def impl_b200(args):
             L.check(lib.nb_host_sync(slot), "nb_host_sync")
         return time.perf_counter() - t0
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
     # ---- value: device-resident
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):
         step_device()
-    barrier()
+    _barrier(torch, dist, world)
     mark0 = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        step_device()
+        step_device(record=True)
     e1.record()
-    barrier()
+    _barrier(torch, dist, world)
     mark1 = sampler.mark()
     t_dev = e0.elapsed_time(e1) * 1e-3
     # ---- e2e: host buffers through the C ABI
     for _ in range(max(1, min(args.warmup, 2))):
         restore_e2e_inputs()
         step_e2e()
-    barrier()
+    _barrier(torch, dist, world)
     t_e2e = 0.0
     for _ in range(args.steps):
         restore_e2e_inputs()
@@ -423,134 +545,256 @@ def impl_b200(args):
             dist.barrier()
         t_e2e += step_e2e()
     torch.cuda.synchronize()
-    barrier()
+    _barrier(torch, dist, world)
     clocks = sampler.stop(mark0, mark1) if rank == 0 else None
-    if world > 1:
-        tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e = float(tt[0]), float(tt[1])
+    t_dev, t_e2e = _allmax(torch, dist, world, dev, t_dev, t_e2e)
     sys_steps = float(B_total) * world * STEPS_PER_SYSTEM * args.steps
 
     # ---- cross-check: e2e and device paths give identical feature tables; count statuses
     same = all(np.array_equal(host[N]["dyn"].numpy(), devb[N].dyn.cpu().numpy(), equal_nan=True) for N in Ns)
     n_bad = int(sum(int((host[N]["status"].numpy() != 0).sum()) for N in Ns))
 
-    # ---- roofline of the dominant kernel family: ensemble_main_kernel<N, yoshida4>, N = 3..8.
-    # The six launches of a step run concurrently on their bucket streams (exactly as in the timed region), so
-    # the figure is: algorithmic flops of those launches / the CUDA-event time from the first launch to the last
-    # completion.  Per-bucket solo timings are reported too; they expose the sequential sub-step tail of the few
-    # n_sub ~ 50 systems, which the concurrent launch hides behind the bulk.
+    # ---- roofline of the dominant kernel family: ensemble_main_kernel<N, yoshida4>, N = 3..8, timed INSIDE the timed
+    # steps: the C ABI records a CUDA-event pair around each bucket's main-phase launches (head + rest); the six
+    # buckets run concurrently on their streams, so the figure per step is the algorithmic flops of the six launches
+    # over the window [first begin, last end].
     roof = None
     if rank == 0:
         peak = L.peak_flops(0, local)
-        per = []
-        tot_fl = 0.0
+        tot_fl, per = 0.0, []
         for N in Ns:
             bk = devb[N]
-            bk.q.copy_(bk.q0); bk.v.copy_(bk.v0)
-            bk.prepare(prep_flags, 0.01, 0.01, DT, 50)
-            bk.sort()
-            bk.vk = bk.v.clone()
-            nsub_sum = int(bk.n_sub.sum().item())
+            nsub_sum = int(bk.n_sub.sum().item())       # n_sub of the last timed step (deterministic in the inputs)
             bk.flops = flops_main(N, nsub_sum, N_STEPS)
             tot_fl += bk.flops
-            best = 1e30
-            for rep in range(2):
-                bk.q.copy_(bk.q0); bk.v.copy_(bk.vk)
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                bk.run(DT, N_STEPS, interval, 0, flags=0, want_dyn=False)
-                b.record()
-                torch.cuda.synchronize()
-                best = min(best, a.elapsed_time(b) * 1e-3)
+            solo = float(np.mean([ev[N][0].elapsed_time(ev[N][1]) for ev in main_events]))
             per.append(dict(N=N, B=bk.B, mean_n_sub=nsub_sum / bk.B, max_n_sub=int(bk.n_sub.max().item()),
-                            solo_ms=best * 1e3, solo_tflops=bk.flops / best * 1e-12))
-        best = 1e30
-        cur = torch.cuda.current_stream()
-        for rep in range(3):
-            for N in Ns:
-                devb[N].q.copy_(devb[N].q0); devb[N].v.copy_(devb[N].vk)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for N in Ns:
-                bk = devb[N]
-                bk.stream.wait_stream(cur)
-                with torch.cuda.stream(bk.stream):
-                    bk.run(DT, N_STEPS, interval, 0, flags=0, want_dyn=False)
-            for N in Ns:
-                cur.wait_stream(devb[N].stream)
-            b.record()
-            torch.cuda.synchronize()
-            best = min(best, a.elapsed_time(b) * 1e-3)
-        ach = tot_fl / best * 1e-12
+                            in_step_ms=solo, flops=bk.flops))
+        windows = []
+        for ev in main_events:
+            t_begin = min(e0.elapsed_time(ev[N][0]) for N in Ns)
+            t_end = max(e0.elapsed_time(ev[N][1]) for N in Ns)
+            windows.append(t_end - t_begin)
+        win = float(np.mean(windows)) * 1e-3
+        ach = tot_fl / win * 1e-12
         roof = {"bound": "fp64", "kernel": "ensemble_main_kernel<N=3..8, yoshida4> (6 concurrent launches per step)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of the six launches of one step (ncu, this workload at
-                # 2^20 systems per GPU: profiles/r1_main_kernels_dram.csv), scaled by the batch size
-                "traffic": 3.377e8 * (B_total / float(1 << 20)),
-                "traffic_note": "bytes per step over the six launches; the state is read once and lives in registers",
-                "flops_per_step": tot_fl, "ms": best * 1e3,
+                "frac_nominal": ach / NOMINAL_FP64, "peak_nominal": NOMINAL_FP64,
+                "traffic": _traffic("ensemble_main_six_launches_bytes_per_2p20_systems"),
+                "traffic_note": "dram bytes over the six launches of one step at 2^20 systems/GPU from the committed ncu "
+                                "capture (profiles/r2_traffic.json); the state is read once and lives in registers",
+                "flops_per_step": tot_fl, "ms": win * 1e3,
+                "timing": "CUDA events recorded by nb_ensemble_run_counted_f64 around the main-phase launches of every "
+                          "bucket inside the timed steps; window = first begin .. last end, mean over the timed steps",
                 "peak_source": "nb_peak_flops(0): register-resident DFMA micro-benchmark, same GPU, same run "
                                "(MEASURED_PEAKS.json has no FP64 figure; nominal 64 DFMA/clk/SM x 148 x 1.965 GHz = 37.2)",
                 "flop_model": "SURVEY.md 8d: per sub-step 3 x 14 N(N-1) + 36 N",
-                "share_of_step": best / (t_dev / args.steps), "per_bucket_solo": per}
+                "share_of_step": win / (t_dev / args.steps), "per_bucket": per}
 
-    # ---- second half of BASELINE.json's metric: pair-interactions/s of the large-N direct sum at N = 2^20
-    # (all ranks take part: i-blocks sharded, in-place NCCL all-gather of the packed positions per evaluation)
-    largen = None
+    # ---- N > 1: cross-rank correctness (the reference's contract: per-system results independent of batching,
+    # batch_stability_analyzer.py:62-80)
+    checks = {"e2e_equals_device_path": bool(same), "systems_with_nonzero_status": n_bad}
+    if world > 1:
+        checks.update(consistency_checks(ctx))
+
+    # free the C3 buffers before the secondary sections
+    for N in Ns:
+        devb[N] = None
+        host[N] = None
+    torch.cuda.empty_cache()
+
+    largen = c1 = c4 = None
     if not args.no_largen:
-        from nbodysimproject_b200 import largen as LN
-        n_ln = 1 << 20
-        mm, qq, vv = LN.make_disc(n_ln, seed=1)
-        lsim = LN.LargeNSimulation(mm, qq, vv, G=1.0, softening=1e-3, device=dev)
-        k_ln = 3
-        t_ln = LN.measure_force(lsim, k_ln, 3)
-        if rank == 0:
-            peak32 = L.peak_flops(1, local)
-            rate = float(n_ln) * n_ln * k_ln / t_ln
-            largen = {"metric": "pair-interactions/s at N=2^20", "value": rate, "unit": "pair-interactions/s",
-                      "n": n_ln, "ms_per_force_evaluation": 1e3 * t_ln / k_ln, "scaling": "strong", "dtype": "f32",
-                      "gpu_launches": 2 * k_ln,
-                      "roofline": {"bound": "fp32", "kernel": "largeN_accel_x2_kernel",
-                                   "achieved": 14.0 * rate * 1e-12 / world, "peak": peak32, "unit": "TFLOP/s",
-                                   "frac": 14.0 * rate * 1e-12 / world / peak32, "flops_per_pair": 14,
-                                   "peak_source": "nb_peak_flops(1): FFMA micro-benchmark, same GPU, same run"}}
-        del lsim
+        largen = largen_section(args, ctx, steps=3, sampler=None, with_hamsoft=not args.no_largen_hamsoft, standalone=False)
+    if not args.no_secondary:
+        c1 = secondary_section(args, ctx, "c1", steps=3, sampler=None, standalone=False)
+        c4 = secondary_section(args, ctx, "c4", steps=3, sampler=None, standalone=False)
 
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        restore_affinity()
         cores = os.cpu_count() or 1
-        n_jobs = max(cores, 8) * 96          # ~10-15 s of CPU work on the box's cores
-        rate, dt_cpu = run_cpu(n_jobs, cores)
-        cpu = {"value": rate, "unit": "system-steps/s", "cores": cores, "kind": "port",
-               "sample": f"{n_jobs} systems x {STEPS_PER_SYSTEM} steps of the same generator, NumPy oracle in "
-                         f"{cores} processes, {dt_cpu:.1f} s"}
+        n_jobs = cores * 96                  # ~10-15 s of CPU work on the box's cores
+        pool = CpuPool(cores)
+        rate, dt_cpu = pool.run(_cpu_worker, cpu_sample_jobs(n_jobs, 777))
+        pool.close()
+        kind = cpu_kind()
+        cpu = {"value": rate, "unit": "system-steps/s", "cores": cores, "kind": kind,
+               "sample": f"{n_jobs} systems x {STEPS_PER_SYSTEM} steps of the same generator (workload-weighted N mix), "
+                         + ("the reference's BatchStabilityAnalyzer" if kind == "reference" else "NumPy oracle")
+                         + f" in {cores} processes, {dt_cpu:.1f} s"}
+    if rank != 0:
+        return None
+    return {
+        "metric": "system-steps/s (N=3-8 ensembles, MEGNO on)", "value": sys_steps / t_dev,
+        "unit": "system-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3 batch stability ensemble (BASELINE.json configs[2]): diverse cohort "
+                               "40% random N=3-8 / 30% hierarchical triples / 20% polygons / 10% close encounters, "
+                               "yoshida4 dt=0.01, 1000 steps + 50 tangent-map MEGNO steps, mode full",
+                   "systems_per_gpu": B_total, "buckets": {str(p["N"]): int(p["B"]) for p in (roof or {}).get("per_bucket", [])},
+                   "sharding": "by system, no collective", "cpu_cores_bound_to_gpu_numa_node": ctx["numa"],
+                   "l2_note": f"inputs re-read from HBM each step ({h2d / 1e6:.0f} MB per GPU > 126 MB L2)"},
+        "e2e": {"value": sys_steps / t_e2e, "unit": "system-steps/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps,
+                "api": "nb_ensemble_analyze_host_async (C ABI, pinned host buffers)"},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "largen": largen, "c1": c1, "c4": c4,
+        "checks": checks,
+    }
 
-    if rank == 0:
-        line = {
-            "metric": "system-steps/s (N=3-8 ensembles, MEGNO on)", "value": sys_steps / t_dev,
-            "unit": "system-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C3 batch stability ensemble (BASELINE.json configs[2]): diverse cohort "
-                                   "40% random N=3-8 / 30% hierarchical triples / 20% polygons / 10% close encounters, "
-                                   "yoshida4 dt=0.01, 1000 steps + 50 tangent-map MEGNO steps, mode full",
-                       "systems_per_gpu": B_total, "buckets": {str(N): int(devb[N].B) for N in Ns},
-                       "sharding": "by system, no collective", "cpu_cores_bound_to_gpu_numa_node": numa, "l2_note": "inputs re-read from HBM each step "
-                       f"({h2d / 1e6:.0f} MB per GPU > 126 MB L2)"},
-            "e2e": {"value": sys_steps / t_e2e, "unit": "system-steps/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps,
-                    "api": "nb_ensemble_analyze_host_async (C ABI, pinned host buffers)"},
-            "gpu_launches": int(launches_per_step * args.steps),
-            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "largen": largen,
-            "checks": {"e2e_equals_device_path": bool(same), "systems_with_nonzero_status": n_bad},
-        }
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+
+def consistency_checks(ctx):
+    """world > 1, every rank: (a) the SAME 4,096-system ensemble analysed in full on every rank -> the feature tables must
+    be bit-identical across ranks; (b) the same ensemble sharded by system over the ranks and gathered -> must equal
+    rank 0's full table bit for bit (results independent of batching / GPU count); (c) ham_soft: eps, pi of the same
+    256 systems equal across ranks."""
+    torch, dist, world, rank, dev = (ctx[k] for k in ("torch", "dist", "world", "rank", "dev"))
+    from nbodysimproject_b200 import ensemble as E
+    from nbodysimproject_b200 import hamsoft as H
+    from nbodysimproject_b200 import sharding as S
+    inp = make_inputs(4096, seed=20261)
+    ident, sharded = True, True
+    for N in sorted(inp):
+        d = inp[N]
+        B = d["m"].shape[0]
+
+        def compute(lo, hi):
+            r = E.analyze_bucket(d["m"][lo:hi], d["q"][lo:hi], d["v"][lo:hi], d["eps"][lo:hi], 1.0, MODE, 200, DT,
+                                 "full", d["raw_dr"][lo:hi], d["raw_dv"][lo:hi], device=dev)
+            return np.concatenate([r.dyn, r.static], axis=1)
+
+        full = compute(0, B)
+        t = torch.from_numpy(full.view(np.int64).copy()).to(dev)
+        lo_t, hi_t = t.clone(), t.clone()
+        dist.all_reduce(lo_t, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_t, op=dist.ReduceOp.MAX)
+        ident &= bool(torch.equal(lo_t, hi_t))
+        gathered = S.analyze_sharded(compute, B)
+        if rank == 0:
+            sharded &= bool(np.array_equal(gathered, full, equal_nan=True))
+    # ham_soft
+    m, q, v = _c1_inputs(256, 5)
+    hs, s0 = H.default_params(object(), 1e-3, 1e-4, 256)
+    hb = H.HamSoftBucket(m, q, v, hs, np.stack([np.maximum(s0, hs[:, H.P["eps_min"]]), np.zeros(256)], 1), 1.0, dev)
+    hb.setup(calibrate=True, freeze_dt=0.01)
+    hb.run(0.01, 50)
+    t = hb.eps_pi.clone().view(torch.int64)
+    lo_t, hi_t = t.clone(), t.clone()
+    dist.all_reduce(lo_t, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi_t, op=dist.ReduceOp.MAX)
+    hs_ident = bool(torch.equal(lo_t, hi_t))
+    flag = torch.tensor([1 if sharded else 0], device=dev)
+    dist.broadcast(flag, 0)
+    return {"ranks_bit_identical": bool(ident), "sharded_equals_single_bit_identical": bool(int(flag[0]) == 1),
+            "hamsoft_eps_pi_identical_across_ranks": hs_ident,
+            "consistency_sample": "4096 systems (same generator, fixed seed), yoshida4, 200 + MEGNO steps, full feature tables"}
+
+
+# ---------------------------------------------------------------------------------------------
+# large-N direct sum (second half of BASELINE.json's metric)
+# ---------------------------------------------------------------------------------------------
+
+def largen_section(args, ctx, steps, sampler, with_hamsoft, standalone):
+    """pair-interactions/s of one force evaluation over all ordered pairs of an N-particle system (strong scaling: N
+    fixed, i-blocks sharded, one in-place position all-gather per evaluation); e2e with host positions in / host
+    accelerations out; fp64 spot check of 48 random particles; wall time of one full ham_soft Strang sub-step."""
+    torch, dist, world, rank, local, dev = (ctx[k] for k in ("torch", "dist", "world", "rank", "local", "dev"))
+    from nbodysimproject_b200 import _lib as L
+    from nbodysimproject_b200 import largen as LN
+    n = int(args.n)
+    m, q, v = LN.make_disc(n, seed=1)
+    sim = LN.LargeNSimulation(m, q, v, G=1.0, softening=1e-3, device=dev)
+    mark0 = sampler.mark() if sampler is not None else 0
+    t = LN.measure_force(sim, steps, args.warmup)
+    mark1 = sampler.mark() if sampler is not None else 0
+    # e2e: host positions in, host accelerations out, every step
+    xym_h = sim.xym.cpu().pin_memory()
+    acc_h = torch.empty((sim.ni, 2), dtype=torch.float32).pin_memory()
+    _barrier(torch, dist, world)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sim.xym.copy_(xym_h, non_blocking=True)
+        sim.accelerations()
+        acc_h.copy_(sim.acc, non_blocking=True)
+        torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    (t_e2e,) = _allmax(torch, dist, world, dev, t_e2e)
+    # fp64 direct sum for 48 random particles of THIS rank's i-block (forces.py:63-75 in fp64 on the device)
+    g = torch.Generator(device="cpu").manual_seed(7 + rank)
+    idx = (torch.randperm(sim.ni, generator=g)[:48] + sim.i0).to(dev)
+    x64 = sim.xym[:, 0:2].double()
+    m64 = sim.xym[:, 2].double()
+    d = x64[idx][:, None, :] - x64[None, :, :]
+    w = (d * d).sum(-1) + 1e-3 ** 2
+    w[torch.arange(48, device=dev), idx] = float("inf")
+    ref = -(m64[None, :, None] * d * (w ** -1.5)[:, :, None]).sum(1)
+    got = sim.acc[idx - sim.i0].double()
+    err = float(((got - ref).norm(dim=1) / ref.norm(dim=1)).max())
+    (err,) = _allmax(torch, dist, world, dev, err)
+    del d, w, x64
+    strang = None
+    if with_hamsoft:
+        n_hs = int(getattr(args, "n_hamsoft", 0) or n)            # C5 as BASELINE.json words it: the same N = 2^20 particles
+        mh, qh, vh = LN.make_disc(n_hs, seed=1)
+        hs = LN.LargeNHamSoftSimulation(mh, qh, vh, softening=2.0 / math.sqrt(n_hs), initial_dt=1e-3, device=dev)
+        hsub = 1e-3 / hs.frozen_n_sub
+        hs.strang_step(hsub)
+        _barrier(torch, dist, world)
+        p0, f0 = hs.n_passes, hs.force_evals
+        t0 = time.perf_counter()
+        hs.strang_step(hsub)
+        torch.cuda.synchronize()
+        ts = time.perf_counter() - t0
+        (ts,) = _allmax(torch, dist, world, dev, ts)
+        n_pass = (hs.n_passes - p0) + (hs.force_evals - f0)
+        # ranks must agree on the replicated scalars
+        sc = torch.tensor([hs.eps, hs.pi], dtype=torch.float64, device=dev).view(torch.int64)
+        same = True
+        if world > 1:
+            lo_t, hi_t = sc.clone(), sc.clone()
+            dist.all_reduce(lo_t, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi_t, op=dist.ReduceOp.MAX)
+            same = bool(torch.equal(lo_t, hi_t))
+        strang = {"n": n_hs, "ms": 1e3 * ts, "n2_passes": n_pass, "solver_sweeps": hs.last_sweeps,
+                  "pair_evaluations_per_s": n_pass * float(n_hs) * n_hs / ts, "frozen_n_sub": hs.frozen_n_sub,
+                  "eps": hs.eps, "pi": hs.pi, "eps_min": hs.eps_min, "eps_max": hs.eps_max,
+                  "eps_pi_identical_across_ranks": same}
+        del hs
+    if rank != 0:
+        return None
+    pairs = float(n) * float(n) * steps
+    peak32 = L.peak_flops(1, local)
+    ach = 14.0 * pairs / t * 1e-12 / world
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        restore_affinity()
+        rate, dtc = cpu_pairs_per_s(4096, 5)
+        cpu = {"value": rate, "unit": "pair-interactions/s", "cores": 1, "kind": cpu_kind(),
+               "sample": f"dense gravitational_force at N=4096 ({dtc * 1e3:.0f} ms per call; the (N,N,2) fp64 temporaries "
+                         "make N=2^20 impossible on the CPU path: 17.6 TB)"}
+    line = {
+        "metric": "pair-interactions/s at N=2^20", "value": pairs / t, "unit": "pair-interactions/s",
+        "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t / steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C5 single large-N direct sum, N={n}, Plummer softening 1e-3, one force evaluation "
+                               "(+ in-place NCCL position all-gather when sharded) per step",
+                   "l2_note": "j-array (16 B x N) is L2-resident by design; inputs are 16 MB at N=2^20"},
+        "e2e": {"value": pairs / t_e2e, "unit": "pair-interactions/s", "h2d_bytes_per_step": int(n * 16),
+                "d2h_bytes_per_step": int(sim.ni * 8), "ms_per_step": 1e3 * t_e2e / steps},
+        "gpu_launches": 2 * steps,
+        "roofline": {"bound": "fp32", "kernel": "largeN_accel_x2_kernel", "achieved": ach, "peak": peak32,
+                     "unit": "TFLOP/s", "frac": ach / peak32, "frac_nominal": ach / NOMINAL_FP32,
+                     "peak_nominal": NOMINAL_FP32, "traffic": _traffic("largeN_accel_bytes_per_launch_2p20"),
+                     "flops_per_pair": 14,
+                     "peak_source": "nb_peak_flops(1): register-resident FFMA micro-benchmark, same GPU, same run"},
+        "checks": {"max_rel_err_vs_fp64_direct_sum": err, "sample": "48 random particles per rank, max over ranks"},
+        "hamsoft_strang_substep": strang, "cpu_baseline": cpu,
+    }
+    if standalone:
+        line["clocks"] = sampler.stop(mark0, mark1) if sampler is not None else None
+    return line
 
 
 # ---------------------------------------------------------------------------------------------
@@ -580,43 +824,81 @@ def _c1_inputs(B, seed):
 
 
 def _cpu_c4(job):
-    from oracle import nbody_oracle as O
     m, q, v, n_steps, dt = job
-    sim = O.OracleSim(m, q, v, softening=0.0, integrator_mode="whfast")
+    if _real_reference() is not None:
+        from minbody.simulation import NBodySimulation
+        sim = NBodySimulation(masses=list(m), positions=[tuple(x) for x in q], velocities=[tuple(x) for x in v],
+                              softening=0.0, integrator_mode="whfast")
+    else:
+        from oracle import nbody_oracle as O
+        sim = O.OracleSim(m, q, v, softening=0.0, integrator_mode="whfast")
     for _ in range(n_steps):
         sim.step(dt)
     return n_steps
 
 
 def _cpu_c1(job):
-    from oracle.hamsoft_oracle import HamSoftOracleSim
     m, q, v, n_steps, dt = job
-    sim = HamSoftOracleSim(m, q, v, softening=1e-3)
+    if _real_reference() is not None:
+        from minbody.simulation import NBodySimulation
+        sim = NBodySimulation(masses=list(m), positions=[tuple(x) for x in q], velocities=[tuple(x) for x in v],
+                              softening=1e-3, integrator_mode="ham_soft")
+    else:
+        from oracle.hamsoft_oracle import HamSoftOracleSim
+        sim = HamSoftOracleSim(m, q, v, softening=1e-3)
     for _ in range(n_steps):
         sim.step(dt)
     return n_steps
 
 
-def _cpu_pool(fn, jobs, cores):
-    import multiprocessing as mp
-    restore_affinity()
+def _c1_api_single_system(n_steps=1000):
+    """BASELINE.json configs[0] exactly as worded: ONE NBodySimulation, `for _ in range(1000): sim.step(0.01)`
+    (simulation.py:667-676).  A single 3-body system cannot fill a GPU: every step() is one H2D + one kernel launch
+    of ONE warp + one D2H, so this number is launch-latency, reported beside the batched figure, not instead of it."""
+    import torch
+    from nbodysimproject_b200 import NBodySimulation
+
+    def make():
+        return NBodySimulation(masses=[1.0, 0.5, 0.1], positions=[(0.0, 0.0), (1.0, 0.0), (2.0, 0.0)],
+                               velocities=[(0.0, 0.0), (0.0, 1.0), (0.0, 0.5)], integrator_mode="ham_soft")
+    sim = make()
+    for _ in range(20):
+        sim.step(0.01)
+    sim = make()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(cores) as pool:
-        done = sum(pool.map(fn, jobs, chunksize=1))
-    dt = time.perf_counter() - t0
-    return done / dt, dt
+    for _ in range(n_steps):
+        sim.step(0.01)
+    torch.cuda.synchronize()
+    t_loop = time.perf_counter() - t0
+    q_loop = sim.pos.copy()
+    sim2 = make()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sim2.step_many(0.01, n_steps)
+    torch.cuda.synchronize()
+    t_many = time.perf_counter() - t0
+    return {"steps": n_steps, "step_loop_steps_per_s": n_steps / t_loop, "step_loop_s": t_loop,
+            "step_many_steps_per_s": n_steps / t_many, "step_many_s": t_many,
+            "step_many_equals_step_loop": bool(np.array_equal(q_loop, sim2.pos)),
+            "reference_cpu_steps_per_s_BASELINE_md": 189.0,
+            "note": "one NBodySimulation(...); for _ in range(1000): sim.step(0.01) -- launch-latency bound (one warp)"}
 
 
-def bench_secondary(args, torch, dist, world, rank, local, dev):
-    """--workload c4 | c1: system-steps/s of the whfast planetary ensemble / the batched README ham_soft system.
-    One bench step = n_steps integrator steps of every system in one persistent-kernel launch per bucket."""
+def secondary_section(args, ctx, which, steps, sampler, standalone):
+    """c4 | c1: system-steps/s of the whfast planetary ensemble / the batched README ham_soft system.
+    One bench step = n_steps integrator steps of every system in one persistent-kernel launch per bucket.
+    The roofline uses COUNTED work returned by the kernels (Newton iterations / Jacobi sweeps), SURVEY.md 8d."""
+    torch, dist, world, rank, local, dev = (ctx[k] for k in ("torch", "dist", "world", "rank", "local", "dev"))
     from nbodysimproject_b200 import _lib as L
     from nbodysimproject_b200 import ensemble as E
     from nbodysimproject_b200 import hamsoft as H
-    c4 = args.workload == "c4"
-    n_steps = 1000
+    c4 = which == "c4"
+    n_steps = int(args.horizon) if (standalone and args.horizon) else 1000
     dt = 0.01 * 2.0 * np.pi if c4 else 0.01
     B = args.systems if c4 else min(args.systems, 1 << 17)
+    if standalone and args.horizon and args.horizon > 1000 and args.systems == (1 << 20):
+        B = 1 << 16                                   # long horizons: 65,536 systems (SURVEY.md 8d C4 / VERDICT r1)
     runs = []
     if c4:
         inp = _c4_inputs(B, 42 + rank)
@@ -624,6 +906,7 @@ def bench_secondary(args, torch, dist, world, rank, local, dev):
             bk = E.DeviceBucket(m, q, v, eps, 1.0, "whfast", dev)
             bk.q0, bk.v0 = bk.q.clone(), bk.v.clone()
             bk.stream = torch.cuda.Stream(device=dev)
+            bk.work = torch.zeros((bk.B, 2), dtype=torch.float64, device=dev)
             runs.append(bk)
     else:
         m, q, v = _c1_inputs(B, 42 + rank)
@@ -631,50 +914,52 @@ def bench_secondary(args, torch, dist, world, rank, local, dev):
         ep = np.stack([np.maximum(s0, hs[:, H.P["eps_min"]]), np.zeros(B)], 1)
         hb = H.HamSoftBucket(m, q, v, hs, ep, 1.0, dev)
         hb.setup(calibrate=True, freeze_dt=dt)
+        hb.sort()
         hb.q0, hb.v0, hb.ep0, hb.hs0 = hb.bk.q.clone(), hb.bk.v.clone(), hb.eps_pi.clone(), hb.hs.clone()
+        hb.work = torch.zeros((B, 2), dtype=torch.float64, device=dev)
         runs.append(hb)
+    main_events = []
 
-    def step():
+    def step(record=False):
         cur = torch.cuda.current_stream()
+        evs = []
         if c4:
             for bk in runs:
                 bk.stream.wait_stream(cur)
                 with torch.cuda.stream(bk.stream):
                     bk.q.copy_(bk.q0); bk.v.copy_(bk.v0)
                     bk.prepare(L.PREP_REMOVE_COM | L.PREP_CTOR_KICK, dt, dt, dt, 50)
-                    bk.run(dt, n_steps, 0, 0, flags=L.RUN_WRITE_STATE, want_dyn=False)
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if record else None
+                    bk.run(dt, n_steps, 0, 0, flags=L.RUN_WRITE_STATE, want_dyn=False, work=bk.work, ev_main=ev)
+                    evs.append(ev)
             for bk in runs:
                 cur.wait_stream(bk.stream)
         else:
             hb = runs[0]
             hb.bk.q.copy_(hb.q0); hb.bk.v.copy_(hb.v0); hb.eps_pi.copy_(hb.ep0); hb.hs.copy_(hb.hs0)
-            hb.run(dt, n_steps)
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if record else None
+            hb.run(dt, n_steps, work=hb.work, ev_main=ev)
+            evs.append(ev)
+        if record:
+            main_events.append(evs)
 
-    for _ in range(args.warmup):
+    for _ in range(args.warmup if n_steps <= 1000 else 1):
         step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier(); torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    mark0 = sampler.mark()
+    _barrier(torch, dist, world)
+    mark0 = sampler.mark() if sampler is not None else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        step()
+    for _ in range(steps):
+        step(record=True)
     e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop(mark0, sampler.mark()) if rank == 0 else None
+    _barrier(torch, dist, world)
+    mark1 = sampler.mark() if sampler is not None else 0
     t_dev = e0.elapsed_time(e1) * 1e-3
     # e2e: pinned host state in, final host state out, every step
     host = []
     for r in runs:
         bk = r if c4 else r.bk
-        host.append((bk.q0.cpu().pin_memory() if c4 else r.q0.cpu().pin_memory(),
-                     bk.v0.cpu().pin_memory() if c4 else r.v0.cpu().pin_memory(),
+        host.append((r.q0.cpu().pin_memory(), r.v0.cpu().pin_memory(),
                      torch.empty(bk.q.shape, dtype=torch.float64).pin_memory(),
                      torch.empty(bk.v.shape, dtype=torch.float64).pin_memory()))
     h2d = sum(a.numel() * 8 + b.numel() * 8 for a, b, _, _ in host)
@@ -682,59 +967,94 @@ def bench_secondary(args, torch, dist, world, rank, local, dev):
 
     def step_e2e():
         for r, (q0h, v0h, qh, vh) in zip(runs, host):
-            if c4:
-                r.q0.copy_(q0h, non_blocking=True); r.v0.copy_(v0h, non_blocking=True)
-            else:
-                r.q0.copy_(q0h, non_blocking=True); r.v0.copy_(v0h, non_blocking=True)
+            r.q0.copy_(q0h, non_blocking=True); r.v0.copy_(v0h, non_blocking=True)
         step()
         for r, (q0h, v0h, qh, vh) in zip(runs, host):
             bk = r if c4 else r.bk
             qh.copy_(bk.q, non_blocking=True); vh.copy_(bk.v, non_blocking=True)
         torch.cuda.synchronize()
 
-    step_e2e()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    e2e_steps = steps if n_steps <= 1000 else 1
+    if n_steps <= 1000:
         step_e2e()
-    t_e2e = time.perf_counter() - t0
-    if world > 1:
-        tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e = float(tt[0]), float(tt[1])
-    n_bad = int(sum(int(((r if c4 else r.bk).status != 0).sum()) for r in runs))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    t_e2e = (time.perf_counter() - t0) * steps / e2e_steps
+    t_dev, t_e2e = _allmax(torch, dist, world, dev, t_dev, t_e2e)
+    stat_words = torch.cat([(r if c4 else r.bk).status for r in runs])
+    n_bad = int((stat_words != 0).sum())
+    n_nonfinite = int(((stat_words & 1) != 0).sum())
     if rank != 0:
-        return
-    sys_steps = float(B) * world * n_steps * args.steps
+        return None
+    # ---- roofline from counted work
+    peak = L.peak_flops(0, local)
+    win = float(np.mean([max(e0.elapsed_time(ev[1]) for ev in evs) - min(e0.elapsed_time(ev[0]) for ev in evs)
+                         for evs in main_events])) * 1e-3
+    if c4:
+        iters = sum(float(bk.work[:, 0].sum()) for bk in runs)
+        solves = sum(float(bk.work[:, 1].sum()) for bk in runs)
+        # SURVEY.md 8d "whfast": 14 N(N-1) per full-force kick + 2 (N-1) K, K = 60 flops x Newton iterations (measured)
+        fl = sum(float(bk.B) * n_steps * 14.0 * bk.N * (bk.N - 1) for bk in runs) + 60.0 * iters
+        counted = {"kepler_solves": solves, "mean_newton_iterations": iters / max(solves, 1.0),
+                   "flop_model": "SURVEY.md 8d: 14 N(N-1) + 60 x Newton iterations per Kepler solve, 2(N-1) solves per step"}
+        kernel = "ensemble_main_kernel<N=3..5, whfast> (3 concurrent launches per step)"
+    else:
+        hb = runs[0]
+        sweeps = float(hb.work[:, 0].sum())
+        halves = float(hb.work[:, 1].sum())
+        N = hb.bk.N
+        # SURVEY.md 8d "ham_soft sub-step": 2 x 17 N(N-1) + (8N+4) S, S = sweeps x N(N-1) x (12 flops + 1 exp)
+        fl = 0.5 * halves * 2 * 17.0 * N * (N - 1) + sweeps * N * (N - 1) * 13.0
+        counted = {"s_half_flows": halves, "mean_jacobi_sweeps_per_eps_star_evaluation": sweeps / max(halves * (4 * N + 1), 1.0),
+                   "flop_model": "SURVEY.md 8d: 2 x 17 N(N-1) per sub-step + 13 flops per pair and Jacobi sweep, "
+                                 "4N+1 eps* evaluations per S half-flow (exp counted as 1 flop)"}
+        kernel = "hamsoft_run_kernel<3>"
+    ach = fl / win * 1e-12
+    roof = {"bound": "fp64", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "frac_nominal": ach / NOMINAL_FP64, "peak_nominal": NOMINAL_FP64, "flops_per_step": fl, "ms": win * 1e3,
+            "traffic": _traffic("c4_main_bytes_per_step" if c4 else "c1_hamsoft_bytes_per_launch"),
+            "timing": "CUDA events around the run-kernel launches inside the timed steps", "counted_work": counted,
+            "note": "algorithmic flops per SURVEY.md 8d with divisions / sqrt / exp counted as ONE flop each although each "
+                    "costs 10-30 FP64 instructions: the FP64-pipe utilisation of these kernels is in profiles/ (ncu)",
+            "share_of_step": win / (t_dev / steps)}
+    sys_steps = float(B) * world * n_steps * steps
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
+        pool = CpuPool(cores)
         if c4:
             inp = _c4_inputs(3 * cores * 2, 7)
             jobs = [(inp[N][0][i], inp[N][1][i], inp[N][2][i], 2000, dt) for N in sorted(inp) for i in range(inp[N][0].shape[0])]
-            rate, dtc = _cpu_pool(_cpu_c4, jobs, cores)
-            sample = f"{len(jobs)} planetary systems x 2000 whfast steps, NumPy oracle in {cores} processes, {dtc:.1f} s"
+            rate, dtc = pool.run(_cpu_c4, jobs)
+            sample = f"{len(jobs)} planetary systems x 2000 whfast steps in {cores} processes, {dtc:.1f} s"
         else:
             m, q, v = _c1_inputs(cores, 7)
             jobs = [(m[i], q[i], v[i], 1000, dt) for i in range(cores)]
-            rate, dtc = _cpu_pool(_cpu_c1, jobs, cores)
-            sample = f"{cores} jittered README systems x 1000 ham_soft steps, oracle in {cores} processes, {dtc:.1f} s"
-        cpu = {"value": rate, "unit": "system-steps/s", "cores": cores, "kind": "port", "sample": sample}
+            rate, dtc = pool.run(_cpu_c1, jobs)
+            sample = f"{cores} jittered README systems x 1000 ham_soft steps in {cores} processes, {dtc:.1f} s"
+        pool.close()
+        cpu = {"value": rate, "unit": "system-steps/s", "cores": cores, "kind": cpu_kind(), "sample": sample}
     name = ("C4 WHFast + Kepler planetary ensemble (BASELINE.json configs[3]): star + 2-4 planets near 3:2/2:1/5:3, "
             "half TTV cohort, dt = 0.01 x 2 pi, bug-compatible Kepler solver") if c4 else \
            ("C1 README 3-body ham_soft (BASELINE.json configs[0]) batched: jittered copies, dt = 0.01, adaptive-epsilon "
             "Strang flow with the finite-difference eps* gradient")
     line = {
         "metric": "system-steps/s", "value": sys_steps / t_dev, "unit": "system-steps/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": name, "systems_per_gpu": B, "integrator_steps_per_bench_step": n_steps,
                    "buckets": {str((r if c4 else r.bk).N): int((r if c4 else r.bk).B) for r in runs}},
         "e2e": {"value": sys_steps / t_e2e, "unit": "system-steps/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps},
-        "gpu_launches": int((2 * len(runs) if c4 else 1) * args.steps), "roofline": None, "cpu_baseline": cpu,
-        "clocks": clocks, "checks": {"systems_with_nonzero_status": n_bad},
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / steps},
+        "gpu_launches": int((2 * len(runs) if c4 else 1) * steps), "roofline": roof, "cpu_baseline": cpu,
+        "checks": {"systems_with_nonzero_status": n_bad, "systems_nonfinite": n_nonfinite},
     }
-    print(json.dumps(line))
+    if not c4:
+        line["api_single_system"] = _c1_api_single_system(1000)
+    if standalone:
+        line["clocks"] = sampler.stop(mark0, mark1) if sampler is not None else None
+    return line
 
 
 def _c2_sims(mode):
@@ -762,7 +1082,7 @@ def bench_c2(args, torch, dist, world, rank, local, dev):
     import contextlib
     from nbodysimproject_b200.stability import BatchStabilityAnalyzer
     if rank != 0:
-        return
+        return None
 
     def step():
         sims = _c2_sims("verlet")
@@ -784,10 +1104,12 @@ def bench_c2(args, torch, dist, world, rank, local, dev):
         sims = _c2_sims("verlet")
         jobs = [(s._mass.copy(), s._pos.copy(), s._vel.copy(), float(s.manager.s0)) for s in sims]
         cores = min(os.cpu_count() or 1, len(jobs))
-        rate, dtc = _cpu_pool(_cpu_c2, jobs, cores)
+        pool = CpuPool(cores)
+        rate, dtc = pool.run(_cpu_c2, jobs)
+        pool.close()
         cpu = {"value": rate, "unit": "system-steps/s", "cores": cores, "kind": "port",
                "sample": f"the same 10 systems, oracle run_stability_analysis in {cores} processes, {dtc:.1f} s"}
-    print(json.dumps({
+    return ({
         "metric": "system-steps/s", "value": sys_steps / t, "unit": "system-steps/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -797,26 +1119,7 @@ def bench_c2(args, torch, dist, world, rank, local, dev):
                    "columns": int(df.shape[1])},
         "e2e": {"value": sys_steps / t, "unit": "system-steps/s", "h2d_bytes_per_step": int(10 * 4 * 5 * 8 * 3),
                 "d2h_bytes_per_step": int(10 * 47 * 8), "api": "BatchStabilityAnalyzer.analyze_batch"},
-        "gpu_launches": None, "roofline": None, "cpu_baseline": cpu}))
-
-
-def bench_largen(args, torch, dist, world, rank, local, dev):
-    from nbodysimproject_b200.largen import bench_largen as run
-    sampler = None
-    if rank == 0:
-        sampler = ClockSampler(local)
-        sampler.start()
-    line = run(args, world, rank, local, dev, sampler)
-    if rank == 0 and line is not None and world == 1 and not args.no_cpu:
-        restore_affinity()
-        rate, dtc = cpu_pairs_per_s(4096, 5)
-        line["cpu_baseline"] = {"value": rate, "unit": "pair-interactions/s", "cores": 1, "kind": "port",
-                                "sample": f"oracle dense gravitational_force at N=4096 ({dtc*1e3:.0f} ms per call; the "
-                                          "(N,N,2) fp64 temporaries make N=2^20 impossible on the CPU path: 17.6 TB)"}
-    if rank == 0 and line is not None:
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        "gpu_launches": None, "roofline": None, "cpu_baseline": cpu})
 
 
 def main():
@@ -831,7 +1134,13 @@ def main():
     ap.add_argument("--n-hamsoft", type=int, default=0, dest="n_hamsoft",
                     help="particles for the ham_soft Strang sub-step timing of --workload largen (default: --n)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-largen", action="store_true", help="skip the secondary large-N force measurement")
+    ap.add_argument("--no-largen", action="store_true", help="skip the large-N section of the default line")
+    ap.add_argument("--no-largen-hamsoft", action="store_true", dest="no_largen_hamsoft",
+                    help="skip the large-N ham_soft Strang sub-step timing of the default line")
+    ap.add_argument("--no-secondary", action="store_true", dest="no_secondary",
+                    help="skip the C1 / C4 sections of the default line")
+    ap.add_argument("--horizon", type=int, default=0,
+                    help="integrator steps per system for --workload c4 / c1 (default 1000; C4 as worded: 1000000)")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 20 if (args.workload == "ensemble" and args.impl == "b200") else 5

@@ -26,6 +26,8 @@ struct RunArgs {
   const double* raw_dv;
   double* dyn;
   int32_t* status;
+  void* ev_begin;           // host only: optional cudaEvent_t recorded right before / after the main-phase launches
+  void* ev_end;
   double* work;             // optional [B][2] counted work: whfast {Newton iterations, Kepler solves}; ham_soft {Jacobi sweeps, S half-flows}
 };
 

@@ -160,6 +160,39 @@ __device__ __forceinline__ double hs_eps_target(const double* qx, const double* 
 // excess with its writes predicated off (`act`).
 // =================================================================================================
 #define HS_NACC 22
+#define NB_INV_PI 0.31830988618379067154
+
+// a / b for a divisor that is finite, positive and far from the denormal range (smoothing lengths, masses, alpha ...):
+// MUFU.RCP64H seed, two Newton steps, one residual correction = 8 FP64-pipe instructions and no slow-path call.
+// The compiler's generic division is ~15 instructions PLUS a ~60-instruction subroutine whenever the dividend is zero
+// or tiny -- which is the common case here (a converged Jacobi sweep divides |h_new - h| = 0, a clamped eps* has a zero
+// central difference): ncu attributed 15-22 % of all executed instructions to that subroutine.  Faithfully rounded
+// (<= 1 ulp), like the compiler's fast path.
+__device__ __forceinline__ double hs_div(double a, double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
+__device__ __forceinline__ double hs_rcp(double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  return fma(r, e, r);
+}
+
+// loop invariants of the spring rotation (hamsoft_flows.py:427-762): k, mu and the sub-step h are frozen for a launch
+struct HsSpring {
+  double om, sn, cs, mo, inv_mu_om, inv_om, inv_den;
+  int rot;      // om != 0 && mu != 0
+  int den_ok;   // mu om^2 != 0
+};
 enum { HA_COM_SUM = 0, HA_COM_MAX, HA_VAR_SUM, HA_VAR_MAX, HA_COS_SUM, HA_COS_MIN, HA_WJ_MEAN, HA_WJ_M2, HA_WT_MEAN,
        HA_WT_M2, HA_LFIRST, HA_NSAMP, HA_WJ_N, HA_WT_N, HA_HAVE_FIRST, HA_COS_NAN, HA_TH_NAN, HA_E0, HA_L0, HA_E1, HA_L1 };
 
@@ -173,6 +206,8 @@ struct HsSh {
   double drx[N], dry[N], dvx[N], dvy[N];   // tangent vectors (MEGNO)
   double rs[NP > 0 ? NP : 1];   // pair separations (median test, legacy gradient)
   double acc[HS_NACC];          // step_metrics accumulators, touched by the group's lane 0 only
+  double inv_alpha;             // 1 / alpha_run
+  HsSpring spr;
   HsPar P;
 };
 
@@ -210,14 +245,14 @@ __device__ __forceinline__ int hs_solve_regs(const double (&r2)[N * (N - 1) / 2 
   int it = 0;
 #pragma unroll 1
   while (it < 8) {
-    double changed = 0.0;
+    bool conv = true;
     double hn[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const double hj = fmax(h[i], 1.0e-12);
-      const double h2 = hj * hj;
-      const double c = 1.0 / (NB_PI * h2);
-      const double nih2 = -1.0 / h2;
+      const double inv = hs_rcp(hj * hj);         // one reciprocal per body and sweep: c = 1/(pi h^2), -1/h^2
+      const double c = inv * NB_INV_PI;
+      const double nih2 = -inv;
       double S = 0.0;
 #pragma unroll
       for (int j = 0; j < N; ++j) {
@@ -227,38 +262,43 @@ __device__ __forceinline__ int hs_solve_regs(const double (&r2)[N * (N - 1) / 2 
         if (arg > -746.0) S += m[j] * (c * exp(arg));
       }
       const double Si = fmax(S, 1.0e-30);
-      double v = eta * sqrt(m[i] / Si);
+      double v = eta * sqrt(hs_div(m[i], Si));
       if (!is_finite(v) || v <= 0.0) v = h[i];
       if (v < flo) v = flo;
       else if (v > cap) v = cap;
-      const double rel = fabs(v - h[i]) / fmax(h[i], 1.0e-12);
-      changed = fmax(changed, rel);
+      // max_i |v - h_i| / max(h_i, 1e-12) < 1e-6, without the division
+      conv = conv && (fabs(v - h[i]) < 1.0e-6 * hj);
       hn[i] = v;
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) h[i] = hn[i];
     ++it;
-    if (changed < 1.0e-6) break;
+    if (conv) break;
   }
   return it;
 }
 
 // hamsoft_eps_model.py:240-289: soft-min of the h_i with temperature alpha_run (+ clamp under the soft policy)
 template <int N>
-__device__ __forceinline__ double hs_softmin(const double (&h)[N], const HsPar& P) {
+__device__ __forceinline__ double hs_softmin(const double (&h)[N], const HsPar& P, double inv_alpha) {
   const double alpha = P.alpha;
-  double tmax = -h[0] / alpha;
+  double t[N];
+  double tmax = -h[0] * inv_alpha;
+  t[0] = tmax;
 #pragma unroll
-  for (int i = 1; i < N; ++i) tmax = fmax(tmax, -h[i] / alpha);
+  for (int i = 1; i < N; ++i) { t[i] = -h[i] * inv_alpha; tmax = fmax(tmax, t[i]); }
   double s = 0.0;
 #pragma unroll
-  for (int i = 0; i < N; ++i) s += exp(-h[i] / alpha - tmax);
+  for (int i = 0; i < N; ++i) {
+    const double d = t[i] - tmax;                // <= 0; the largest term is exp(0) = 1 exactly
+    s += (d == 0.0) ? 1.0 : ((d > -746.0) ? exp(d) : 0.0);
+  }
   double es;
   if (s <= 0.0 || !is_finite(s)) es = P.s0;
   else es = -alpha * (tmax + log(s));
   if (P.policy == 0) {
     double lo = P.eps_min, hi = P.eps_max;
-    if (hi < lo) { const double t = lo; lo = hi; hi = t; }
+    if (hi < lo) { const double t2 = lo; lo = hi; hi = t2; }
     if (es < lo) es = lo;
     else if (es > hi) es = hi;
   }
@@ -307,9 +347,9 @@ __device__ __forceinline__ double hs_eps_target_coop(HsSh<N>& sh, double eps_cur
 #pragma unroll 1
   for (int it = 0; it < 8; ++it) {
     const double hj = fmax(hcur, 1.0e-12);
-    const double h2 = hj * hj;
-    const double c = 1.0 / (NB_PI * h2);
-    const double nih2 = -1.0 / h2;
+    const double inv = hs_rcp(hj * hj);
+    const double c = inv * NB_INV_PI;
+    const double nih2 = -inv;
     double S = 0.0;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
@@ -317,20 +357,21 @@ __device__ __forceinline__ double hs_eps_target_coop(HsSh<N>& sh, double eps_cur
       if (j != i && arg > -746.0) S += sh.m[j] * (c * exp(arg));
     }
     const double Si = fmax(S, 1.0e-30);
-    double v = P.eta * sqrt(mi / Si);
+    double v = P.eta * sqrt(hs_div(mi, Si));
     if (!is_finite(v) || v <= 0.0) v = hcur;
     if (v < flo) v = flo;
     else if (v > cap) v = cap;
-    const double rel = grp_max<LPS>(fabs(v - hcur) / fmax(hcur, 1.0e-12));
+    const bool conv_i = (lane >= N) || (fabs(v - hcur) < 1.0e-6 * hj);
+    const bool conv = grp_max<LPS>(conv_i ? 0.0 : 1.0) == 0.0;
     if (!done) { hcur = v; ++used; }
-    if (rel < 1.0e-6) done = true;                          // group-uniform
+    if (conv) done = true;                                  // group-uniform
   }
   if (lane == 0) sweeps += used;
   if (lane < N) sh.h[lane] = hcur;
   double h[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) h[k] = __shfl_sync(0xffffffffu, hcur, base + k);
-  return hs_softmin<N>(h, P);
+  return hs_softmin<N>(h, P, sh.inv_alpha);
 }
 
 // FD step of coordinate value x (hamsoft_eps_model.py:136-144)
@@ -354,9 +395,10 @@ __device__ __forceinline__ void hs_fallback_grp(HsSh<N>& sh, int lane, bool comm
   const double xi = sh.x[i], yi = sh.y[i], mi = sh.m[i];
   const double flo = fmax(P.eps_min, 1.0e-12);
   const double hmin = fmax(1.0e-12, 0.1 * flo);
-  const double ti = -sh.h[i] / P.alpha;
+  const double ti = -sh.h[i] * sh.inv_alpha;
   const double tmax = grp_max<LPS>(ti);
-  const double ei = exp(ti - tmax);
+  const double di = ti - tmax;
+  const double ei = (di == 0.0) ? 1.0 : ((di > -746.0) ? exp(di) : 0.0);
   __syncwarp();
   if (mine) sh.bx[i] = ei;
   __syncwarp();
@@ -364,9 +406,10 @@ __device__ __forceinline__ void hs_fallback_grp(HsSh<N>& sh, int lane, bool comm
 #pragma unroll
   for (int k = 0; k < N; ++k) den += sh.bx[k];
   const bool bad = (den <= 0.0 || !is_finite(den));
-  const double wi = ei / den;
+  const double wi = bad ? 0.0 : hs_div(ei, den);
   const double hj = fmax(sh.h[i], hmin);
-  const double c = 1.0 / (NB_PI * hj * hj);
+  const double ihj = hs_rcp(hj), ih2 = ihj * ihj;           // 1/h, 1/h^2: every quotient of this body reuses them
+  const double c = ih2 * NB_INV_PI;
   double S = 0.0, Sd = 0.0;
   double W[N];
 #pragma unroll
@@ -375,39 +418,39 @@ __device__ __forceinline__ void hs_fallback_grp(HsSh<N>& sh, int lane, bool comm
     if (j == i) continue;
     const double dx = xi - sh.x[j], dy = yi - sh.y[j];
     const double rr = dx * dx + dy * dy;
-    const double arg = -rr / (hj * hj);
+    const double arg = -rr * ih2;
     if (arg > -746.0) {
       W[j] = c * exp(arg);
       S += sh.m[j] * W[j];
-      Sd += sh.m[j] * (W[j] * (-2.0 / hj + 2.0 * rr / (hj * hj * hj)));
+      Sd += sh.m[j] * (W[j] * (2.0 * ihj * (rr * ih2 - 1.0)));      // dW/dh = W (-2/h + 2 r^2/h^3)
     }
   }
   const double Si = fmax(S, 1.0e-30);
-  double Om = 1.0 + hj * Sd / (2.0 * Si);
+  double Om = (Sd == 0.0) ? 1.0 : 1.0 + hs_div(hj * Sd, 2.0 * Si);
   if (!is_finite(Om) || Om == 0.0) Om = 1.0;
-  const double si = -wi * (-hj / (2.0 * Si * Om));
+  const double si = wi * hs_div(hj, 2.0 * Si * Om);           // -w_i P_i with P_i = -h / (2 Sigma Omega)
   __syncwarp();
-  if (mine) { sh.bx[i] = si; sh.by[i] = hj; }
+  if (mine) { sh.bx[i] = si; sh.by[i] = ih2; }
   __syncwarp();
   // the reference scatters s_i m_j coef_i(r_ij) (q_i - q_j) onto i (+) and j (-); gathered per body here
   double gx = 0.0, gy = 0.0;
 #pragma unroll
   for (int j = 0; j < N; ++j) {
-    if (j == i) continue;
+    if (j == i || W[j] == 0.0) continue;
     const double rx = xi - sh.x[j], ry = yi - sh.y[j];
-    const double coef = -2.0 * W[j] / (hj * hj);
+    const double coef = -2.0 * W[j] * ih2;
     gx += si * sh.m[j] * (coef * rx);
     gy += si * sh.m[j] * (coef * ry);
   }
 #pragma unroll
   for (int a = 0; a < N; ++a) {
     if (a == i) continue;
-    const double ha = sh.by[a], sa = sh.bx[a];
+    const double ia2 = sh.by[a], sa = sh.bx[a];
     const double rx = sh.x[a] - xi, ry = sh.y[a] - yi;
-    const double arg = -(rx * rx + ry * ry) / (ha * ha);
+    const double arg = -(rx * rx + ry * ry) * ia2;
     if (arg > -746.0) {
-      const double Wa = (1.0 / (NB_PI * ha * ha)) * exp(arg);
-      const double coef = -2.0 * Wa / (ha * ha);
+      const double Wa = (ia2 * NB_INV_PI) * exp(arg);
+      const double coef = -2.0 * Wa * ia2;
       gx -= sa * mi * (coef * rx);
       gy -= sa * mi * (coef * ry);
     }
@@ -415,10 +458,12 @@ __device__ __forceinline__ void hs_fallback_grp(HsSh<N>& sh, int lane, bool comm
   if (bad || !is_finite(gx)) gx = 0.0;
   if (bad || !is_finite(gy)) gy = 0.0;
   // sign alignment against the legacy gradient: only sum(g_use . g_legacy) matters
-  const double dp = lane < NP ? 1.0 / (fmax(sh.rs[lane < NP ? lane : 0], 1.0e-15) + 1.0e-12) : 0.0;
-  const double D = grp_sum<LPS>(dp);
+  // (only the SIGN of sum(g_use . g_legacy) is used, and only when the analytic gradient is non-zero)
+  const bool any_g = grp_max<LPS>((mine && (gx != 0.0 || gy != 0.0)) ? 1.0 : 0.0) != 0.0;
   double sg = 1.0;
   {
+    const double dp = lane < NP ? hs_rcp(fmax(sh.rs[lane < NP ? lane : 0], 1.0e-15) + 1.0e-12) : 0.0;
+    const double D = grp_sum<LPS>(dp);
     const double cp = P.lam * ((double)N / (D * D));
     double sx = 0.0, sy = 0.0;
 #pragma unroll
@@ -427,14 +472,14 @@ __device__ __forceinline__ void hs_fallback_grp(HsSh<N>& sh, int lane, bool comm
       const int a = i < j ? i : j, b = i < j ? j : i;
       const double r = fmax(sh.rs[hs_pair_index<N>(a, b)], 1.0e-15);
       const double dn = r + 1.0e-12;
-      const double A = 1.0 / (r * dn * dn);
+      const double A = hs_rcp(r * dn * dn);
       sx += A * (xi - sh.x[j]);
       sy += A * (yi - sh.y[j]);
     }
     const double lx = -cp * sx, ly = -cp * sy;
     const double nok = grp_max<LPS>((mine && !(is_finite(lx) && is_finite(ly))) ? 1.0 : 0.0);
     const double dot = grp_sum<LPS>(mine ? gx * lx + gy * ly : 0.0);
-    if (is_finite(D) && D > 0.0 && nok == 0.0 && is_finite(dot) && dot < 0.0) sg = -1.0;
+    if (any_g && is_finite(D) && D > 0.0 && nok == 0.0 && is_finite(dot) && dot < 0.0) sg = -1.0;
   }
   if (commit && mine) { sh.gx[i] = sg * gx; sh.gy[i] = sg * gy; }
 }
@@ -486,7 +531,7 @@ __device__ __forceinline__ double hs_eps_star_and_grad(HsSh<N>& sh, double eps_c
 #pragma unroll
       for (int i = 0; i < N; ++i) sh.h[i] = h[i];
     }
-    f = hs_softmin<N>(h, P);
+    f = hs_softmin<N>(h, P, sh.inv_alpha);
   }
   double es;
   if constexpr (COOP) es = hs_eps_target_coop<N>(sh, eps_cur, lane, base, sweeps);
@@ -498,8 +543,10 @@ __device__ __forceinline__ double hs_eps_star_and_grad(HsSh<N>& sh, double eps_c
   const double fpx = __shfl_sync(0xffffffffu, f, src), fmx = __shfl_sync(0xffffffffu, f, src + 1);
   const double fpy = __shfl_sync(0xffffffffu, f, src + 2), fmy = __shfl_sync(0xffffffffu, f, src + 3);
   const double xi = sh.x[i], yi = sh.y[i];
-  double gx = (fpx - fmx) / (2.0 * hs_fd_step(xi));
-  double gy = (fpy - fmy) / (2.0 * hs_fd_step(yi));
+  // a clamped eps* has an exactly zero central difference (the common case under the soft policy)
+  const double dfx = fpx - fmx, dfy = fpy - fmy;
+  double gx = (dfx == 0.0) ? 0.0 : dfx / (2.0 * hs_fd_step(xi));
+  double gy = (dfy == 0.0) ? 0.0 : dfy / (2.0 * hs_fd_step(yi));
   if (!is_finite(gx)) gx = 0.0;
   if (!is_finite(gy)) gy = 0.0;
   const double gmax = sqrt(grp_max<LPS>(mine ? gx * gx + gy * gy : 0.0));
@@ -548,6 +595,28 @@ __device__ __forceinline__ void hs_fold(double& eps, double& pi, const HsPar& P)
   else { eps = b - (y - R); pi = -pi; }
 }
 
+// rotation constants of the S half-flow for sub-step h (theta = omega h / 2; small-angle series below 1e-8)
+__device__ __forceinline__ void hs_spring_setup(HsSpring& R, const HsPar& P, double h) {
+  const double k = P.k, mu = P.mu;
+  const double om = (k > 0.0 && mu > 0.0) ? sqrt(k / mu) : 0.0;
+  const double th = om * (0.5 * h);
+  if (fabs(th) < 1.0e-8) {
+    const double t2 = th * th;
+    R.sn = th - t2 * th / 6.0 + t2 * t2 * th / 120.0;
+    R.cs = 1.0 - t2 / 2.0 + t2 * t2 / 24.0;
+  } else {
+    sincos(th, &R.sn, &R.cs);
+  }
+  R.om = om;
+  R.rot = (om != 0.0 && mu != 0.0) ? 1 : 0;
+  R.mo = sqrt(mu * fmax(k, 0.0));
+  const double den = mu * om * om;
+  R.den_ok = (den != 0.0) ? 1 : 0;
+  R.inv_mu_om = R.rot ? 1.0 / (mu * om) : 0.0;
+  R.inv_om = R.rot ? 1.0 / om : 0.0;
+  R.inv_den = R.den_ok ? 1.0 / den : 0.0;
+}
+
 // S half-flow: hamsoft_stepper.py:47-88 -> spring_oscillation (live definition) hamsoft_flows.py:427-762.
 // eps, pi are replicated scalars of the group; momenta are updated by the body lanes.
 template <int N>
@@ -561,27 +630,17 @@ __device__ __forceinline__ void hs_s_half(HsSh<N>& sh, double& eps, double& pi, 
   hs_fold(eps0, pi0, P);                         // hamsoft_stepper.py:107-113
   bool fb;
   const double es = hs_eps_star_and_grad<N>(sh, eps0, lane_full, fb, sweeps);
-  const double k = P.k, mu = P.mu;
-  const double om = (k > 0.0 && mu > 0.0) ? sqrt(k / mu) : 0.0;
-  const double th = om * dt;
-  double sn, cs;
-  if (fabs(th) < 1.0e-8) {
-    const double t2 = th * th;
-    sn = th - t2 * th / 6.0 + t2 * t2 * th / 120.0;
-    cs = 1.0 - t2 / 2.0 + t2 * t2 / 24.0;
-  } else {
-    sincos(th, &sn, &cs);
-  }
+  const HsSpring& R = sh.spr;                    // k, mu, h are frozen for the launch: rotation constants precomputed
+  const double k = P.k;
+  const double sn = R.sn, cs = R.cs;
   const double kick1 = (P.policy == 0) ? 0.5 * dt * hs_barrier_force(eps0, P) : 0.0;
   const double D0 = eps0 - es;
   const double pin = pi0 + kick1;
   double dlt, eta_t, I;
-  if (om != 0.0 && mu != 0.0) {
-    const double mo = sqrt(mu * fmax(k, 0.0));
-    dlt = D0 * cs + (pin / (mu * om)) * sn;
-    eta_t = pin * cs - mo * D0 * sn;
-    const double den = mu * om * om;
-    I = den != 0.0 ? (D0 / om) * sn + (pin / den) * (1.0 - cs) : 0.0;
+  if (R.rot) {
+    dlt = D0 * cs + (pin * R.inv_mu_om) * sn;
+    eta_t = pin * cs - R.mo * D0 * sn;
+    I = R.den_ok ? (D0 * R.inv_om) * sn + (pin * R.inv_den) * (1.0 - cs) : 0.0;
   } else {
     dlt = D0; eta_t = pin; I = 0.0;
   }
@@ -599,9 +658,10 @@ __device__ __forceinline__ void hs_s_half(HsSh<N>& sh, double& eps, double& pi, 
   const double dp_inf = sqrt(dmax2);
   const double thr = P.jcap * p_scale;
   const double Ja = (dp_inf > thr && dp_inf > 0.0) ? J * (thr / dp_inf) : J;
-  if (act && mine) {
-    sh.vx[i] = (mi * vx + Ja * gx) / mi;
-    sh.vy[i] = (mi * vy + Ja * gy) / mi;
+  if (act && mine && Ja != 0.0) {               // p += J grad eps*; v = p / m
+    const double im = hs_rcp(mi);
+    sh.vx[i] = (mi * vx + Ja * gx) * im;
+    sh.vy[i] = (mi * vy + Ja * gy) * im;
   }
   double pi_out = eta_t + kick2;
   hs_fold(eps_rot, pi_out, P);                   // hamsoft_stepper.py:72-80
@@ -639,8 +699,9 @@ __device__ __forceinline__ void hs_v_half(HsSh<N>& sh, double eps, double& pi, d
     }
   }
   if (act && mine) {
-    sh.vx[i] = (mi * sh.vx[i] + hh * fx) / mi;
-    sh.vy[i] = (mi * sh.vy[i] + hh * fy) / mi;
+    const double im = hs_rcp(mi);
+    sh.vx[i] = (mi * sh.vx[i] + hh * fx) * im;
+    sh.vy[i] = (mi * sh.vy[i] + hh * fy) * im;
   }
   const double s3t = grp_sum<LPS>(mine ? s3 : 0.0);
   const double dU = (eps == 0.0 || G == 0.0) ? 0.0 : G * eps * s3t;
@@ -744,6 +805,7 @@ __device__ __forceinline__ void hs_load_system(HsSh<N>& sh, const double* m, con
   }
   if (lane == 0) {
     sh.P = hs_load(hs + (size_t)sys * NB_HS_NPARAM);
+    sh.inv_alpha = 1.0 / sh.P.alpha;
 #pragma unroll
     for (int k = 0; k < HS_NACC; ++k) sh.acc[k] = 0.0;
     sh.acc[HA_COM_MAX] = -1.0; sh.acc[HA_VAR_MAX] = -1.0; sh.acc[HA_COS_MIN] = 2.0;
@@ -753,7 +815,7 @@ __device__ __forceinline__ void hs_load_system(HsSh<N>& sh, const double* m, con
 }
 
 template <int N>
-__global__ void __launch_bounds__(128, (N <= 4 ? 4 : (N <= 6 ? 3 : 2))) hamsoft_run_kernel(HsArgs a) {
+__global__ void __launch_bounds__(128, (N <= 3 ? 6 : (N <= 4 ? 5 : (N <= 6 ? 3 : 2)))) hamsoft_run_kernel(HsArgs a) {
   constexpr int LPS = HsLanes<N>::LPS, SPW = 32 / LPS;   // lanes per system, systems per warp
   __shared__ HsSh<N> shs[4 * SPW];
   const int lane_full = threadIdx.x & 31;
@@ -780,6 +842,7 @@ __global__ void __launch_bounds__(128, (N <= 4 ? 4 : (N <= 6 ? 3 : 2))) hamsoft_
     const double mu_macro = sh.P.k * (fabs(dt) / sh.P.theta_imp) * (fabs(dt) / sh.P.theta_imp);
     if (sh.P.mu < mu_macro) sh.P.mu = mu_macro;
   }
+  if (lane == 0) hs_spring_setup(sh.spr, sh.P, h);
   __syncwarp();
   const bool want_energy = (a.flags & NB_RUN_ENERGY) != 0;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
