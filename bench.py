@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -461,13 +462,16 @@ def ensemble_section(args, ctx):
     prep_flags = L.PREP_REMOVE_COM | L.PREP_CTOR_KICK | L.PREP_SNAPSHOT_KICK
     interval = max(1, N_STEPS // 100)
     launches_per_step = 0
-    main_events = []            # per timed step: {N: (begin, end)} recorded by the C ABI around the main-phase launches
+    # per timed step and bucket: {earliest CTA start, latest warp end} of the main-phase kernels in %globaltimer ns,
+    # published by the kernels themselves (nb_ensemble_run_counted_f64, t_main)
+    I64MAX = (1 << 63) - 1
+    stamps = {N: torch.tensor([[I64MAX, 0]] * (args.steps + 1), dtype=torch.int64, device=dev) for N in Ns}
+    timed_step = [0]
 
     def step_device(record=False):
         nonlocal launches_per_step
         cur = torch.cuda.current_stream()
         n = 0
-        evs = {}
         # the construction-time kernels of every bucket first (0.3 % of the step), then the runs: nb_ensemble_run_f64
         # launches each bucket's sub-step-heavy head at high priority, so no head waits behind another bucket's bulk
         for N in Ns:
@@ -481,17 +485,14 @@ def ensemble_section(args, ctx):
         for N in Ns:
             bk = devb[N]
             with torch.cuda.stream(bk.stream):
-                ev = None
-                if record:
-                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                    evs[N] = ev
-                bk.dyn = bk.run(DT, N_STEPS, interval, N_MEGNO, bk.rdr, bk.rdv, flags=L.RUN_ENERGY, ev_main=ev)  # 2+2+1+1 kernels
+                ts = stamps[N][timed_step[0]] if record else None
+                bk.dyn = bk.run(DT, N_STEPS, interval, N_MEGNO, bk.rdr, bk.rdv, flags=L.RUN_ENERGY, t_main=ts)  # 2+2+1+1 kernels
                 n += 10
         for N in Ns:
             cur.wait_stream(devb[N].stream)
         launches_per_step = n
         if record:
-            main_events.append(evs)
+            timed_step[0] += 1
 
     def restore_e2e_inputs():
         # nb_ensemble_analyze_host* returns the kicked velocities in the caller's v (the reference mutates the caller's
@@ -567,15 +568,12 @@ def ensemble_section(args, ctx):
             nsub_sum = int(bk.n_sub.sum().item())       # n_sub of the last timed step (deterministic in the inputs)
             bk.flops = flops_main(N, nsub_sum, N_STEPS)
             tot_fl += bk.flops
-            solo = float(np.mean([ev[N][0].elapsed_time(ev[N][1]) for ev in main_events]))
+            ts = stamps[N][:args.steps].cpu().numpy()
+            bk.ts = ts
             per.append(dict(N=N, B=bk.B, mean_n_sub=nsub_sum / bk.B, max_n_sub=int(bk.n_sub.max().item()),
-                            in_step_ms=solo, flops=bk.flops))
-        windows = []
-        for ev in main_events:
-            t_begin = min(e0.elapsed_time(ev[N][0]) for N in Ns)
-            t_end = max(e0.elapsed_time(ev[N][1]) for N in Ns)
-            windows.append(t_end - t_begin)
-        win = float(np.mean(windows)) * 1e-3
+                            in_step_ms=float(np.mean(ts[:, 1] - ts[:, 0])) * 1e-6, flops=bk.flops))
+        windows = [max(devb[N].ts[k, 1] for N in Ns) - min(devb[N].ts[k, 0] for N in Ns) for k in range(args.steps)]
+        win = float(np.mean(windows)) * 1e-9
         ach = tot_fl / win * 1e-12
         roof = {"bound": "fp64", "kernel": "ensemble_main_kernel<N=3..8, yoshida4> (6 concurrent launches per step)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
@@ -584,8 +582,9 @@ def ensemble_section(args, ctx):
                 "traffic_note": "dram bytes over the six launches of one step at 2^20 systems/GPU from the committed ncu "
                                 "capture (profiles/r2_traffic.json); the state is read once and lives in registers",
                 "flops_per_step": tot_fl, "ms": win * 1e3,
-                "timing": "CUDA events recorded by nb_ensemble_run_counted_f64 around the main-phase launches of every "
-                          "bucket inside the timed steps; window = first begin .. last end, mean over the timed steps",
+                "timing": "%globaltimer stamps published by the main kernels themselves (first CTA start, last warp end; "
+                          "nb_ensemble_run_counted_f64 t_main) inside the timed steps; window = earliest start .. latest end "
+                          "over the six buckets, mean over the timed steps",
                 "peak_source": "nb_peak_flops(0): register-resident DFMA micro-benchmark, same GPU, same run "
                                "(MEASURED_PEAKS.json has no FP64 figure; nominal 64 DFMA/clk/SM x 148 x 1.965 GHz = 37.2)",
                 "flop_model": "SURVEY.md 8d: per sub-step 3 x 14 N(N-1) + 36 N",
@@ -918,30 +917,29 @@ def secondary_section(args, ctx, which, steps, sampler, standalone):
         hb.q0, hb.v0, hb.ep0, hb.hs0 = hb.bk.q.clone(), hb.bk.v.clone(), hb.eps_pi.clone(), hb.hs.clone()
         hb.work = torch.zeros((B, 2), dtype=torch.float64, device=dev)
         runs.append(hb)
-    main_events = []
+    I64MAX = (1 << 63) - 1
+    for r in runs:
+        r.stamps = torch.tensor([[I64MAX, 0]] * (steps + 1), dtype=torch.int64, device=dev)
+    timed_step = [0]
 
     def step(record=False):
         cur = torch.cuda.current_stream()
-        evs = []
         if c4:
             for bk in runs:
                 bk.stream.wait_stream(cur)
                 with torch.cuda.stream(bk.stream):
                     bk.q.copy_(bk.q0); bk.v.copy_(bk.v0)
                     bk.prepare(L.PREP_REMOVE_COM | L.PREP_CTOR_KICK, dt, dt, dt, 50)
-                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if record else None
-                    bk.run(dt, n_steps, 0, 0, flags=L.RUN_WRITE_STATE, want_dyn=False, work=bk.work, ev_main=ev)
-                    evs.append(ev)
+                    bk.run(dt, n_steps, 0, 0, flags=L.RUN_WRITE_STATE, want_dyn=False, work=bk.work,
+                           t_main=bk.stamps[timed_step[0]] if record else None)
             for bk in runs:
                 cur.wait_stream(bk.stream)
         else:
             hb = runs[0]
             hb.bk.q.copy_(hb.q0); hb.bk.v.copy_(hb.v0); hb.eps_pi.copy_(hb.ep0); hb.hs.copy_(hb.hs0)
-            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if record else None
-            hb.run(dt, n_steps, work=hb.work, ev_main=ev)
-            evs.append(ev)
+            hb.run(dt, n_steps, work=hb.work, t_main=hb.stamps[timed_step[0]] if record else None)
         if record:
-            main_events.append(evs)
+            timed_step[0] += 1
 
     for _ in range(args.warmup if n_steps <= 1000 else 1):
         step()
@@ -989,14 +987,14 @@ def secondary_section(args, ctx, which, steps, sampler, standalone):
         return None
     # ---- roofline from counted work
     peak = L.peak_flops(0, local)
-    win = float(np.mean([max(e0.elapsed_time(ev[1]) for ev in evs) - min(e0.elapsed_time(ev[0]) for ev in evs)
-                         for evs in main_events])) * 1e-3
+    tss = [r.stamps[:steps].cpu().numpy() for r in runs]
+    win = float(np.mean([max(t[k, 1] for t in tss) - min(t[k, 0] for t in tss) for k in range(steps)])) * 1e-9
     if c4:
         iters = sum(float(bk.work[:, 0].sum()) for bk in runs)
         solves = sum(float(bk.work[:, 1].sum()) for bk in runs)
         # SURVEY.md 8d "whfast": 14 N(N-1) per full-force kick + 2 (N-1) K, K = 60 flops x Newton iterations (measured)
         fl = sum(float(bk.B) * n_steps * 14.0 * bk.N * (bk.N - 1) for bk in runs) + 60.0 * iters
-        counted = {"kepler_solves": solves, "mean_newton_iterations": iters / max(solves, 1.0),
+        counted = {"kepler_solves": solves, "mean_newton_iterations_executed": iters / max(solves, 1.0),
                    "flop_model": "SURVEY.md 8d: 14 N(N-1) + 60 x Newton iterations per Kepler solve, 2(N-1) solves per step"}
         kernel = "ensemble_main_kernel<N=3..5, whfast> (3 concurrent launches per step)"
     else:
@@ -1014,7 +1012,7 @@ def secondary_section(args, ctx, which, steps, sampler, standalone):
     roof = {"bound": "fp64", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             "frac_nominal": ach / NOMINAL_FP64, "peak_nominal": NOMINAL_FP64, "flops_per_step": fl, "ms": win * 1e3,
             "traffic": _traffic("c4_main_bytes_per_step" if c4 else "c1_hamsoft_bytes_per_launch"),
-            "timing": "CUDA events around the run-kernel launches inside the timed steps", "counted_work": counted,
+            "timing": "%globaltimer stamps published by the run kernels inside the timed steps", "counted_work": counted,
             "note": "algorithmic flops per SURVEY.md 8d with divisions / sqrt / exp counted as ONE flop each although each "
                     "costs 10-30 FP64 instructions: the FP64-pipe utilisation of these kernels is in profiles/ (ncu)",
             "share_of_step": win / (t_dev / steps)}
@@ -1024,15 +1022,15 @@ def secondary_section(args, ctx, which, steps, sampler, standalone):
         cores = os.cpu_count() or 1
         pool = CpuPool(cores)
         if c4:
-            inp = _c4_inputs(3 * cores * 2, 7)
+            inp = _c4_inputs(3 * cores * 8, 7)
             jobs = [(inp[N][0][i], inp[N][1][i], inp[N][2][i], 2000, dt) for N in sorted(inp) for i in range(inp[N][0].shape[0])]
             rate, dtc = pool.run(_cpu_c4, jobs)
             sample = f"{len(jobs)} planetary systems x 2000 whfast steps in {cores} processes, {dtc:.1f} s"
         else:
-            m, q, v = _c1_inputs(cores, 7)
-            jobs = [(m[i], q[i], v[i], 1000, dt) for i in range(cores)]
+            m, q, v = _c1_inputs(6 * cores, 7)
+            jobs = [(m[i], q[i], v[i], 1000, dt) for i in range(6 * cores)]
             rate, dtc = pool.run(_cpu_c1, jobs)
-            sample = f"{cores} jittered README systems x 1000 ham_soft steps in {cores} processes, {dtc:.1f} s"
+            sample = f"{6 * cores} jittered README systems x 1000 ham_soft steps in {cores} processes, {dtc:.1f} s"
         pool.close()
         cpu = {"value": rate, "unit": "system-steps/s", "cores": cores, "kind": cpu_kind(), "sample": sample}
     name = ("C4 WHFast + Kepler planetary ensemble (BASELINE.json configs[3]): star + 2-4 planets near 3:2/2:1/5:3, "

@@ -125,9 +125,10 @@ int nb_ensemble_run_f64(const double* m, double* q, double* v, const double* eps
                         double* eps_pi, const double* hs_params,
                         double* dyn_features, int32_t* status, void* stream);
 
-/* the same call, instrumented for the roofline figures.  ev_main_begin / ev_main_end (cudaEvent_t, may be
- *      NULL) are recorded right before and right after the main-phase kernel launches of this call (head + rest when the
- *      launch is split), so a benchmark can time the dominant kernels INSIDE its timed loop.  work[B][2] (may be NULL)
+/* the same call, instrumented for the roofline figures.  t_main (device uint64[2], may be NULL; the
+ *      caller initialises it to {UINT64_MAX, 0}) receives {earliest start, latest end} of the MAIN-phase kernels' CTAs in
+ *      %globaltimer nanoseconds, published by the kernels themselves (one atomic per CTA / warp), so a benchmark can
+ *      time the dominant kernels inside its timed loop without adding stream operations.  work[B][2] (may be NULL)
  *      receives, per system,
  *      whfast  : {Newton iterations summed over all Kepler solves, number of Kepler solves}   (kepler_solver.py:48-91)
  *      ham_soft: {Jacobi sweeps of _solve_hi summed over the 4N+1 evaluations of every S half-flow, number of S half-flows}
@@ -137,8 +138,8 @@ int nb_ensemble_run_counted_f64(const double* m, double* q, double* v, const dou
                                 const int32_t* n_sub, const int32_t* perm, const int32_t* n_heavy,
                                 const double* raw_dr, const double* raw_dv,
                                 double* eps_pi, const double* hs_params,
-                                double* dyn_features, int32_t* status, double* work,
-                                void* ev_main_begin, void* ev_main_end, void* stream);
+                                double* dyn_features, int32_t* status, double* work, uint64_t* t_main,
+                                void* stream);
 
 /* ---- classic ADAPTIVE softening (adaptive_softening=True with verlet / yoshida4): n_steps macro steps in which the
  *      softening is re-derived from the minimum separation after every sub-step (integrator.py:126-136, 204-225;

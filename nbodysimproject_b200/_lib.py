@@ -74,7 +74,7 @@ def load():
     lib.nb_variational_batched_f64.argtypes = [p, p, p, p, d, i, i, p, p]
     lib.nb_ensemble_prepare_f64.argtypes = [p, p, p, p, d, i, i, i, u, d, d, d, i, p, p, p, p]
     lib.nb_ensemble_run_f64.argtypes = [p, p, p, p, d, i, i, i, u, d, i, i, i, p, p, p, p, p, p, p, p, p, p]
-    lib.nb_ensemble_run_counted_f64.argtypes = [p, p, p, p, d, i, i, i, u, d, i, i, i, p, p, p, p, p, p, p, p, p, p, p, p, p]
+    lib.nb_ensemble_run_counted_f64.argtypes = [p, p, p, p, d, i, i, i, u, d, i, i, i, p, p, p, p, p, p, p, p, p, p, p, p]
     lib.nb_sort_by_nsub.argtypes = [p, i, i, p, p, p]
     lib.nb_ensemble_set_heavy_nsub.argtypes = [i]
     lib.nb_ensemble_run_adaptive_f64.argtypes = [p, p, p, p, p, d, i, i, i, d, i, p, d, i, p, p, p, p]

@@ -26,8 +26,7 @@ struct RunArgs {
   const double* raw_dv;
   double* dyn;
   int32_t* status;
-  void* ev_begin;           // host only: optional cudaEvent_t recorded right before / after the main-phase launches
-  void* ev_end;
+  unsigned long long* tstamp;   // optional device [2]: {min start, max end} of the main-phase CTAs in %globaltimer ns
   double* work;             // optional [B][2] counted work: whfast {Newton iterations, Kepler solves}; ham_soft {Jacobi sweeps, S half-flows}
 };
 

@@ -50,7 +50,7 @@ int largeN_kick_drift(float* xym_local, float* vel, const float* acc, int ni, fl
 int hamsoft_run(const double* m, double* q, double* v, double G, int B, int N, unsigned flags, double dt, int n_steps,
                 int sample_interval, int n_megno, const int32_t* n_sub, const int32_t* perm, const double* raw_dr,
                 const double* raw_dv, double* eps_pi, const double* hs, double* dyn, int32_t* status, double* work,
-                cudaStream_t st);
+                unsigned long long* tstamp, cudaStream_t st);
 
 int hamsoft_setup(const double* m, const double* q, double G, int B, int N, unsigned flags, double dt, double* hs,
                   double* eps_pi, int32_t* n_sub, cudaStream_t st);
@@ -266,20 +266,17 @@ int nb_ensemble_run_counted_f64(const double* m, double* q, double* v, const dou
                                 unsigned flags, double dt, int n_steps, int sample_interval, int n_megno,
                                 const int32_t* n_sub, const int32_t* perm, const int32_t* n_heavy, const double* raw_dr,
                                 const double* raw_dv, double* eps_pi, const double* hs_params, double* dyn_features,
-                                int32_t* status, double* work, void* ev_main_begin, void* ev_main_end, void* stream) {
+                                int32_t* status, double* work, uint64_t* t_main, void* stream) {
   if (!m || !q || !v || B < 0 || N < NB_MIN_N || N > NB_MAX_N || n_steps < 0 || n_megno < 0) { set_error("nb_ensemble_run_f64: bad arguments"); return NB_ERR_ARG; }
   if (n_megno > 0 && (!raw_dr || !raw_dv)) { set_error("nb_ensemble_run_f64: n_megno > 0 needs raw_dr/raw_dv"); return NB_ERR_ARG; }
   if (B == 0) return NB_OK;
   if (mode == NB_MODE_HAMSOFT) {
     if (!eps_pi || !hs_params) { set_error("nb_ensemble_run_f64: ham_soft needs eps_pi and hs_params"); return NB_ERR_ARG; }
-    if (ev_main_begin) NB_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev_main_begin, (cudaStream_t)stream));
-    int rc = hamsoft_run(m, q, v, G, B, N, flags, dt, n_steps, sample_interval, n_megno, n_sub, perm, raw_dr, raw_dv,
-                         eps_pi, hs_params, dyn_features, status, work, (cudaStream_t)stream);
-    if (rc == NB_OK && ev_main_end) NB_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev_main_end, (cudaStream_t)stream));
-    return rc;
+    return hamsoft_run(m, q, v, G, B, N, flags, dt, n_steps, sample_interval, n_megno, n_sub, perm, raw_dr, raw_dv,
+                       eps_pi, hs_params, dyn_features, status, work, (unsigned long long*)t_main, (cudaStream_t)stream);
   }
   if (!eps) { set_error("nb_ensemble_run_f64: eps is required"); return NB_ERR_ARG; }
-  RunArgs a{m, q, v, eps, G, B, flags, dt, n_steps, sample_interval, n_megno, n_sub, perm, perm ? n_heavy : nullptr, 0, 0, 0, raw_dr, raw_dv, dyn_features, status, ev_main_begin, ev_main_end, work};
+  RunArgs a{m, q, v, eps, G, B, flags, dt, n_steps, sample_interval, n_megno, n_sub, perm, perm ? n_heavy : nullptr, 0, 0, 0, raw_dr, raw_dv, dyn_features, status, (unsigned long long*)t_main, work};
   return ensemble_run_classic(a, N, mode, (cudaStream_t)stream);
 }
 
@@ -288,7 +285,7 @@ int nb_ensemble_run_f64(const double* m, double* q, double* v, const double* eps
                         const int32_t* perm, const int32_t* n_heavy, const double* raw_dr, const double* raw_dv,
                         double* eps_pi, const double* hs_params, double* dyn_features, int32_t* status, void* stream) {
   return nb_ensemble_run_counted_f64(m, q, v, eps, G, B, N, mode, flags, dt, n_steps, sample_interval, n_megno, n_sub, perm,
-                                     n_heavy, raw_dr, raw_dv, eps_pi, hs_params, dyn_features, status, nullptr, nullptr, nullptr, stream);
+                                     n_heavy, raw_dr, raw_dv, eps_pi, hs_params, dyn_features, status, nullptr, nullptr, stream);
 }
 
 int nb_hamsoft_setup_f64(const double* m, const double* q, double G, int B, int N, unsigned flags, double dt,
@@ -392,7 +389,7 @@ int nb_ensemble_analyze_host_async(const double* m, const double* q, double* v, 
   rc = sort_by_nsub(d_nsub, B, N, d_perm, d_bins, st);
   if (rc != NB_OK) return rc;
   const int interval = n_steps / 100 > 1 ? n_steps / 100 : 1;
-  RunArgs ra{d_m, d_q, d_v, d_eps, G, B, NB_RUN_ENERGY, dt, n_steps, interval, n_megno, d_nsub, d_perm, d_bins + 64, 0, 0, 0, d_dr, d_dv, d_dyn, d_status, nullptr, nullptr, nullptr};
+  RunArgs ra{d_m, d_q, d_v, d_eps, G, B, NB_RUN_ENERGY, dt, n_steps, interval, n_megno, d_nsub, d_perm, d_bins + 64, 0, 0, 0, d_dr, d_dv, d_dyn, d_status, nullptr, nullptr};
   rc = ensemble_run_classic(ra, N, mode, st);
   if (rc != NB_OK) return rc;
   NB_CUDA_CHECK(cudaMemcpyAsync(dyn_features, d_dyn, (size_t)B * NB_N_DYN * 8, cudaMemcpyDeviceToHost, st));

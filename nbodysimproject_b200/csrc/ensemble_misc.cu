@@ -154,10 +154,8 @@ int ensemble_run_classic(const RunArgs& a_in, int N, int mode, cudaStream_t st) 
   int rc;
   if (!split) {
     if (energy) energy_kernel<<<blocks, threads, 0, st>>>(a.m, a.q, a.v, a.eps, a.G, a.B, N, a.dyn, 0);
-    if (a.ev_begin) NB_CUDA_CHECK(cudaEventRecord((cudaEvent_t)a.ev_begin, st));
     rc = phase(0, write, a, st);
     if (rc != NB_OK) return rc;
-    if (a.ev_end) NB_CUDA_CHECK(cudaEventRecord((cudaEvent_t)a.ev_end, st));
   } else {
     int total = 0, prefix = 0;
     if (mode == NB_MODE_YOSHIDA4) main_blocks_n<NB_MODE_YOSHIDA4>(a, N, &total, &prefix);
@@ -182,7 +180,6 @@ int ensemble_run_classic(const RunArgs& a_in, int N, int mode, cudaStream_t st) 
     if (energy) energy_kernel<<<blocks, threads, 0, s_head>>>(a.m, a.q, a.v, a.eps, a.G, a.B, N, a.dyn, 0);
     NB_CUDA_CHECK(cudaEventRecord(sp->ev[k][1], s_head));          // E0 is read before anything advances the state
     NB_CUDA_CHECK(cudaStreamWaitEvent(s_rest, sp->ev[k][1], 0));
-    if (a.ev_begin) NB_CUDA_CHECK(cudaEventRecord((cudaEvent_t)a.ev_begin, s_head));
     RunArgs h = a, r = a;
     h.block0 = 0; h.block_count = head;
     r.block0 = head; r.block_count = total - head;
@@ -194,7 +191,6 @@ int ensemble_run_classic(const RunArgs& a_in, int N, int mode, cudaStream_t st) 
     }
     NB_CUDA_CHECK(cudaEventRecord(sp->ev[k][2], side));            // join
     NB_CUDA_CHECK(cudaStreamWaitEvent(st, sp->ev[k][2], 0));
-    if (a.ev_end) NB_CUDA_CHECK(cudaEventRecord((cudaEvent_t)a.ev_end, st));
   }
   if (energy) energy_kernel<<<blocks, threads, 0, st>>>(a.m, a.q, a.v, a.eps, a.G, a.B, N, a.dyn, 1);
   if (megno) {

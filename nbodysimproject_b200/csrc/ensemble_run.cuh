@@ -73,9 +73,10 @@ __device__ __forceinline__ int kepler_drift(SysState<N>& s, const double* m, dou
       const double mu = G * (cum + m[i]);
       cum += m[i];
       double rx = jx[i], ry = jy[i], ux = jvx[i], uy = jvy[i];
-      const int it = EXACT ? kepler_exact(rx, ry, ux, uy, mu, tau) : kepler_reference(rx, ry, ux, uy, mu, tau);
+      int done = 0;
+      const int it = EXACT ? kepler_exact(rx, ry, ux, uy, mu, tau) : kepler_reference(rx, ry, ux, uy, mu, tau, done);
       worst = max(worst, it);
-      iters += min(it, 64);
+      iters += EXACT ? min(it, 64) : done;
       jx[i] = rx; jy[i] = ry; jvx[i] = ux; jvy[i] = uy;
     }
   }
@@ -251,6 +252,7 @@ __host__ __device__ constexpr bool use_pairlane() { return N >= 5 && MODE != NB_
 template <int N, int MODE, bool GUARD, bool EXACT>
 __global__ void __launch_bounds__(128) ensemble_main_kernel(RunArgs a, int write_state) {
   const int bid = (int)blockIdx.x + a.block0;                          // logical CTA (the launch may be split head / rest)
+  stamp_begin(a.tstamp);
   if (MODE != NB_MODE_WHFAST && bid < a.group_blocks) {                // latency-optimised mappings for the n_sub-heavy head
     if constexpr (use_pairlane<N, MODE>()) {
       __shared__ __align__(16) double pl_smem[PairLane<N>::SMEM_DOUBLES];
@@ -258,6 +260,7 @@ __global__ void __launch_bounds__(128) ensemble_main_kernel(RunArgs a, int write
     } else {
       group_body<N, MODE == NB_MODE_WHFAST ? NB_MODE_VERLET : MODE, GUARD>(a, 0, write_state, bid);   // one body per lane
     }
+    stamp_end(a.tstamp);
     return;
   }
   const int nh = (a.group_blocks > 0) ? min(*a.n_heavy, a.B) : 0;
@@ -336,6 +339,7 @@ __global__ void __launch_bounds__(128) ensemble_main_kernel(RunArgs a, int write
     f[NB_F_TIDAL_MEAN] = n_samp > 0 ? 0.0 : nan;  // integrator.py:48 -- _last_tr_hessian is never updated
     f[NB_F_TIDAL_MAX] = n_samp > 0 ? 0.0 : nan;
   }
+  stamp_end(a.tstamp);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -781,7 +781,7 @@ __device__ __noinline__ double hs_eps_target_sh(const HsSh<N>* sh, double eps_cu
 struct HsArgs {
   const double* m; double* q; double* v; double G; int B; unsigned flags; double dt; int n_steps; int sample_interval;
   int n_megno; const int32_t* n_sub; const int32_t* perm; const double* raw_dr; const double* raw_dv; double* eps_pi;
-  const double* hs; double* dyn; int32_t* status; double* work;
+  const double* hs; double* dyn; int32_t* status; double* work; unsigned long long* tstamp;
 };
 
 template <int N>
@@ -822,6 +822,7 @@ __global__ void __launch_bounds__(128, (N <= 3 ? 6 : (N <= 4 ? 5 : (N <= 6 ? 3 :
   const int lane = lane_full & (LPS - 1);
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp * SPW >= a.B) return;                        // warp-uniform
+  stamp_begin(a.tstamp);
   // an odd tail slot shadows the warp's first system (same arithmetic, no global writes) so the warp stays converged
   const int slot = warp * SPW + lane_full / LPS;
   const bool live = slot < a.B;
@@ -985,6 +986,7 @@ __global__ void __launch_bounds__(128, (N <= 3 ? 6 : (N <= 4 ? 5 : (N <= 6 ? 3 :
   }
   const double sweeps_tot = grp_sum<LPS>((double)sweeps);
   __syncwarp();
+  stamp_end(a.tstamp);
   if (lane != 0 || !live) return;
   bool finite = is_finite(eps) && is_finite(pi);
 #pragma unroll
@@ -1202,9 +1204,9 @@ __global__ void __launch_bounds__(128) hamsoft_probe_kernel(const double* m_, co
 int hamsoft_run(const double* m, double* q, double* v, double G, int B, int N, unsigned flags, double dt, int n_steps,
                 int sample_interval, int n_megno, const int32_t* n_sub, const int32_t* perm, const double* raw_dr,
                 const double* raw_dv, double* eps_pi, const double* hs, double* dyn, int32_t* status, double* work,
-                cudaStream_t st) {
+                unsigned long long* tstamp, cudaStream_t st) {
   HsArgs a{m, q, v, G, B, flags, dt, n_steps, sample_interval, n_megno, n_sub, perm, raw_dr, raw_dv, eps_pi, hs, dyn,
-           status, work};
+           status, work, tstamp};
   NB_HS_DISPATCH(N, (hamsoft_run_kernel<NN><<<hs_run_blocks<NN>(a.B), 128, 0, st>>>(a)));
   NB_CUDA_CHECK(cudaGetLastError());
   return NB_OK;

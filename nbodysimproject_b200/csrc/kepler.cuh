@@ -67,7 +67,7 @@ __device__ __forceinline__ void cfunc_reference(double z_in, sd& c0, sd& c1, sd&
 
 // kepler_solver.py:48-91.  Returns the Newton iteration count (64 = cap reached).
 __device__ __forceinline__ int kepler_reference(double& rx, double& ry, double& vx, double& vy, double mu_in,
-                                                double dt_in) {
+                                                double dt_in, int& executed) {
   const sd r_x(rx), r_y(ry), v_x(vx), v_y(vy), mu(mu_in), dt(dt_in);
   const sd r0(hypot(rx, ry));
   if (r0.v < 1e-14) {
@@ -110,6 +110,7 @@ __device__ __forceinline__ int kepler_reference(double& rx, double& ry, double& 
     // the one with the parity of 64.  Detected after ~8 iterations instead of running all 64 in lock-step per warp.
     if (chi_new.v == x2) {
       if (((64 - it) & 1) == 0) chi = chi_new;
+      executed += it - 64;                       // counted work = iterations actually executed, not the reference's 64
       it = 64;
       break;
     }
@@ -118,6 +119,7 @@ __device__ __forceinline__ int kepler_reference(double& rx, double& ry, double& 
   }
   // the reference's exit test is exact equality, so running into the 64-iteration cap while hovering within a
   // few ulps of the root is normal; only a cap hit with a still-moving iterate is reported (as 65)
+  executed += it;
   if (it >= 64 && !(last_step <= 1e-9 * fabs(chi.v))) it = 65;
   const sd z = alpha * chi * chi;
   cfunc_reference(z.v, c0, c1, c2, c3);

@@ -73,16 +73,6 @@ def variational_batched(q, m, s2, dr, G: float = 1.0, device=None):
     return da
 
 
-def _ev_handle(ev):
-    """cudaEvent_t of a torch.cuda.Event (created lazily by torch: record it once before first use)."""
-    import ctypes
-    h = ev.cuda_event
-    if not h:
-        ev.record()
-        h = ev.cuda_event
-    return ctypes.c_void_p(h)
-
-
 # ---------------------------------------------------------------------------------------------
 # one (N, mode, G) bucket resident on the device
 # ---------------------------------------------------------------------------------------------
@@ -149,8 +139,9 @@ class DeviceBucket:
                                              L.stream_ptr()), "nb_sort_by_nsub")
 
     def run(self, dt, n_steps, sample_interval=0, n_megno=0, raw_dr=None, raw_dv=None, flags=0, want_dyn=True,
-            eps_pi=None, hs_params=None, work=None, ev_main=None):
-        """`ev_main` = (begin, end) torch.cuda.Event pair recorded around the main-phase launches.  `work` (optional float64 [B, 2] device tensor) receives the counted work of the run: whfast {Newton
+            eps_pi=None, hs_params=None, work=None, t_main=None):
+        """`t_main` = int64 device tensor [2] initialised to {2^63-1, 0}: earliest start / latest end of the main-phase
+        kernels in %globaltimer ns.  `work` (optional float64 [B, 2] device tensor) receives the counted work of the run: whfast {Newton
         iterations, Kepler solves}, ham_soft {Jacobi sweeps, S half-flows} (nb_ensemble_run_counted_f64)."""
         torch = self.torch
         dyn = torch.empty((self.B, L.N_DYN), dtype=torch.float64, device=self.device) if want_dyn else None
@@ -161,8 +152,7 @@ class DeviceBucket:
                 L.ptr(self.m), L.ptr(self.q), L.ptr(self.v), L.ptr(self.eps), self.G, self.B, self.N, self.mode,
                 int(flags), float(dt), int(n_steps), int(sample_interval), int(n_megno), L.ptr(self.n_sub),
                 L.ptr(self.perm), L.ptr(self._bins[64:]) if self.perm is not None else None, L.ptr(rdr), L.ptr(rdv),
-                L.ptr(eps_pi), L.ptr(hs_params), L.ptr(dyn), L.ptr(self.status), L.ptr(work),
-                _ev_handle(ev_main[0]) if ev_main else None, _ev_handle(ev_main[1]) if ev_main else None, L.stream_ptr()),
+                L.ptr(eps_pi), L.ptr(hs_params), L.ptr(dyn), L.ptr(self.status), L.ptr(work), L.ptr(t_main), L.stream_ptr()),
                 "nb_ensemble_run_counted_f64")
         return dyn
 

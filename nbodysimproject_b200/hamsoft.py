@@ -80,9 +80,9 @@ class HamSoftBucket:
         self.bk.sort()
 
     def run(self, dt, n_steps, sample_interval=0, n_megno=0, raw_dr=None, raw_dv=None, flags=L.RUN_WRITE_STATE,
-            want_dyn=False, work=None, ev_main=None):
+            want_dyn=False, work=None, t_main=None):
         dyn = self.bk.run(dt, n_steps, sample_interval, n_megno, raw_dr, raw_dv, flags, want_dyn,
-                          eps_pi=self.eps_pi, hs_params=self.hs, work=work, ev_main=ev_main)
+                          eps_pi=self.eps_pi, hs_params=self.hs, work=work, t_main=t_main)
         if n_steps + n_megno > 0:
             self.bump_mu(dt)
         return dyn
