@@ -66,6 +66,7 @@ enum {
   NB_F_VARL_MEAN, NB_F_VARL_MAX, NB_F_TIDAL_MEAN, NB_F_TIDAL_MAX, NB_F_MEGNO, NB_F_LYAP_TIME,
   NB_F_E0, NB_F_E1, NB_F_L0, NB_F_L1, NB_F_T_END, NB_N_DYN
 };
+#define NB_N_DYN_USER 17   /* the columns a reference user sees; E0/E1/L0/L1/t_end behind them are parity taps */
 
 /* columns of static_features[B][NB_N_STATIC] (dynamical_features.py:27-155, in the reference's order) */
 enum {
@@ -194,14 +195,57 @@ int nb_ensemble_analyze_host(const double* m, const double* q, double* v, const 
                              const double* raw_dv, double* dyn_features, double* static_features,
                              int32_t* n_sub_out, int32_t* status, int device);
 
-/* asynchronous form: enqueues everything on workspace slot `slot` (0..7, each with its own stream and
- * device buffers) and returns; host buffers must stay alive (and should be pinned) until nb_host_sync(slot).
- * Several buckets in flight on different slots overlap their copies and kernels. */
+/* asynchronous form: enqueues everything on workspace slot `slot` (0..15, each with its own copy-in / compute /
+ * copy-out streams and device buffers) and returns; host buffers must stay alive (and should be pinned) until
+ * nb_host_sync(slot).  Several buckets -- and consecutive batches -- in flight on different slots overlap their copies
+ * and kernels.  The caller's current CUDA device is left unchanged. */
 int nb_ensemble_analyze_host_async(const double* m, const double* q, double* v, const double* eps, double G,
                              int B, int N, int mode, unsigned prep_flags, double kick_dt, double sched_dt,
                              double dt, int n_steps, int n_megno, int split_n_max, const double* raw_dr,
                              const double* raw_dv, double* dyn_features, double* static_features,
                              int32_t* n_sub_out, int32_t* status, int device, int slot);
+
+/* extended form: the same call with options.  This is the entry point for the reference's DEFAULT integrator mode
+ * (sim_config.py:38 integrator_mode = "ham_soft", what ml_training_pipeline.py:77-84, 211 runs) and for classic
+ * adaptive softening:
+ *   mode == NB_MODE_HAMSOFT : eps[B] is the constructor softening; the call performs the constructor work of
+ *       hamiltonian_softening_integrator.py:47-141 (COM removal if NB_PREP_REMOVE_COM, SimConfig-default parameters
+ *       unless opts->hs_params, calibration unless NB_HOST_HS_NO_CALIBRATE, frozen schedule for sched_dt and again for
+ *       dt when they differ by > 1 %) and then run_stability_analysis.  opts->eps_pi (in/out) overrides the start state.
+ *   NB_HOST_ADAPTIVE (verlet / yoshida4): classic adaptive softening, opts->soft_par[B][3] = {s0, min_softening,
+ *       softening_scale}; opts->eps_start / eps_energy default to eps (softening_manager.py:298-336, 423-471, 541-547).
+ *   NB_HOST_COMPACT_DYN   : dyn_features is [B][NB_N_DYN_USER] (no E0/E1/L0/L1/t_end taps): 23 % fewer D2H bytes
+ *   NB_HOST_KEEP_V        : do not write the kicked velocities back into v (the reference's snapshot() mutation)
+ *   NB_HOST_DEVICE_TANGENT: draw the MEGNO tangent vectors on the device (Philox4x32-10 keyed by opts->tangent_seed,
+ *       counted by opts->first_index + system index) instead of reading raw_dr / raw_dv: 45 % fewer H2D bytes.  The
+ *       host-draw form stays the one that reproduces the reference's np.random.randn stream (evolution_features.py:37-44).
+ *   opts->n_chunks: cut the bucket into chunks that pipeline H2D -> kernels -> D2H inside the call (0 / 1 = off; pays
+ *       for buckets without sub-step-heavy tails).  Results do not depend on it (bit-identical). */
+#define NB_HOST_COMPACT_DYN 1u
+#define NB_HOST_KEEP_V 2u
+#define NB_HOST_DEVICE_TANGENT 4u
+#define NB_HOST_ADAPTIVE 8u
+#define NB_HOST_HS_NO_CALIBRATE 16u
+typedef struct nb_host_opts {
+  uint32_t size;             /* sizeof(nb_host_opts) of the caller (versioning) */
+  uint32_t flags;            /* NB_HOST_* */
+  int32_t n_chunks;          /* 0 or 1 = one piece */
+  int32_t barrier_exponent;  /* adaptive: SimConfig.barrier_exponent (0 = 5) */
+  uint64_t tangent_seed;     /* NB_HOST_DEVICE_TANGENT */
+  uint64_t first_index;      /* global index of system 0 (sharded ensembles draw the same tangents as unsharded) */
+  const double* hs_params;   /* ham_soft: HOST [B][NB_HS_NPARAM], NULL = SimConfig defaults */
+  double* eps_pi;            /* ham_soft: HOST [B][2] (epsilon, pi) in/out, NULL = (max(s0, eps_min), 0), not returned */
+  const double* soft_par;    /* adaptive: HOST [B][3] */
+  const double* eps_start;   /* adaptive: HOST [B] softening the restored copy starts from (NULL = eps) */
+  const double* eps_energy;  /* adaptive: HOST [B] constant epsilon of the energy diagnostics (NULL = eps) */
+  double* energy_delta;      /* adaptive: HOST [B] out, softening_energy_delta (may be NULL) */
+  double k_wall;             /* adaptive: SimConfig.k_wall (0 = 1e9) */
+} nb_host_opts;
+int nb_ensemble_analyze_host_ex(const double* m, const double* q, double* v, const double* eps, double G,
+                             int B, int N, int mode, unsigned prep_flags, double kick_dt, double sched_dt,
+                             double dt, int n_steps, int n_megno, int split_n_max, const double* raw_dr,
+                             const double* raw_dv, double* dyn_features, double* static_features,
+                             int32_t* n_sub_out, int32_t* status, int device, int slot, const nb_host_opts* opts);
 int nb_host_sync(int slot);
 
 /* ---- large-N direct sum (new capability, same formula as forces.py:63-75 / 77-112 / potential.py:23-64),
@@ -251,6 +295,9 @@ int nb_largeN_set_variant(int variant);
 #define NB_GEN_PLANETARY_TTV 5
 int nb_generate_ensemble_f64(int cohort, int N, int B, uint64_t seed, uint64_t first_index, double* m, double* q, double* v,
                              double* eps, void* stream);
+/* the two randn(N, 2) draws per system of EvolutionFeatures.compute_megno (evolution_features.py:37-44) from the same
+ * counter-based generator: dr[B][N][2], dv[B][N][2] ~ N(0, 1), a function of (seed, first_index + system) only */
+int nb_generate_tangent_f64(int N, int B, uint64_t seed, uint64_t first_index, double* dr, double* dv, void* stream);
 
 /* ---- stability-classifier inference on the feature tensors (model_zoo.py:18-33 MLP F-128-64-1 with ReLU;
  *      train_mlp.py:141-217 sigmoid + threshold; stability_dataset.py:83-85 nan_to_num; StandardScaler).

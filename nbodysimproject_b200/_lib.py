@@ -44,10 +44,32 @@ EXPORTS = [
     "nb_last_error", "nb_version", "nb_pair_batched_f64", "nb_variational_batched_f64",
     "nb_ensemble_prepare_f64", "nb_ensemble_run_f64", "nb_ensemble_run_counted_f64", "nb_sort_by_nsub", "nb_ensemble_set_heavy_nsub",
     "nb_ensemble_run_adaptive_f64", "nb_ensemble_analyze_adaptive_f64", "nb_ensemble_analyze_host",
-    "nb_ensemble_analyze_host_async", "nb_host_sync", "nb_hamsoft_setup_f64", "nb_hamsoft_probe_f64",
+    "nb_ensemble_analyze_host_async", "nb_ensemble_analyze_host_ex", "nb_host_sync", "nb_generate_tangent_f64", "nb_hamsoft_setup_f64", "nb_hamsoft_probe_f64",
     "nb_largeN_accel_f32", "nb_largeN_kick_drift_f32", "nb_largeN_set_variant", "nb_largeN_pass_f32", "nb_mlp_classify_f32", "nb_generate_ensemble_f64",
     "nb_peak_flops",
 ]
+
+HOST_COMPACT_DYN, HOST_KEEP_V, HOST_DEVICE_TANGENT, HOST_ADAPTIVE, HOST_HS_NO_CALIBRATE = 1, 2, 4, 8, 16
+N_DYN_USER = 17
+
+
+class HostOpts(C.Structure):
+    """nb_host_opts (include/nbody_b200.h)."""
+    _fields_ = [("size", C.c_uint32), ("flags", C.c_uint32), ("n_chunks", C.c_int32), ("barrier_exponent", C.c_int32),
+                ("tangent_seed", C.c_uint64), ("first_index", C.c_uint64), ("hs_params", C.c_void_p),
+                ("eps_pi", C.c_void_p), ("soft_par", C.c_void_p), ("eps_start", C.c_void_p), ("eps_energy", C.c_void_p),
+                ("energy_delta", C.c_void_p), ("k_wall", C.c_double)]
+
+    def __init__(self, **kw):
+        super().__init__()
+        self.size = C.sizeof(HostOpts)
+        self._keep = []
+        for k, val in kw.items():
+            if hasattr(val, "ctypes") or hasattr(val, "data_ptr"):
+                self._keep.append(val)                      # keep the buffer alive as long as the struct
+                val = val.data_ptr() if hasattr(val, "data_ptr") else val.ctypes.data
+            setattr(self, k, val)
+
 
 _lib = None
 
@@ -81,6 +103,8 @@ def load():
     lib.nb_ensemble_analyze_adaptive_f64.argtypes = [p, p, p, p, p, p, d, i, i, i, d, i, i, i, p, p, p, d, i, p, p, p, p]
     lib.nb_ensemble_analyze_host.argtypes = [p, p, p, p, d, i, i, i, u, d, d, d, i, i, i, p, p, p, p, p, p, i]
     lib.nb_ensemble_analyze_host_async.argtypes = lib.nb_ensemble_analyze_host.argtypes + [i]
+    lib.nb_ensemble_analyze_host_ex.argtypes = lib.nb_ensemble_analyze_host.argtypes + [i, p]
+    lib.nb_generate_tangent_f64.argtypes = [i, i, C.c_uint64, C.c_uint64, p, p, p]
     lib.nb_host_sync.argtypes = [i]
     lib.nb_hamsoft_setup_f64.argtypes = [p, p, d, i, i, u, d, p, p, p, p]
     lib.nb_hamsoft_probe_f64.argtypes = [p, p, p, d, i, i, p, p, p, p]

@@ -40,6 +40,7 @@ int mlp_classify(const double* dyn, const double* stat, const int32_t* idx, int 
 int ensemble_run_adaptive(const double* m, double* q, double* v, double* eps, const double* soft_par, double G, int B,
                           int N, int mode, double dt, int n_steps, const int32_t* n_sub, double k_wall, int n_exp,
                           double* e_delta, double* eps_hist, int32_t* status, cudaStream_t st);
+int generate_tangent(int N, int B, uint64_t seed, uint64_t first, double* dr, double* dv, cudaStream_t st);
 int largeN_accel(const float* xym, int n_total, int i0, int ni, float eps, float G, float* acc, double* sums,
                  cudaStream_t st);
 int largeN_set_variant(int variant);
@@ -140,95 +141,51 @@ __global__ void __launch_bounds__(256) peak_kernel(int iters, float seed, float*
 
 static int peak_flops(int which, int device, double* tflops) {
   if (!tflops || which < 0 || which > 4) { set_error("nb_peak_flops: bad arguments"); return NB_ERR_ARG; }
-  NB_CUDA_CHECK(cudaSetDevice(device));
-  int sms = 0;
-  NB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  // the caller's current device is restored on every path; resources are released on every path
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaError_t err = cudaSetDevice(device);
   float* out = nullptr;
-  NB_CUDA_CHECK(cudaMalloc(&out, 4));
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int sms = 0;
+  double best = 0.0;
+  if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  if (err == cudaSuccess) err = cudaMalloc(&out, 4);
+  if (err == cudaSuccess) err = cudaEventCreate(&e0);
+  if (err == cudaSuccess) err = cudaEventCreate(&e1);
   const int blocks = sms * 8, threads = 256;
   const int iters = 4096;
-  cudaEvent_t e0, e1;
-  NB_CUDA_CHECK(cudaEventCreate(&e0));
-  NB_CUDA_CHECK(cudaEventCreate(&e1));
-  double best = 0.0;
-  for (int rep = 0; rep < 6; ++rep) {
-    NB_CUDA_CHECK(cudaEventRecord(e0));
+  for (int rep = 0; rep < 6 && err == cudaSuccess; ++rep) {
+    err = cudaEventRecord(e0, st);
+    if (err != cudaSuccess) break;
     switch (which) {
-      case 0: peak_kernel<0><<<blocks, threads>>>(iters, 0.f, out); break;
-      case 1: peak_kernel<1><<<blocks, threads>>>(iters, 0.f, out); break;
-      case 2: peak_kernel<2><<<blocks, threads>>>(iters, 0.f, out); break;
-      case 3: peak_kernel<3><<<blocks, threads>>>(iters, 0.f, out); break;
-      default: peak_kernel<4><<<blocks, threads>>>(iters, 0.f, out); break;
+      case 0: peak_kernel<0><<<blocks, threads, 0, st>>>(iters, 0.f, out); break;
+      case 1: peak_kernel<1><<<blocks, threads, 0, st>>>(iters, 0.f, out); break;
+      case 2: peak_kernel<2><<<blocks, threads, 0, st>>>(iters, 0.f, out); break;
+      case 3: peak_kernel<3><<<blocks, threads, 0, st>>>(iters, 0.f, out); break;
+      default: peak_kernel<4><<<blocks, threads, 0, st>>>(iters, 0.f, out); break;
     }
-    NB_CUDA_CHECK(cudaEventRecord(e1));
-    NB_CUDA_CHECK(cudaEventSynchronize(e1));
+    err = cudaEventRecord(e1, st);
+    if (err == cudaSuccess) err = cudaEventSynchronize(e1);
     float ms = 0.f;
-    NB_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e0, e1);
+    if (err != cudaSuccess) break;
     const double per_thread = which == 0 ? 8.0 * 2 : which == 1 ? 16.0 * 2 : which == 2 ? 16.0 * 4 : 8.0;
     const double ops = per_thread * iters * (double)blocks * threads;
     const double t = ops / (ms * 1e-3) * 1e-12;
     if (rep > 0 && t > best) best = t;
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(out);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (out) cudaFree(out);
+  if (st) cudaStreamDestroy(st);
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
+  if (err != cudaSuccess) return cuda_fail(err, "nb_peak_flops");
   *tflops = best;
   return NB_OK;
 }
-
-// ---- cached workspaces for the *_host entry points: NB_HOST_SLOTS independent (stream, buffer) pairs so that
-// callers can keep several buckets in flight (H2D of one overlapping the kernels of another) -----------------
-constexpr int NB_HOST_SLOTS = 8;
-struct HostWs {
-  int device = -1;
-  cudaStream_t stream = nullptr;
-  cudaStream_t copy_stream = nullptr;   // early D2H of what is final after the prepare kernel (static features, kicked v, n_sub)
-  cudaEvent_t prep_done = nullptr;
-  cudaEvent_t copy_done = nullptr;      // end of the previous call's early D2H: the next call on this slot waits for it
-  void* buf = nullptr;
-  size_t cap = 0;
-};
-static HostWs g_ws[NB_HOST_SLOTS];
-static std::mutex g_ws_mu;
-
-static int ws_reserve(int slot, int device, size_t bytes) {
-  HostWs& w = g_ws[slot];
-  if (w.device != device) {
-    if (w.device >= 0) {
-      cudaSetDevice(w.device);
-      if (w.buf) cudaFree(w.buf);
-      if (w.stream) cudaStreamDestroy(w.stream);
-      if (w.copy_stream) cudaStreamDestroy(w.copy_stream);
-      if (w.prep_done) cudaEventDestroy(w.prep_done);
-      if (w.copy_done) cudaEventDestroy(w.copy_done);
-    }
-    w = HostWs();
-    NB_CUDA_CHECK(cudaSetDevice(device));
-    // high priority: everything of a bucket except the bulk of its main kernel (which ensemble_run_classic moves
-    // to a normal-priority side stream) should be dispatched ahead of other buckets' queued bulk CTAs
-    int prio_lo = 0, prio_hi = 0;
-    NB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    NB_CUDA_CHECK(cudaStreamCreateWithPriority(&w.stream, cudaStreamNonBlocking, prio_hi));
-    NB_CUDA_CHECK(cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
-    NB_CUDA_CHECK(cudaEventCreateWithFlags(&w.prep_done, cudaEventDisableTiming));
-    NB_CUDA_CHECK(cudaEventCreateWithFlags(&w.copy_done, cudaEventDisableTiming));
-    NB_CUDA_CHECK(cudaEventRecord(w.copy_done, w.copy_stream));
-    w.device = device;
-  }
-  NB_CUDA_CHECK(cudaSetDevice(device));
-  if (w.cap < bytes) {
-    NB_CUDA_CHECK(cudaStreamSynchronize(w.stream));
-    NB_CUDA_CHECK(cudaStreamSynchronize(w.copy_stream));
-    if (w.buf) cudaFree(w.buf);
-    w.buf = nullptr;
-    w.cap = 0;
-    NB_CUDA_CHECK(cudaMalloc(&w.buf, bytes));
-    w.cap = bytes;
-  }
-  return NB_OK;
-}
-
-static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace nb
 
@@ -328,95 +285,6 @@ int nb_sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* 
   return sort_by_nsub(n_sub, B, N, perm, workspace, (cudaStream_t)stream);
 }
 
-int nb_ensemble_analyze_host_async(const double* m, const double* q, double* v, const double* eps, double G, int B, int N,
-                             int mode, unsigned prep_flags, double kick_dt, double sched_dt, double dt, int n_steps,
-                             int n_megno, int split_n_max, const double* raw_dr, const double* raw_dv, double* dyn_features,
-                             double* static_features, int32_t* n_sub_out, int32_t* status, int device, int slot) {
-  if (slot < 0 || slot >= NB_HOST_SLOTS) { set_error("nb_ensemble_analyze_host_async: slot out of range"); return NB_ERR_ARG; }
-  if (!m || !q || !v || !eps || !dyn_features || B < 0 || N < NB_MIN_N || N > NB_MAX_N) { set_error("nb_ensemble_analyze_host: bad arguments"); return NB_ERR_ARG; }
-  if (mode == NB_MODE_HAMSOFT) { set_error("nb_ensemble_analyze_host: ham_soft goes through nb_ensemble_run_f64"); return NB_ERR_UNSUPPORTED; }
-  if (n_megno > 0 && (!raw_dr || !raw_dv)) { set_error("nb_ensemble_analyze_host: n_megno > 0 needs raw_dr/raw_dv"); return NB_ERR_ARG; }
-  if (B == 0) return NB_OK;
-  std::lock_guard<std::mutex> lock(g_ws_mu);
-  const size_t bn = (size_t)B * N;
-  const size_t sz_m = align256(bn * 8), sz_q = align256(bn * 16), sz_b = align256((size_t)B * 8);
-  const size_t sz_dyn = align256((size_t)B * NB_N_DYN * 8), sz_stat = align256((size_t)B * NB_N_STATIC * 8);
-  const size_t sz_i = align256((size_t)B * 4);
-  const size_t total = sz_m + 5 * sz_q + sz_b + sz_dyn + sz_stat + 3 * sz_i + 512;
-  int rc = ws_reserve(slot, device, total);
-  if (rc != NB_OK) return rc;
-  cudaStream_t st = g_ws[slot].stream;
-  char* p = (char*)g_ws[slot].buf;
-  double* d_m = (double*)p; p += sz_m;
-  double* d_q = (double*)p; p += sz_q;
-  double* d_v = (double*)p; p += sz_q;
-  double* d_dr = (double*)p; p += sz_q;
-  double* d_dv = (double*)p; p += sz_q;
-  double* d_vk = (double*)p; p += sz_q;      // kicked velocities, frozen for the early D2H while the run advances d_v
-  double* d_eps = (double*)p; p += sz_b;
-  double* d_dyn = (double*)p; p += sz_dyn;
-  double* d_stat = (double*)p; p += sz_stat;
-  int32_t* d_nsub = (int32_t*)p; p += sz_i;
-  int32_t* d_perm = (int32_t*)p; p += sz_i;
-  int32_t* d_status = (int32_t*)p; p += sz_i;
-  int32_t* d_bins = (int32_t*)p;
-  NB_CUDA_CHECK(cudaStreamWaitEvent(st, g_ws[slot].copy_done, 0));   // the workspace is reused: previous early D2H first
-  NB_CUDA_CHECK(cudaMemcpyAsync(d_m, m, bn * 8, cudaMemcpyHostToDevice, st));
-  NB_CUDA_CHECK(cudaMemcpyAsync(d_q, q, bn * 16, cudaMemcpyHostToDevice, st));
-  NB_CUDA_CHECK(cudaMemcpyAsync(d_v, v, bn * 16, cudaMemcpyHostToDevice, st));
-  NB_CUDA_CHECK(cudaMemcpyAsync(d_eps, eps, (size_t)B * 8, cudaMemcpyHostToDevice, st));
-  if (n_megno > 0) {
-    NB_CUDA_CHECK(cudaMemcpyAsync(d_dr, raw_dr, bn * 16, cudaMemcpyHostToDevice, st));
-    NB_CUDA_CHECK(cudaMemcpyAsync(d_dv, raw_dv, bn * 16, cudaMemcpyHostToDevice, st));
-  }
-  unsigned pf = prep_flags;
-  if (static_features) pf |= NB_PREP_STATIC_FEATURES; else pf &= ~NB_PREP_STATIC_FEATURES;
-  PrepArgs pa{d_m, d_q, d_v, d_eps, G, B, mode, pf, kick_dt, sched_dt, dt, split_n_max, nullptr, d_nsub, d_stat};
-  rc = ensemble_prepare(pa, N, st);
-  if (rc != NB_OK) return rc;
-  // Everything that is final after the prepare kernel goes back on the copy stream while the run is in flight:
-  // the kicked velocities (the reference mutates the caller's sims), the static features and n_sub -- 60 % of the
-  // D2H bytes, which would otherwise all queue up behind the run together with the dynamic features.
-  cudaStream_t cs = g_ws[slot].copy_stream;
-  const bool kicked = (pf & (NB_PREP_REMOVE_COM | NB_PREP_CTOR_KICK | NB_PREP_SNAPSHOT_KICK)) != 0;
-  if (kicked) NB_CUDA_CHECK(cudaMemcpyAsync(d_vk, d_v, bn * 16, cudaMemcpyDeviceToDevice, st));
-  NB_CUDA_CHECK(cudaEventRecord(g_ws[slot].prep_done, st));
-  NB_CUDA_CHECK(cudaStreamWaitEvent(cs, g_ws[slot].prep_done, 0));
-  if (kicked) NB_CUDA_CHECK(cudaMemcpyAsync(v, d_vk, bn * 16, cudaMemcpyDeviceToHost, cs));
-  if (static_features) NB_CUDA_CHECK(cudaMemcpyAsync(static_features, d_stat, (size_t)B * NB_N_STATIC * 8, cudaMemcpyDeviceToHost, cs));
-  if (n_sub_out) NB_CUDA_CHECK(cudaMemcpyAsync(n_sub_out, d_nsub, (size_t)B * 4, cudaMemcpyDeviceToHost, cs));
-  NB_CUDA_CHECK(cudaEventRecord(g_ws[slot].copy_done, cs));
-  rc = sort_by_nsub(d_nsub, B, N, d_perm, d_bins, st);
-  if (rc != NB_OK) return rc;
-  const int interval = n_steps / 100 > 1 ? n_steps / 100 : 1;
-  RunArgs ra{d_m, d_q, d_v, d_eps, G, B, NB_RUN_ENERGY, dt, n_steps, interval, n_megno, d_nsub, d_perm, d_bins + 64, 0, 0, 0, d_dr, d_dv, d_dyn, d_status, nullptr, nullptr};
-  rc = ensemble_run_classic(ra, N, mode, st);
-  if (rc != NB_OK) return rc;
-  NB_CUDA_CHECK(cudaMemcpyAsync(dyn_features, d_dyn, (size_t)B * NB_N_DYN * 8, cudaMemcpyDeviceToHost, st));
-  if (status) NB_CUDA_CHECK(cudaMemcpyAsync(status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-  return NB_OK;
-}
-
-int nb_host_sync(int slot) {
-  if (slot < 0 || slot >= NB_HOST_SLOTS) { set_error("nb_host_sync: slot out of range"); return NB_ERR_ARG; }
-  if (g_ws[slot].device < 0) return NB_OK;
-  NB_CUDA_CHECK(cudaSetDevice(g_ws[slot].device));
-  NB_CUDA_CHECK(cudaStreamSynchronize(g_ws[slot].stream));
-  NB_CUDA_CHECK(cudaStreamSynchronize(g_ws[slot].copy_stream));
-  return NB_OK;
-}
-
-int nb_ensemble_analyze_host(const double* m, const double* q, double* v, const double* eps, double G, int B, int N,
-                             int mode, unsigned prep_flags, double kick_dt, double sched_dt, double dt, int n_steps,
-                             int n_megno, int split_n_max, const double* raw_dr, const double* raw_dv, double* dyn_features,
-                             double* static_features, int32_t* n_sub_out, int32_t* status, int device) {
-  int rc = nb_ensemble_analyze_host_async(m, q, v, eps, G, B, N, mode, prep_flags, kick_dt, sched_dt, dt, n_steps, n_megno,
-                                          split_n_max, raw_dr, raw_dv, dyn_features, static_features, n_sub_out, status,
-                                          device, 0);
-  if (rc != NB_OK) return rc;
-  return nb_host_sync(0);
-}
-
 int nb_largeN_accel_f32(const float* xym, int n_total, int i0, int ni, float eps, float G, float* acc, double* sums,
                         void* stream) {
   return largeN_accel(xym, n_total, i0, ni, eps, G, acc, sums, (cudaStream_t)stream);
@@ -443,6 +311,10 @@ int nb_mlp_classify_f32(const double* dyn_features, const double* static_feature
 int nb_generate_ensemble_f64(int cohort, int N, int B, uint64_t seed, uint64_t first_index, double* m, double* q, double* v,
                              double* eps, void* stream) {
   return generate_ensemble(cohort, N, B, seed, first_index, m, q, v, eps, (cudaStream_t)stream);
+}
+
+int nb_generate_tangent_f64(int N, int B, uint64_t seed, uint64_t first_index, double* dr, double* dv, void* stream) {
+  return generate_tangent(N, B, seed, first_index, dr, dv, (cudaStream_t)stream);
 }
 
 int nb_peak_flops(int which, int device, double* tflops) { return peak_flops(which, device, tflops); }

@@ -177,6 +177,24 @@ __global__ void __launch_bounds__(128) generate_kernel(GenArgs a) {
   a.eps[t] = eps;
 }
 
+__global__ void __launch_bounds__(128) tangent_kernel(int N, int B, uint64_t seed, uint64_t first, double* dr, double* dv) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B) return;
+  Philox g(seed, 0x7a6e67ull, first + (uint64_t)t);       // its own stream: independent of the initial conditions
+  double* r = dr + (size_t)t * N * 2;
+  double* w = dv + (size_t)t * N * 2;
+  for (int i = 0; i < N; ++i) g.normal2(r[2 * i], r[2 * i + 1]);
+  for (int i = 0; i < N; ++i) g.normal2(w[2 * i], w[2 * i + 1]);
+}
+
+int generate_tangent(int N, int B, uint64_t seed, uint64_t first, double* dr, double* dv, cudaStream_t st) {
+  if (!dr || !dv || B < 0 || N < 1) { set_error("nb_generate_tangent_f64: bad arguments"); return NB_ERR_ARG; }
+  if (B == 0) return NB_OK;
+  tangent_kernel<<<(B + 127) / 128, 128, 0, st>>>(N, B, seed, first, dr, dv);
+  NB_CUDA_CHECK(cudaGetLastError());
+  return NB_OK;
+}
+
 int generate_ensemble(int cohort, int N, int B, uint64_t seed, uint64_t first, double* m, double* q, double* v, double* eps,
                       cudaStream_t st) {
   if (!m || !q || !v || !eps || B < 0 || cohort < 0 || cohort > 5 || (cohort == 1 && N != 3)) {

@@ -86,6 +86,7 @@ class BucketResult:
     v_kicked: Optional[np.ndarray]
     q_final: Optional[np.ndarray] = None
     v_final: Optional[np.ndarray] = None
+    extra: Optional[dict] = None
 
 
 class DeviceBucket:
@@ -208,6 +209,66 @@ def analyze_bucket(m, q, v, eps, G=1.0, mode="verlet", n_steps=1000, dt=0.01, an
     dyn = bk.run(dt, n_steps, interval, n_megno, raw_dr, raw_dv, flags=L.RUN_ENERGY)
     return BucketResult(dyn.cpu().numpy(), bk.static.cpu().numpy() if want_static else None,
                         bk.n_sub.cpu().numpy(), bk.status.cpu().numpy(), v_kicked)
+
+
+def analyze_host(m, q, v, eps, G=1.0, mode="verlet", n_steps=1000, dt=0.01, n_megno=0, raw_dr=None, raw_dv=None,
+                 prep_flags=L.PREP_SNAPSHOT_KICK, kick_dt=0.01, sched_dt=0.01, split_n_max=50, device=None, slot=0,
+                 want_static=True, compact=False, keep_v=False, tangent_seed=None, first_index=0, n_chunks=0,
+                 hs_params=None, eps_pi=None, soft_par=None, eps_start=None, eps_energy=None, k_wall=0.0,
+                 barrier_exponent=0, calibrate=True) -> BucketResult:
+    """One nb_ensemble_analyze_host_ex call (HOST buffers in and out; chunk-pipelined H2D -> kernels -> D2H).
+    mode "ham_soft" runs the reference's default integrator (constructor calibration + analysis in the same call);
+    `soft_par` switches on classic adaptive softening.  `v` is mutated like the reference's snapshot() unless keep_v.
+    Returns BucketResult with `extra` = dict(eps_pi=..., energy_delta=...) where applicable."""
+    torch = L.require_cuda()
+    dev_index = _dev(device).index or 0
+    m = np.ascontiguousarray(m, dtype=np.float64)
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    if not (isinstance(v, np.ndarray) and v.dtype == np.float64 and v.flags.c_contiguous and v.flags.writeable):
+        v = np.array(v, dtype=np.float64, order="C")
+    B, N = m.shape
+    eps = np.ascontiguousarray(np.broadcast_to(np.asarray(eps, dtype=np.float64), (B,)))
+    flags = (L.HOST_COMPACT_DYN if compact else 0) | (L.HOST_KEEP_V if keep_v else 0)
+    kw = dict(n_chunks=int(n_chunks), first_index=int(first_index), k_wall=float(k_wall),
+              barrier_exponent=int(barrier_exponent))
+    if tangent_seed is not None:
+        flags |= L.HOST_DEVICE_TANGENT
+        kw["tangent_seed"] = int(tangent_seed)
+    if not calibrate:
+        flags |= L.HOST_HS_NO_CALIBRATE
+    ep = ed = None
+    if hs_params is not None:
+        kw["hs_params"] = np.ascontiguousarray(hs_params, dtype=np.float64)
+    if eps_pi is not None:
+        ep = np.array(eps_pi, dtype=np.float64, order="C")
+        kw["eps_pi"] = ep
+    if soft_par is not None:
+        flags |= L.HOST_ADAPTIVE
+        kw["soft_par"] = np.ascontiguousarray(soft_par, dtype=np.float64)
+        ed = np.zeros((B,))
+        kw["energy_delta"] = ed
+        if eps_start is not None:
+            kw["eps_start"] = np.ascontiguousarray(np.broadcast_to(np.asarray(eps_start, dtype=np.float64), (B,)))
+        if eps_energy is not None:
+            kw["eps_energy"] = np.ascontiguousarray(np.broadcast_to(np.asarray(eps_energy, dtype=np.float64), (B,)))
+    opts = L.HostOpts(flags=flags, **kw)
+    dyn = np.empty((B, L.N_DYN_USER if compact else L.N_DYN))
+    stat = np.empty((B, L.N_STATIC)) if want_static else None
+    nsub = np.empty((B,), dtype=np.int32)
+    status = np.empty((B,), dtype=np.int32)
+    rdr = np.ascontiguousarray(raw_dr, dtype=np.float64) if (n_megno > 0 and tangent_seed is None) else None
+    rdv = np.ascontiguousarray(raw_dv, dtype=np.float64) if (n_megno > 0 and tangent_seed is None) else None
+    import ctypes
+    lib = L.load()
+    L.check(lib.nb_ensemble_analyze_host_ex(
+        L.ptr(m), L.ptr(q), L.ptr(v), L.ptr(eps), float(G), B, N, L.MODES[mode] if isinstance(mode, str) else int(mode),
+        int(prep_flags), float(kick_dt), float(sched_dt), float(dt), int(n_steps), int(n_megno), int(split_n_max),
+        L.ptr(rdr), L.ptr(rdv), L.ptr(dyn), L.ptr(stat), L.ptr(nsub), L.ptr(status), dev_index, int(slot),
+        ctypes.byref(opts)), "nb_ensemble_analyze_host_ex")
+    L.check(lib.nb_host_sync(int(slot)), "nb_host_sync")
+    r = BucketResult(dyn, stat, nsub, status, v)
+    r.extra = dict(eps_pi=ep, energy_delta=ed)
+    return r
 
 
 def advance_bucket(m, q, v, eps, h_sub_ref, G=1.0, mode="verlet", dt=0.01, n_steps=1, split_n_max=50, device=None,
