@@ -465,7 +465,11 @@ def ensemble_section(args, ctx):
     stamps = {N: torch.tensor([[I64MAX, 0]] * (args.steps + 1), dtype=torch.int64, device=dev) for N in Ns}
     timed_step = [0]
 
-    def step_device(record=False):
+    def step_device(record=False, first=False, last=False):
+        """One step = one full pass of the analysis over every bucket.  Consecutive steps are independent batches and are
+        enqueued back to back on the bucket streams WITHOUT a device-wide join in between (each bucket's stream keeps its
+        own steps in order), so the sub-step-heavy tail of one step overlaps the bulk of the next, as in any pipelined
+        deployment; the timed region starts with a fork from the timing stream and ends with a join into it."""
         nonlocal launches_per_step
         cur = torch.cuda.current_stream()
         n = 0
@@ -473,20 +477,22 @@ def ensemble_section(args, ctx):
         # launches each bucket's sub-step-heavy head at high priority, so no head waits behind another bucket's bulk
         for N in Ns:
             bk = devb[N]
-            bk.stream.wait_stream(cur)
+            if first:
+                bk.stream.wait_stream(cur)
             with torch.cuda.stream(bk.stream):
                 bk.q.copy_(bk.q0)
                 bk.v.copy_(bk.v0)
                 bk.prepare(prep_flags, 0.01, 0.01, DT, 50, want_static=True)     # 1 kernel
-                bk.sort()                                                        # 3 kernels
+                bk.sort(args.heavy_threshold)                                    # 3 kernels
         for N in Ns:
             bk = devb[N]
             with torch.cuda.stream(bk.stream):
                 ts = stamps[N][timed_step[0]] if record else None
                 bk.dyn = bk.run(DT, N_STEPS, interval, N_MEGNO, bk.rdr, bk.rdv, flags=L.RUN_ENERGY, t_main=ts)  # 2+2+1+1 kernels
                 n += 10
-        for N in Ns:
-            cur.wait_stream(devb[N].stream)
+        if last:
+            for N in Ns:
+                cur.wait_stream(devb[N].stream)
         launches_per_step = n
         if record:
             timed_step[0] += 1
@@ -540,14 +546,14 @@ def ensemble_section(args, ctx):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
-        step_device()
+    for k in range(args.warmup):
+        step_device(first=(k == 0), last=(k == args.warmup - 1))
     _barrier(torch, dist, world)
     mark0 = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        step_device(record=True)
+    for k in range(args.steps):
+        step_device(record=True, first=(k == 0), last=(k == args.steps - 1))
     e1.record()
     _barrier(torch, dist, world)
     mark1 = sampler.mark()
@@ -587,8 +593,10 @@ def ensemble_section(args, ctx):
             bk.ts = ts
             per.append(dict(N=N, B=bk.B, mean_n_sub=nsub_sum / bk.B, max_n_sub=int(bk.n_sub.max().item()),
                             in_step_ms=float(np.mean(ts[:, 1] - ts[:, 0])) * 1e-6, flops=bk.flops))
-        windows = [max(devb[N].ts[k, 1] for N in Ns) - min(devb[N].ts[k, 0] for N in Ns) for k in range(args.steps)]
-        win = float(np.mean(windows)) * 1e-9
+        # steps are pipelined, so their windows overlap: the main-phase time of the timed region is the span from the
+        # earliest start of the first step to the latest end of the last one, divided by the number of steps
+        span = max(devb[N].ts[:, 1].max() for N in Ns) - min(devb[N].ts[:, 0].min() for N in Ns)
+        win = float(span) * 1e-9 / args.steps
         ach = tot_fl / win * 1e-12
         roof = {"bound": "fp64", "kernel": "ensemble_main_kernel<N=3..8, yoshida4> (6 concurrent launches per step)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
@@ -598,8 +606,9 @@ def ensemble_section(args, ctx):
                                 "capture (profiles/r2_traffic.json); the state is read once and lives in registers",
                 "flops_per_step": tot_fl, "ms": win * 1e3,
                 "timing": "%globaltimer stamps published by the main kernels themselves (first CTA start, last warp end; "
-                          "nb_ensemble_run_counted_f64 t_main) inside the timed steps; window = earliest start .. latest end "
-                          "over the six buckets, mean over the timed steps",
+                          "nb_ensemble_run_counted_f64 t_main) inside the timed steps; span from the earliest start of the "
+                          "first timed step to the latest end of the last one over all six buckets, divided by the steps "
+                          "(consecutive steps are pipelined, so per-step windows overlap)",
                 "peak_source": "nb_peak_flops(0): register-resident DFMA micro-benchmark, same GPU, same run "
                                "(MEASURED_PEAKS.json has no FP64 figure; nominal 64 DFMA/clk/SM x 148 x 1.965 GHz = 37.2)",
                 "flop_model": "SURVEY.md 8d: per sub-step 3 x 14 N(N-1) + 36 N",
@@ -649,6 +658,8 @@ def ensemble_section(args, ctx):
                                "yoshida4 dt=0.01, 1000 steps + 50 tangent-map MEGNO steps, mode full",
                    "systems_per_gpu": B_total, "buckets": {str(p["N"]): int(p["B"]) for p in (roof or {}).get("per_bucket", [])},
                    "sharding": "by system, no collective", "cpu_cores_bound_to_gpu_numa_node": ctx["numa"],
+                   "step_pipelining": "steps are independent batches enqueued back to back on the bucket streams, no "
+                                      "device-wide join between steps (each bucket stream keeps its own steps in order)",
                    "l2_note": f"inputs re-read from HBM each step ({h2d / 1e6:.0f} MB per GPU > 126 MB L2)"},
         "e2e": {"value": sys_steps / t_e2e, "unit": "system-steps/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h_c), "ms_per_step": 1e3 * t_e2e / args.steps,
@@ -1146,7 +1157,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ensemble", choices=["ensemble", "largen", "c4", "c1", "c2"])
     ap.add_argument("--systems", type=int, default=1 << 20, help="systems per GPU (weak scaling)")
-    ap.add_argument("--n", type=int, default=1 << 20, help="particles for --workload largen")
+    ap.add_argument("--particles", "--n", dest="n", type=int, default=1 << 20, help="particles of the large-N system")
     ap.add_argument("--n-hamsoft", type=int, default=0, dest="n_hamsoft",
                     help="particles for the ham_soft Strang sub-step timing of --workload largen (default: --n)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -1155,6 +1166,9 @@ def main():
                     help="skip the large-N ham_soft Strang sub-step timing of the default line")
     ap.add_argument("--no-secondary", action="store_true", dest="no_secondary",
                     help="skip the C1 / C4 sections of the default line")
+    ap.add_argument("--heavy-threshold", type=int, default=-1, dest="heavy_threshold",
+                    help="tuning sweeps only: fixed n_sub threshold of the latency mappings on the device-resident path "
+                         "(-1 = the automatic N-only rule, the product setting)")
     ap.add_argument("--horizon", type=int, default=0,
                     help="integrator steps per system for --workload c4 / c1 (default 1000; C4 as worded: 1000000)")
     args = ap.parse_args()

@@ -15,7 +15,7 @@
  *   - `*_host` entry points take HOST pointers and do H2D -> kernels -> D2H themselves (they own a
  *     cached per-device workspace); they return after the result is in the host buffers.
  *   - arrays use the reference's own layouts: m[B][N], q[B][N][2], v[B][N][2] row-major fp64
- *     (simulation_state.py:28-31), one batch = B systems with the same body count N (2..NB_MAX_N).
+ *     (simulation_state.py:28-31), one batch = B systems with the same body count N (2..NB_MAX_N_MID).
  *   - every function returns NB_OK (0) or a negative error code and never throws.  Numerical failure
  *     of one system is reported per system in `status[B]`, never as a hang or exception.
  */
@@ -34,7 +34,9 @@ extern "C" {
 #define NB_ERR_UNSUPPORTED (-3)
 
 #define NB_MIN_N 2
-#define NB_MAX_N 8             /* ensemble kernels are templated on N = 2..8 */
+#define NB_MAX_N 8             /* register-resident ensemble kernels are templated on N = 2..8 (all modes) */
+#define NB_MAX_N_MID 64        /* 9..64 bodies: one CTA per system, one body per thread (verlet / yoshida4 / whfast,
+                                  pair + variational calls, prepare, host entry); ham_soft and adaptive softening: N <= 8 */
 
 /* integrator_mode (sim_config.py:19-24) */
 #define NB_MODE_VERLET 0
@@ -179,12 +181,12 @@ int nb_hamsoft_probe_f64(const double* m, const double* q, const double* v, doub
 
 /* counting sort of systems by n_sub (descending) -> perm[B]; workspace: 128 int32 on the device;
  * on return workspace[64] = number of systems in the "heavy" head of perm (n_sub > workspace[65]) that the run
- * kernels map for latency instead of throughput.  The threshold depends on N only (bodies per system, 0 = unknown;
- * max(4, 50 / measured chain speed-up of the latency mapping)), never on the batch, so a system is integrated by the
- * same arithmetic however the ensemble is sharded. */
-int nb_sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* workspace, void* stream);
-/* override the heavy threshold (process-wide; tests and tuning): -1 = automatic (default), 0..63 = fixed */
-int nb_ensemble_set_heavy_nsub(int threshold);
+ * kernels map for latency instead of throughput.  heavy_threshold = -1 (the product setting): automatic, a function of
+ * N only (bodies per system, 0 = unknown; max(4, 50 / measured chain speed-up of the latency mapping)) and never of the
+ * batch, so a system is integrated by the same arithmetic however the ensemble is sharded; 0..63 fixes it (tests,
+ * tuning sweeps).  No process-wide state: every call carries its own setting. */
+int nb_sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* workspace, int heavy_threshold,
+                    void* stream);
 
 /* ---- the same path end to end with HOST buffers (BatchStabilityAnalyzer.analyze_batch,
  *      batch_stability_analyzer.py:62-80): prepare(flags) -> sort -> run -> features.
@@ -251,9 +253,12 @@ int nb_host_sync(int slot);
 /* ---- large-N direct sum (new capability, same formula as forces.py:63-75 / 77-112 / potential.py:23-64),
  *      fp32 pair arithmetic, fp64 accumulation across j-tiles.  xym[n_total] = (x, y, m, 0) packed float4.
  *      Rank-local i-range [i0, i0+ni).  acc[ni] float2; sums[2] += {sum_{i in range, j} m_i m_j/rho, sum m_i m_j/rho^3}
- *      (ordered pairs i != j; halve for i<j). */
+ *      (ordered pairs i != j; halve for i<j).  workspace: ni x 2 doubles of DEVICE memory owned by the caller (the fp64
+ *      accumulators of this call; concurrent calls pass distinct workspaces).  variant: -1 = default (10: packed f32x2
+ *      over j-pairs, 2 i per thread); 0..7 scalar-fp32 kernel (bit0: TMA staging, bits1-2: 4/2/1 i-particles per thread);
+ *      8 / 9: packed f32x2 with 4 / 8 i per thread -- A-B tests only, the results agree to fp32 rounding. */
 int nb_largeN_accel_f32(const float* xym, int n_total, int i0, int ni, float eps, float G, float* acc,
-                        double* sums, void* stream);
+                        double* sums, double* workspace, int variant, void* stream);
 /* kick/drift on the rank-local block and re-pack into the gather buffer (fused pack for the all-gather) */
 int nb_largeN_kick_drift_f32(float* xym_local, float* vel, const float* acc, int ni, float kick_h, float drift_h,
                              void* stream);
@@ -274,12 +279,15 @@ int nb_largeN_kick_drift_f32(float* xym_local, float* vel, const float* acc, int
 #define NB_LN_UNITGRAD 2
 #define NB_LN_TAUMIN 3
 int nb_largeN_pass_f32(int kind, const float* xym, const float* jaux, int n_total, int i0, int ni,
-                       const float* iparam, float eps, double* out, void* stream);
-
-/* kernel variant of nb_largeN_accel_f32 (tuning / A-B tests only; process-wide): -1 default (= 10);
- * 0..7 scalar-fp32 kernel (bit0: TMA staging, bits1-2: 4/2/1 i-particles per thread);
- * 8 packed f32x2 over j-pairs, 4 i per thread; 9 same with 8 i per thread, 2 CTAs/SM; 10 same with 2 i per thread */
-int nb_largeN_set_variant(int variant);
+                       const float* iparam, float eps, double* out, const float* tile_boxes, void* stream);
+/* locality culling of the DENSITY / EPSGRAD passes: e^{-r^2/h^2} is evaluated as ex2.approx.ftz and is EXACTLY zero
+ * beyond r > 9.35 h, so whole (i-block, j-tile) pairs whose bounding boxes are farther apart than that contribute exact
+ * zeros and are skipped when tile_boxes (NB_LN_TILE-particle tiles, NB_LN_BOX_FLOATS floats each: xmin, ymin, xmax, ymax,
+ * min |jaux.x|, 3 pad; written by nb_largeN_tile_boxes_f32 for the CURRENT xym / jaux) is passed; NULL = every tile.
+ * Bit-identical either way; with a spatially ordered particle array the passes cost O(N x neighbours), not O(N^2). */
+#define NB_LN_TILE 512
+#define NB_LN_BOX_FLOATS 8
+int nb_largeN_tile_boxes_f32(const float* xym, const float* jaux, int n_total, float* tile_boxes, void* stream);
 
 /* ---- on-GPU initial conditions with a counter-based RNG (Philox4x32-10 keyed by seed, counted by the GLOBAL system
  *      index first_index + b): the distributions of InitialConditionGenerator.generate_single
@@ -301,8 +309,11 @@ int nb_generate_tangent_f64(int N, int B, uint64_t seed, uint64_t first_index, d
 
 /* ---- stability-classifier inference on the feature tensors (model_zoo.py:18-33 MLP F-128-64-1 with ReLU;
  *      train_mlp.py:141-217 sigmoid + threshold; stability_dataset.py:83-85 nan_to_num; StandardScaler).
- *      feature_index[F]: value c < 64 reads dyn_features[:, c], c >= 64 reads static_features[:, c - 64]; F <= 64.
+ *      feature_index[F]: value c < 63 reads dyn_features[:, c], c >= 64 reads static_features[:, c - 64], and
+ *      c == NB_MLP_COL_PATHOLOGICAL (63) is the dataset's derived column pathological_energy = |energy_drift| > 10
+ *      (batch_stability_analyzer.py:45-52), which the feature tables a reference-trained model saw contain; F <= 64.
  *      w1[F][128] and w2[128][64] are INPUT-major (the transpose of torch's nn.Linear.weight); prob[B], label[B]. */
+#define NB_MLP_COL_PATHOLOGICAL 63
 int nb_mlp_classify_f32(const double* dyn_features, const double* static_features, const int32_t* feature_index, int F,
                         const float* mean, const float* inv_scale, const float* w1, const float* b1, const float* w2,
                         const float* b2, const float* w3, float b3, float threshold, int B, float* prob, int32_t* label,

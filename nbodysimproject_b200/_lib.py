@@ -42,10 +42,10 @@ N_HS = len(HS_PARAMS)
 
 EXPORTS = [
     "nb_last_error", "nb_version", "nb_pair_batched_f64", "nb_variational_batched_f64",
-    "nb_ensemble_prepare_f64", "nb_ensemble_run_f64", "nb_ensemble_run_counted_f64", "nb_sort_by_nsub", "nb_ensemble_set_heavy_nsub",
+    "nb_ensemble_prepare_f64", "nb_ensemble_run_f64", "nb_ensemble_run_counted_f64", "nb_sort_by_nsub",
     "nb_ensemble_run_adaptive_f64", "nb_ensemble_analyze_adaptive_f64", "nb_ensemble_analyze_host",
     "nb_ensemble_analyze_host_async", "nb_ensemble_analyze_host_ex", "nb_host_sync", "nb_generate_tangent_f64", "nb_hamsoft_setup_f64", "nb_hamsoft_probe_f64",
-    "nb_largeN_accel_f32", "nb_largeN_kick_drift_f32", "nb_largeN_set_variant", "nb_largeN_pass_f32", "nb_mlp_classify_f32", "nb_generate_ensemble_f64",
+    "nb_largeN_accel_f32", "nb_largeN_kick_drift_f32", "nb_largeN_pass_f32", "nb_largeN_tile_boxes_f32", "nb_mlp_classify_f32", "nb_generate_ensemble_f64",
     "nb_peak_flops",
 ]
 
@@ -97,8 +97,7 @@ def load():
     lib.nb_ensemble_prepare_f64.argtypes = [p, p, p, p, d, i, i, i, u, d, d, d, i, p, p, p, p]
     lib.nb_ensemble_run_f64.argtypes = [p, p, p, p, d, i, i, i, u, d, i, i, i, p, p, p, p, p, p, p, p, p, p]
     lib.nb_ensemble_run_counted_f64.argtypes = [p, p, p, p, d, i, i, i, u, d, i, i, i, p, p, p, p, p, p, p, p, p, p, p, p]
-    lib.nb_sort_by_nsub.argtypes = [p, i, i, p, p, p]
-    lib.nb_ensemble_set_heavy_nsub.argtypes = [i]
+    lib.nb_sort_by_nsub.argtypes = [p, i, i, p, p, i, p]
     lib.nb_ensemble_run_adaptive_f64.argtypes = [p, p, p, p, p, d, i, i, i, d, i, p, d, i, p, p, p, p]
     lib.nb_ensemble_analyze_adaptive_f64.argtypes = [p, p, p, p, p, p, d, i, i, i, d, i, i, i, p, p, p, d, i, p, p, p, p]
     lib.nb_ensemble_analyze_host.argtypes = [p, p, p, p, d, i, i, i, u, d, d, d, i, i, i, p, p, p, p, p, p, i]
@@ -108,10 +107,10 @@ def load():
     lib.nb_host_sync.argtypes = [i]
     lib.nb_hamsoft_setup_f64.argtypes = [p, p, d, i, i, u, d, p, p, p, p]
     lib.nb_hamsoft_probe_f64.argtypes = [p, p, p, d, i, i, p, p, p, p]
-    lib.nb_largeN_accel_f32.argtypes = [p, i, i, i, f, f, p, p, p]
+    lib.nb_largeN_accel_f32.argtypes = [p, i, i, i, f, f, p, p, p, i, p]
     lib.nb_largeN_kick_drift_f32.argtypes = [p, p, p, i, f, f, p]
-    lib.nb_largeN_set_variant.argtypes = [i]
-    lib.nb_largeN_pass_f32.argtypes = [i, p, p, i, i, i, p, f, p, p]
+    lib.nb_largeN_pass_f32.argtypes = [i, p, p, i, i, i, p, f, p, p, p]
+    lib.nb_largeN_tile_boxes_f32.argtypes = [p, p, i, p, p]
     lib.nb_mlp_classify_f32.argtypes = [p, p, p, i, p, p, p, p, p, p, p, f, f, i, p, p, p]
     lib.nb_generate_ensemble_f64.argtypes = [i, i, i, C.c_uint64, C.c_uint64, p, p, p, p, p]
     lib.nb_peak_flops.argtypes = [i, i, C.POINTER(C.c_double)]

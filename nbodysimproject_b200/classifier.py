@@ -14,10 +14,15 @@ from . import _lib as L
 from .dataset import PUBLIC_DYN
 
 
+COL_PATHOLOGICAL = 63      # NB_MLP_COL_PATHOLOGICAL: |energy_drift| > 10, synthesised by the kernel
+
+
 def default_feature_index(analysis_mode: str = "full"):
-    """Feature order of StabilityDataset.load on a table written from the tensors: the public dynamic columns minus
-    the label, then (full mode) the static columns, then pathological_energy is NOT included (it is a function of
-    energy_drift); returns (names, index) with index values < 64 for dyn columns and 64 + c for static ones."""
+    """Feature order of StabilityDataset.load on a table written by dataset.save_feature_table (which is the order the
+    reference's loader, stability_dataset.py:21-125, sees in a DataFrame.to_csv of analyze_batch): the public dynamic
+    columns minus the label, then (full mode) the 25 static columns, then `pathological_energy` -- a numeric column of
+    the table, so a model trained by the reference's train_mlp on such a file has 42 (full) / 17 (core) inputs.
+    Returns (names, index): index < 63 -> dyn column, 63 -> pathological_energy, 64 + c -> static column c."""
     names, idx = [], []
     for c, name in enumerate(PUBLIC_DYN):
         if name == "is_stable":
@@ -26,6 +31,7 @@ def default_feature_index(analysis_mode: str = "full"):
     if analysis_mode == "full":
         for c, name in enumerate(L.STATIC_COLUMNS):
             names.append("initial_" + name); idx.append(64 + c)
+    names.append("pathological_energy"); idx.append(COL_PATHOLOGICAL)
     return names, np.asarray(idx, dtype=np.int32)
 
 
@@ -42,7 +48,9 @@ class StabilityClassifier:
             raise L.NBodyB200Error("expected the reference's MLP: F -> 128 -> 64 -> 1 (model_zoo.py:18-33)")
         self.F = int(w1.shape[1])
         if feature_index is None:
-            _, feature_index = default_feature_index("full" if self.F > 16 else "core")
+            _, feature_index = default_feature_index("full" if self.F > 17 else "core")
+            if feature_index.size == self.F + 1:              # a table written without the derived column
+                feature_index = feature_index[:-1]
         feature_index = np.asarray(feature_index, dtype=np.int32)
         if feature_index.size != self.F or self.F > 64:
             raise L.NBodyB200Error(f"feature_index must list the {self.F} input columns (F <= 64)")

@@ -25,8 +25,7 @@ int pair_batched(const double* q, const double* m, const double* eps, double G, 
                  double* dV, cudaStream_t st);
 int variational_batched(const double* q, const double* m, const double* s2, const double* dr, double G, int B, int N,
                         double* da, cudaStream_t st);
-int sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* ws, cudaStream_t st);
-int set_heavy_nsub(int thr);
+int sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* ws, int heavy_threshold, cudaStream_t st);
 int generate_ensemble(int cohort, int N, int B, uint64_t seed, uint64_t first, double* m, double* q, double* v, double* eps,
                       cudaStream_t st);
 int ensemble_analyze_adaptive(const double* m, double* q, double* v, double* eps, const double* eps_energy,
@@ -40,12 +39,18 @@ int mlp_classify(const double* dyn, const double* stat, const int32_t* idx, int 
 int ensemble_run_adaptive(const double* m, double* q, double* v, double* eps, const double* soft_par, double G, int B,
                           int N, int mode, double dt, int n_steps, const int32_t* n_sub, double k_wall, int n_exp,
                           double* e_delta, double* eps_hist, int32_t* status, cudaStream_t st);
+int mid_run(const RunArgs& a, int N, int mode, cudaStream_t st);
+int mid_prepare(const PrepArgs& a, int N, cudaStream_t st);
+int mid_pair(const double* q, const double* m, const double* eps, double G, int B, int N, double* acc, double* U, double* dV,
+             cudaStream_t st);
+int mid_variational(const double* q, const double* m, const double* s2, const double* dr, double G, int B, int N, double* da,
+                    cudaStream_t st);
 int generate_tangent(int N, int B, uint64_t seed, uint64_t first, double* dr, double* dv, cudaStream_t st);
 int largeN_accel(const float* xym, int n_total, int i0, int ni, float eps, float G, float* acc, double* sums,
-                 cudaStream_t st);
-int largeN_set_variant(int variant);
+                 double* workspace, int variant, cudaStream_t st);
 int largeN_pass(int kind, const float* xym, const float* jaux, int n_total, int i0, int ni, const float* iparam,
-                float eps, double* out, cudaStream_t st);
+                float eps, double* out, const float* boxes, cudaStream_t st);
+int largeN_tile_boxes(const float* xym, const float* jaux, int n_total, float* boxes, cudaStream_t st);
 int largeN_kick_drift(float* xym_local, float* vel, const float* acc, int ni, float kick_h, float drift_h,
                       cudaStream_t st);
 int hamsoft_run(const double* m, double* q, double* v, double G, int B, int N, unsigned flags, double dt, int n_steps,
@@ -198,24 +203,27 @@ int nb_version(void) { return 100; }
 
 int nb_pair_batched_f64(const double* q, const double* m, const double* eps, double G, int B, int N, double* acc,
                         double* U, double* dVdeps, void* stream) {
-  if (!q || !m || !eps || B < 0 || N < NB_MIN_N || N > NB_MAX_N) { set_error("nb_pair_batched_f64: bad arguments"); return NB_ERR_ARG; }
+  if (!q || !m || !eps || B < 0 || N < NB_MIN_N || N > NB_MAX_N_MID) { set_error("nb_pair_batched_f64: bad arguments"); return NB_ERR_ARG; }
   if (B == 0) return NB_OK;
+  if (N > NB_MAX_N) return mid_pair(q, m, eps, G, B, N, acc, U, dVdeps, (cudaStream_t)stream);
   return pair_batched(q, m, eps, G, B, N, acc, U, dVdeps, (cudaStream_t)stream);
 }
 
 int nb_variational_batched_f64(const double* q, const double* m, const double* s2, const double* dr, double G, int B,
                                int N, double* da, void* stream) {
-  if (!q || !m || !s2 || !dr || !da || B < 0 || N < NB_MIN_N || N > NB_MAX_N) { set_error("nb_variational_batched_f64: bad arguments"); return NB_ERR_ARG; }
+  if (!q || !m || !s2 || !dr || !da || B < 0 || N < NB_MIN_N || N > NB_MAX_N_MID) { set_error("nb_variational_batched_f64: bad arguments"); return NB_ERR_ARG; }
   if (B == 0) return NB_OK;
+  if (N > NB_MAX_N) return mid_variational(q, m, s2, dr, G, B, N, da, (cudaStream_t)stream);
   return variational_batched(q, m, s2, dr, G, B, N, da, (cudaStream_t)stream);
 }
 
 int nb_ensemble_prepare_f64(const double* m, const double* q, double* v, const double* eps, double G, int B, int N,
                             int mode, unsigned flags, double kick_dt, double sched_dt, double dt, int split_n_max,
                             double* h_sub_ref, int32_t* n_sub, double* static_features, void* stream) {
-  if (!m || !q || !v || !eps || B < 0 || N < NB_MIN_N || N > NB_MAX_N) { set_error("nb_ensemble_prepare_f64: bad arguments"); return NB_ERR_ARG; }
+  if (!m || !q || !v || !eps || B < 0 || N < NB_MIN_N || N > NB_MAX_N_MID) { set_error("nb_ensemble_prepare_f64: bad arguments"); return NB_ERR_ARG; }
   if (B == 0) return NB_OK;
   PrepArgs a{m, q, v, eps, G, B, mode, flags, kick_dt, sched_dt, dt, split_n_max, h_sub_ref, n_sub, static_features};
+  if (N > NB_MAX_N) return mid_prepare(a, N, (cudaStream_t)stream);
   return ensemble_prepare(a, N, (cudaStream_t)stream);
 }
 
@@ -224,7 +232,8 @@ int nb_ensemble_run_counted_f64(const double* m, double* q, double* v, const dou
                                 const int32_t* n_sub, const int32_t* perm, const int32_t* n_heavy, const double* raw_dr,
                                 const double* raw_dv, double* eps_pi, const double* hs_params, double* dyn_features,
                                 int32_t* status, double* work, uint64_t* t_main, void* stream) {
-  if (!m || !q || !v || B < 0 || N < NB_MIN_N || N > NB_MAX_N || n_steps < 0 || n_megno < 0) { set_error("nb_ensemble_run_f64: bad arguments"); return NB_ERR_ARG; }
+  if (!m || !q || !v || B < 0 || N < NB_MIN_N || N > NB_MAX_N_MID || n_steps < 0 || n_megno < 0) { set_error("nb_ensemble_run_f64: bad arguments"); return NB_ERR_ARG; }
+  if (N > NB_MAX_N && mode == NB_MODE_HAMSOFT) { set_error("nb_ensemble_run_f64: the ham_soft kernels cover N <= 8 bodies"); return NB_ERR_UNSUPPORTED; }
   if (n_megno > 0 && (!raw_dr || !raw_dv)) { set_error("nb_ensemble_run_f64: n_megno > 0 needs raw_dr/raw_dv"); return NB_ERR_ARG; }
   if (B == 0) return NB_OK;
   if (mode == NB_MODE_HAMSOFT) {
@@ -234,6 +243,7 @@ int nb_ensemble_run_counted_f64(const double* m, double* q, double* v, const dou
   }
   if (!eps) { set_error("nb_ensemble_run_f64: eps is required"); return NB_ERR_ARG; }
   RunArgs a{m, q, v, eps, G, B, flags, dt, n_steps, sample_interval, n_megno, n_sub, perm, perm ? n_heavy : nullptr, 0, 0, 0, raw_dr, raw_dv, dyn_features, status, (unsigned long long*)t_main, work};
+  if (N > NB_MAX_N) return mid_run(a, N, mode, (cudaStream_t)stream);    // 9..64 bodies: one CTA per system
   return ensemble_run_classic(a, N, mode, (cudaStream_t)stream);
 }
 
@@ -259,8 +269,6 @@ int nb_hamsoft_probe_f64(const double* m, const double* q, const double* v, doub
   return hamsoft_probe(m, q, v, G, B, N, eps_pi, hs_params, out, (cudaStream_t)stream);
 }
 
-int nb_ensemble_set_heavy_nsub(int threshold) { return set_heavy_nsub(threshold); }
-
 int nb_ensemble_run_adaptive_f64(const double* m, double* q, double* v, double* eps, const double* soft_par, double G,
                                  int B, int N, int mode, double dt, int n_steps, const int32_t* n_sub, double k_wall,
                                  int barrier_exponent, double* energy_delta, double* eps_hist, int32_t* status,
@@ -279,21 +287,24 @@ int nb_ensemble_analyze_adaptive_f64(const double* m, double* q, double* v, doub
                                    (cudaStream_t)stream);
 }
 
-int nb_sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* workspace, void* stream) {
+int nb_sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* workspace, int heavy_threshold,
+                    void* stream) {
   if (!n_sub || !perm || !workspace || B < 0) { set_error("nb_sort_by_nsub: bad arguments"); return NB_ERR_ARG; }
   if (B == 0) return NB_OK;
-  return sort_by_nsub(n_sub, B, N, perm, workspace, (cudaStream_t)stream);
+  return sort_by_nsub(n_sub, B, N, perm, workspace, heavy_threshold, (cudaStream_t)stream);
 }
 
 int nb_largeN_accel_f32(const float* xym, int n_total, int i0, int ni, float eps, float G, float* acc, double* sums,
-                        void* stream) {
-  return largeN_accel(xym, n_total, i0, ni, eps, G, acc, sums, (cudaStream_t)stream);
+                        double* workspace, int variant, void* stream) {
+  return largeN_accel(xym, n_total, i0, ni, eps, G, acc, sums, workspace, variant, (cudaStream_t)stream);
 }
 
-int nb_largeN_set_variant(int variant) { return largeN_set_variant(variant); }
 int nb_largeN_pass_f32(int kind, const float* xym, const float* jaux, int n_total, int i0, int ni, const float* iparam,
-                       float eps, double* out, void* stream) {
-  return largeN_pass(kind, xym, jaux, n_total, i0, ni, iparam, eps, out, (cudaStream_t)stream);
+                       float eps, double* out, const float* tile_boxes, void* stream) {
+  return largeN_pass(kind, xym, jaux, n_total, i0, ni, iparam, eps, out, tile_boxes, (cudaStream_t)stream);
+}
+int nb_largeN_tile_boxes_f32(const float* xym, const float* jaux, int n_total, float* tile_boxes, void* stream) {
+  return largeN_tile_boxes(xym, jaux, n_total, tile_boxes, (cudaStream_t)stream);
 }
 int nb_largeN_kick_drift_f32(float* xym_local, float* vel, const float* acc, int ni, float kick_h, float drift_h,
                              void* stream) {

@@ -17,7 +17,7 @@ constexpr int MLP_H1 = 128, MLP_H2 = 64, MLP_ROWS = 64, MLP_THREADS = 256, MLP_M
 struct MlpArgs {
   const double* dyn;      // [B][NB_N_DYN]
   const double* stat;     // [B][NB_N_STATIC] or null
-  const int32_t* idx;     // [F]: < 64 -> dyn column, >= 64 -> static column idx - 64
+  const int32_t* idx;     // [F]: < 63 -> dyn column, 63 -> pathological_energy (derived), >= 64 -> static column idx - 64
   const float* mean;      // [F]
   const float* inv_scale; // [F]
   const float* w1;        // [F][128]  (input-major)
@@ -49,7 +49,13 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_classify_kernel(MlpArgs a) {
       const int r = i / F, k = i - r * F;
       const int row = min(row0 + r, a.B - 1);
       const int c = a.idx[k];
-      double v = c < 64 ? a.dyn[(size_t)row * NB_N_DYN + c] : a.stat[(size_t)row * NB_N_STATIC + (c - 64)];
+      double v;
+      if (c == NB_MLP_COL_PATHOLOGICAL) {
+        // the dataset writer's derived column: pathological_energy = |energy_drift| > 10 (batch_stability_analyzer.py:45-52)
+        v = fabs(a.dyn[(size_t)row * NB_N_DYN + NB_F_ENERGY_DRIFT]) > 10.0 ? 1.0 : 0.0;
+      } else {
+        v = c < 64 ? a.dyn[(size_t)row * NB_N_DYN + c] : a.stat[(size_t)row * NB_N_STATIC + (c - 64)];
+      }
       if (v != v) v = 0.0;                                         // nan_to_num(nan=0.0); +-inf stay as in numpy
       Xs[r * F + k] = ((float)v - a.mean[k]) * a.inv_scale[k];
     }
@@ -121,12 +127,9 @@ int mlp_classify(const double* dyn, const double* stat, const int32_t* idx, int 
     return NB_ERR_ARG;
   }
   if (B == 0) return NB_OK;
-  static bool configured = false;
   const size_t smem = sizeof(float) * (MLP_ROWS * MLP_MAXF + MLP_MAXF * MLP_H1 + MLP_ROWS * MLP_H1 + MLP_H1 * MLP_H2);
-  if (!configured) {
-    NB_CUDA_CHECK(cudaFuncSetAttribute(mlp_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  // the opt-in above 48 KB is per DEVICE: set it on every call (a cheap host-side call) instead of once per process
+  NB_CUDA_CHECK(cudaFuncSetAttribute(mlp_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MlpArgs a{dyn, stat, idx, mean, inv_scale, w1, b1, w2, b2, w3, b3, threshold, B, F, prob, label};
   const int tiles = (B + MLP_ROWS - 1) / MLP_ROWS;
   const int grid = tiles < 148 * 2 ? tiles : 148 * 2;

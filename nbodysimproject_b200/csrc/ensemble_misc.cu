@@ -109,7 +109,7 @@ struct SidePool {
 };
 static SidePool g_side[16];
 static std::mutex g_side_mu;
-static int g_split_min_b = -1;        // below this a bucket is one launch (nothing to overlap); NB_SPLIT_MIN_B overrides
+constexpr int NB_SPLIT_MIN_B = 4096;   // below this a bucket is one launch (nothing to overlap)
 
 static int side_pool(int dev, cudaStream_t st, SidePool** out, int* k) {
   SidePool& p = g_side[dev & 15];
@@ -136,7 +136,6 @@ static int side_pool(int dev, cudaStream_t st, SidePool** out, int* k) {
 int ensemble_run_classic(const RunArgs& a_in, int N, int mode, cudaStream_t st) {
   if (N < NB_MIN_N || N > NB_MAX_N) { set_error("N must be in 2..8"); return NB_ERR_ARG; }
   RunArgs a = a_in;
-  if (g_split_min_b < 0) g_split_min_b = getenv("NB_SPLIT_MIN_B") ? atoi(getenv("NB_SPLIT_MIN_B")) : 4096;
   auto phase = [&](int ph, int write_state, const RunArgs& ra, cudaStream_t s) -> int {
     switch (mode) {
       case NB_MODE_VERLET: return ensemble_run_verlet(ra, N, ph, write_state, s);
@@ -149,7 +148,7 @@ int ensemble_run_classic(const RunArgs& a_in, int N, int mode, cudaStream_t st) 
   const bool energy = (a.flags & NB_RUN_ENERGY) != 0 && a.dyn != nullptr;
   const bool megno = a.n_megno > 0;
   const int write = ((a.flags & NB_RUN_WRITE_STATE) || energy || megno) ? 1 : 0;
-  const bool split = a.perm && a.n_heavy && a.B >= g_split_min_b && a.n_steps > 0 &&
+  const bool split = a.perm && a.n_heavy && a.B >= NB_SPLIT_MIN_B && a.n_steps > 0 &&
                      (mode == NB_MODE_VERLET || mode == NB_MODE_YOSHIDA4);
   int rc;
   if (!split) {
@@ -513,15 +512,8 @@ int variational_batched(const double* q, const double* m, const double* s2, cons
   return NB_OK;
 }
 
-static int g_heavy_fixed = -1;
-
-int set_heavy_nsub(int thr) {
-  if (thr < -1 || thr > 63) { set_error("nb_ensemble_set_heavy_nsub: threshold must be -1 (automatic) or 0..63"); return NB_ERR_ARG; }
-  g_heavy_fixed = thr;
-  return NB_OK;
-}
-
-int sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* ws, cudaStream_t st) {
+int sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* ws, int heavy_threshold, cudaStream_t st) {
+  if (heavy_threshold < -1 || heavy_threshold > 63) { set_error("nb_sort_by_nsub: heavy_threshold must be -1 (automatic) or 0..63"); return NB_ERR_ARG; }
   NB_CUDA_CHECK(cudaMemsetAsync(ws, 0, 66 * sizeof(int32_t), st));
   const int threads = 256;
   const int blocks = min((B + threads - 1) / threads, 148 * 8);
@@ -529,7 +521,7 @@ int sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* ws,
   // measured on B200 (tools/check_thr.py): chain time of an n_sub = 50 system, thread mapping / fast mapping
   static const float speedup[9] = {1.f, 1.f, 1.f, 1.f, 1.8f, 2.1f, 3.0f, 3.5f, 4.5f};
   const int n = (N >= 2 && N <= 8) ? N : 0;
-  sort_scan_kernel<<<1, 32, 0, st>>>(ws, speedup[n], g_heavy_fixed);
+  sort_scan_kernel<<<1, 32, 0, st>>>(ws, speedup[n], heavy_threshold);
   sort_scatter_kernel<<<blocks, threads, 0, st>>>(n_sub, B, ws, perm);
   NB_CUDA_CHECK(cudaGetLastError());
   return NB_OK;

@@ -25,7 +25,7 @@ namespace nb {
 
 int ensemble_run_classic(const RunArgs& a, int N, int mode, cudaStream_t st);
 int ensemble_prepare(const PrepArgs& a, int N, cudaStream_t st);
-int sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* ws, cudaStream_t st);
+int sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* ws, int heavy_threshold, cudaStream_t st);
 int ensemble_analyze_adaptive(const double* m, double* q, double* v, double* eps, const double* eps_energy,
                               const double* soft_par, double G, int B, int N, int mode, double dt, int n_steps,
                               int sample_interval, int n_megno, const int32_t* n_sub, const double* raw_dr,
@@ -38,6 +38,8 @@ int hamsoft_run(const double* m, double* q, double* v, double G, int B, int N, u
 int hamsoft_setup(const double* m, const double* q, double G, int B, int N, unsigned flags, double dt, double* hs,
                   double* eps_pi, int32_t* n_sub, cudaStream_t st);
 int generate_tangent(int N, int B, uint64_t seed, uint64_t first, double* dr, double* dv, cudaStream_t st);
+int mid_run(const RunArgs& a, int N, int mode, cudaStream_t st);
+int mid_prepare(const PrepArgs& a, int N, cudaStream_t st);
 
 // RAII: entry points that take a `device` argument leave the caller's current device as they found it
 struct DeviceGuard {
@@ -185,7 +187,8 @@ static int analyze_host_ex(const double* m, const double* q, double* v, const do
   const bool compact = (o.flags & NB_HOST_COMPACT_DYN) != 0;
   const bool keep_v = (o.flags & NB_HOST_KEEP_V) != 0;
   if (slot < 0 || slot >= NB_HOST_SLOTS) { set_error("nb_ensemble_analyze_host: slot out of range"); return NB_ERR_ARG; }
-  if (!m || !q || !v || !eps || !dyn_features || B < 0 || N < NB_MIN_N || N > NB_MAX_N || n_steps < 0 || n_megno < 0) { set_error("nb_ensemble_analyze_host: bad arguments"); return NB_ERR_ARG; }
+  if (!m || !q || !v || !eps || !dyn_features || B < 0 || N < NB_MIN_N || N > NB_MAX_N_MID || n_steps < 0 || n_megno < 0) { set_error("nb_ensemble_analyze_host: bad arguments"); return NB_ERR_ARG; }
+  if (N > NB_MAX_N && (mode == NB_MODE_HAMSOFT || (opts_in && (opts_in->flags & NB_HOST_ADAPTIVE)))) { set_error("nb_ensemble_analyze_host: ham_soft / adaptive softening cover N <= 8 bodies"); return NB_ERR_UNSUPPORTED; }
   if (mode != NB_MODE_VERLET && mode != NB_MODE_YOSHIDA4 && mode != NB_MODE_WHFAST && !hamsoft) { set_error("nb_ensemble_analyze_host: unknown integrator mode"); return NB_ERR_ARG; }
   if (n_megno > 0 && !dev_tangent && (!raw_dr || !raw_dv)) { set_error("nb_ensemble_analyze_host: n_megno > 0 needs raw_dr/raw_dv (or NB_HOST_DEVICE_TANGENT)"); return NB_ERR_ARG; }
   if (adaptive && (hamsoft || mode == NB_MODE_WHFAST || !o.soft_par)) { set_error("nb_ensemble_analyze_host: NB_HOST_ADAPTIVE needs verlet / yoshida4 and opts->soft_par"); return NB_ERR_UNSUPPORTED; }
@@ -279,7 +282,7 @@ static int analyze_host_ex(const double* m, const double* q, double* v, const do
     const unsigned pf1 = hamsoft ? (pf & NB_PREP_REMOVE_COM) : pf;
     PrepArgs pa{d_m + oN, d_q + 2 * oN, d_v + 2 * oN, d_eps + o1, G, nb, hamsoft ? NB_MODE_VERLET : mode, pf1, kick_dt,
                 sched_dt, dt, split_n_max, nullptr, d_nsub + o1, d_stat + o1 * NB_N_STATIC};
-    rc = ensemble_prepare(pa, N, sk);
+    rc = N > NB_MAX_N ? mid_prepare(pa, N, sk) : ensemble_prepare(pa, N, sk);
     if (rc != NB_OK) return rc;
     if (hamsoft) {
       const int blocks = (nb + 127) / 128;
@@ -314,7 +317,7 @@ static int analyze_host_ex(const double* m, const double* q, double* v, const do
     if (n_sub_out) NB_CUDA_CHECK(cudaMemcpyAsync(n_sub_out + o1, d_nsub + o1, (size_t)nb * 4, cudaMemcpyDeviceToHost, w.s_out));
     // ---- stage 3: the run
     int32_t* bins = (int32_t*)(d_bins0 + (size_t)c * align256(128 * 4));
-    rc = sort_by_nsub(d_nsub + o1, nb, N, d_perm + o1, bins, sk);
+    rc = sort_by_nsub(d_nsub + o1, nb, N, d_perm + o1, bins, -1, sk);
     if (rc != NB_OK) return rc;
     if (hamsoft) {
       rc = hamsoft_run(d_m + oN, d_q + 2 * oN, d_v + 2 * oN, G, nb, N, NB_RUN_ENERGY | NB_RUN_WRITE_STATE, dt, n_steps,
@@ -330,7 +333,7 @@ static int analyze_host_ex(const double* m, const double* q, double* v, const do
       RunArgs ra{d_m + oN, d_q + 2 * oN, d_v + 2 * oN, d_eps + o1, G, nb, NB_RUN_ENERGY, dt, n_steps, interval, n_megno,
                  d_nsub + o1, d_perm + o1, bins + 64, 0, 0, 0, d_dr + 2 * oN, d_dv + 2 * oN, d_dyn + o1 * NB_N_DYN,
                  d_status + o1, nullptr, nullptr};
-      rc = ensemble_run_classic(ra, N, mode, sk);
+      rc = N > NB_MAX_N ? mid_run(ra, N, mode, sk) : ensemble_run_classic(ra, N, mode, sk);
     }
     if (rc != NB_OK) return rc;
     if (compact) compact_dyn_kernel<<<(nb * NB_N_DYN_USER + 255) / 256, 256, 0, sk>>>(d_dyn + o1 * NB_N_DYN, d_dyn_c + o1 * NB_N_DYN_USER, nb);

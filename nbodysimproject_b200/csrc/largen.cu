@@ -370,49 +370,27 @@ __global__ void largeN_kick_drift_kernel(float4* __restrict__ xym_local, float2*
   }
 }
 
-// NB_LARGEN_VARIANT (tuning only): 0..7 = v1 scalar kernel (bit0 TMA, bits1-2 IPT selector 4/2/1);
-// 8 = v2 packed f32x2, IPT 4, 4 CTAs/SM (default); 9 = v2 IPT 8, 2 CTAs/SM; 10 = v2 IPT 2, 4 CTAs/SM
-static int g_ln_variant = -1;
-static int g_sm_count = 0;
-static double* g_acc64 = nullptr;
-static size_t g_acc64_cap = 0;
-static int g_acc64_dev = -1;
-
-int largeN_set_variant(int variant) {
-  if (variant < -1 || variant > 10) { set_error("nb_largeN_set_variant: variant must be -1..10"); return NB_ERR_ARG; }
-  g_ln_variant = variant;
-  return NB_OK;
-}
-
+// kernel variants (tuning / A-B tests): 0..7 = v1 scalar kernel (bit0 TMA, bits1-2 IPT selector 4/2/1);
+// 8 = v2 packed f32x2, IPT 4, 4 CTAs/SM; 9 = v2 IPT 8, 2 CTAs/SM; 10 = v2 IPT 2, 4 CTAs/SM (default, -1)
 int largeN_accel(const float* xym, int n_total, int i0, int ni, float eps, float G, float* acc, double* sums,
-                 cudaStream_t st) {
-  if (!xym || !acc || n_total <= 0 || ni <= 0 || i0 < 0 || i0 + ni > n_total) {
-    set_error("nb_largeN_accel_f32: bad arguments");
+                 double* workspace, int variant_in, cudaStream_t st) {
+  if (!xym || !acc || !workspace || n_total <= 0 || ni <= 0 || i0 < 0 || i0 + ni > n_total || variant_in < -1 || variant_in > 10) {
+    set_error("nb_largeN_accel_f32: bad arguments (workspace = ni x 2 doubles of device memory is required; variant -1..10)");
     return NB_ERR_ARG;
   }
-  int dev = 0;
+  // stateless: the fp64 accumulators live in the CALLER's workspace, so calls on different streams / devices / threads
+  // never share anything (round 1 kept one process-global buffer here)
+  int dev = 0, sm_count = 0;
   NB_CUDA_CHECK(cudaGetDevice(&dev));
-  if (g_sm_count == 0 || g_acc64_dev != dev) {
-    NB_CUDA_CHECK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
-  if (g_acc64_dev != dev || g_acc64_cap < (size_t)ni * 2) {
-    if (g_acc64) cudaFree(g_acc64);
-    g_acc64 = nullptr;
-    NB_CUDA_CHECK(cudaMalloc(&g_acc64, sizeof(double) * 2 * (size_t)ni));
-    g_acc64_cap = (size_t)ni * 2;
-    g_acc64_dev = dev;
-  }
-  if (g_ln_variant < 0) {
-    const char* e = getenv("NB_LARGEN_VARIANT");
-    g_ln_variant = e ? atoi(e) : -1;
-  }
+  NB_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  double* const acc64 = workspace;
   // default (-1): 2 i-particles per thread, 4 CTAs/SM, 16 j-particles per unrolled iteration: measured 3.25e12 pairs/s
   // (4 or 8 i per thread: 3.13-3.17e12; with the fused scalar sums their extra accumulators spill at 64 registers)
-  const int variant = g_ln_variant >= 0 ? g_ln_variant : 10;
+  const int variant = variant_in >= 0 ? variant_in : 10;
   const bool v2 = variant >= 8;
   const int v2_ipt = variant == 9 ? 8 : (variant == 10 ? 2 : 4);
   const int v2_minb = variant == 9 ? 2 : 4;
-  NB_CUDA_CHECK(cudaMemsetAsync(g_acc64, 0, sizeof(double) * 2 * (size_t)ni, st));
+  NB_CUDA_CHECK(cudaMemsetAsync(acc64, 0, sizeof(double) * 2 * (size_t)ni, st));
   const bool use_tma = (variant & 1) != 0;
   const int ipt = v2 ? v2_ipt : (((variant >> 1) & 3) == 0 ? 4 : (((variant >> 1) & 3) == 1 ? 2 : 1));
   const int tile = v2 ? LN2_TILE : LN_TILE;
@@ -423,12 +401,12 @@ int largeN_accel(const float* xym, int n_total, int i0, int ni, float eps, float
   a.ni = ni;
   a.eps2 = eps * eps;
   a.G = G;
-  a.acc64 = g_acc64;
+  a.acc64 = acc64;
   a.sums = sums;
   const int per_block = LN_TPB * ipt;
   a.n_ichunks = (ni + per_block - 1) / per_block;
   // enough j-chunks that the persistent grid gets >= ~12 rounds of units, but each chunk >= 8 tiles
-  const int resident = g_sm_count * (v2 ? v2_minb : 4);
+  const int resident = sm_count * (v2 ? v2_minb : 4);
   int n_j = (12 * resident + a.n_ichunks - 1) / a.n_ichunks;
   const int max_j = (n_total + 8 * tile - 1) / (8 * tile);
   n_j = n_j < 1 ? 1 : (n_j > max_j ? max_j : n_j);
@@ -438,7 +416,8 @@ int largeN_accel(const float* xym, int n_total, int i0, int ni, float eps, float
   a.n_jchunks = (n_total + jchunk - 1) / jchunk;
   const int n_units = a.n_ichunks * a.n_jchunks;
   const int grid = n_units < resident ? n_units : resident;
-  const bool eps_zero = !(eps > 0.f);
+  // decided on eps^2, which is what the kernel adds: an eps whose square flushes to zero must take the guarded path
+  const bool eps_zero = !(eps * eps > 1.17549435e-38f);
   const bool scal = sums != nullptr;
 #define NB_LN_LAUNCH(IPT, SC, EZ, TMA) largeN_accel_kernel<IPT, SC, EZ, TMA><<<grid, LN_TPB, 0, st>>>(a)
 #define NB_LN_SWITCH(IPT)                                                          \
@@ -469,7 +448,7 @@ int largeN_accel(const float* xym, int n_total, int i0, int ni, float eps, float
 #undef NB_LN_SWITCH
 #undef NB_LN_LAUNCH
   NB_CUDA_CHECK(cudaGetLastError());
-  largeN_finish_kernel<<<(ni + 255) / 256, 256, 0, st>>>(g_acc64, ni, reinterpret_cast<float2*>(acc));
+  largeN_finish_kernel<<<(ni + 255) / 256, 256, 0, st>>>(acc64, ni, reinterpret_cast<float2*>(acc));
   NB_CUDA_CHECK(cudaGetLastError());
   return NB_OK;
 }

@@ -23,7 +23,60 @@ constexpr int LP_IPT = 2;
 
 enum { LP_DENSITY = 0, LP_EPSGRAD = 1, LP_UNITGRAD = 2, LP_TAUMIN = 3 };
 
+// ---- locality culling ------------------------------------------------------------------------------------------
+// exp(-r^2/h^2) is evaluated as ex2.approx.ftz(r^2 nk) with nk = -log2(e)/h^2: it is EXACTLY +0 once r^2 |nk| > 126
+// (the result would be subnormal and .ftz flushes it), i.e. beyond r > 9.35 h.  Smoothing lengths are a few mean
+// inter-particle distances, so for a spatially ordered particle array (LargeNHamSoftSimulation sorts along a Morton
+// curve) almost every (i-block, j-tile) pair of the DENSITY and EPSGRAD passes contributes exact zeros.  A tile is
+// skipped -- no TMA load, no arithmetic -- when the distance between the bounding boxes of the i-block and of the tile
+// puts every pair beyond that radius for the largest h involved; the result is bit-identical to the unculled pass
+// (only exact zeros are dropped; tests/test_gpu_largen_hamsoft.py) and the cost drops from O(N^2) to O(N x neighbours).
+// Correctness never depends on the ordering, only the hit rate does.  UNITGRAD / TAUMIN (long range) are never culled.
+struct TileBox {
+  float xmin, ymin, xmax, ymax;
+  float kmin;      // min_j |jaux.x| of the tile (EPSGRAD: the j-side exponent scale), +inf when no jaux
+  float pad[3];
+};
+constexpr float LP_CULL = 127.0f;      // > 126 with a margin for the fp32 rounding of r^2 vs the box distance
+constexpr int LP_MAX_TILES = 1024;     // tiles per (i-block, j-chunk) unit (the launcher caps the j-chunk accordingly)
+
+__global__ void __launch_bounds__(256) largeN_tile_box_kernel(const float4* __restrict__ xym, const float2* __restrict__ jaux,
+                                                              int n_total, int tile, TileBox* boxes) {
+  const int t = blockIdx.x;
+  const int j0 = t * tile, j1 = min(n_total, j0 + tile);
+  float xmin = 3.0e38f, ymin = 3.0e38f, xmax = -3.0e38f, ymax = -3.0e38f, kmin = 3.0e38f;
+  for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
+    const float4 p = xym[j];
+    xmin = fminf(xmin, p.x); xmax = fmaxf(xmax, p.x);
+    ymin = fminf(ymin, p.y); ymax = fmaxf(ymax, p.y);
+    if (jaux) kmin = fminf(kmin, fabsf(jaux[j].x));
+  }
+  __shared__ float red[5][8];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, off));
+    ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, off));
+    xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, off));
+    ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, off));
+    kmin = fminf(kmin, __shfl_xor_sync(0xffffffffu, kmin, off));
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[0][w] = xmin; red[1][w] = ymin; red[2][w] = xmax; red[3][w] = ymax; red[4][w] = kmin; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+      xmin = fminf(xmin, red[0][k]); ymin = fminf(ymin, red[1][k]);
+      xmax = fmaxf(xmax, red[2][k]); ymax = fmaxf(ymax, red[3][k]); kmin = fminf(kmin, red[4][k]);
+    }
+    TileBox b;
+    b.xmin = xmin; b.ymin = ymin; b.xmax = xmax; b.ymax = ymax; b.kmin = kmin;
+    b.pad[0] = b.pad[1] = b.pad[2] = 0.f;
+    boxes[t] = b;
+  }
+}
+
 struct PassArgs {
+  const TileBox* boxes;   // per LP_TILE-aligned j-tile, or null (no culling)
   const float4* xym;
   const float2* jaux;     // EPSGRAD: (nk_j, A_j) per particle, nk = -log2(e)/h^2
   const float* iparam;    // DENSITY: h_i for the local particles
@@ -41,6 +94,10 @@ __global__ void __launch_bounds__(LN_TPB, 4) largeN_pass_kernel(PassArgs a) {
   __shared__ __align__(128) float2 rawaux[AUX ? 2 : 1][AUX ? LP_TILE : 1];
   __shared__ __align__(16) float rows[2][NROW][LP_TILE];
   __shared__ __align__(8) uint64_t bars[2];
+  __shared__ unsigned short act[LP_MAX_TILES];       // tiles of this unit that survive the culling test, ascending
+  __shared__ float bred[5][LN_TPB / 32];
+  __shared__ int wcount[LN_TPB / 32 + 1];
+  constexpr bool CULL = (KIND == LP_DENSITY || KIND == LP_EPSGRAD);
   const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
@@ -87,10 +144,64 @@ __global__ void __launch_bounds__(LN_TPB, 4) largeN_pass_kernel(PassArgs a) {
       o0[k] = (KIND == LP_TAUMIN) ? 1e300 : 0.0;
       o1[k] = 0.0; o2[k] = 0.0; o3[k] = 0.0;
     }
-    const int n_tiles = (j_end - j_begin + LP_TILE - 1) / LP_TILE;
-    auto issue = [&](int t, int buf) {
+    const int n_tiles_all = (j_end - j_begin + LP_TILE - 1) / LP_TILE;
+    // ---- culling: bounding box and largest cut-off radius of this i-block, then the ordered list of live tiles
+    int n_tiles = n_tiles_all;
+    if (CULL && a.boxes != nullptr) {
+      float xmin = 3.0e38f, ymin = 3.0e38f, xmax = -3.0e38f, ymax = -3.0e38f, kmin = 3.0e38f;
+#pragma unroll
+      for (int k = 0; k < LP_IPT; ++k) {
+        xmin = fminf(xmin, -nxi[k].x); xmax = fmaxf(xmax, -nxi[k].x);
+        ymin = fminf(ymin, -nyi[k].x); ymax = fmaxf(ymax, -nyi[k].x);
+        kmin = fminf(kmin, fabsf(nk[k].x));
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, off));
+        ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, off));
+        xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, off));
+        ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, off));
+        kmin = fminf(kmin, __shfl_xor_sync(0xffffffffu, kmin, off));
+      }
+      if ((tid & 31) == 0) { bred[0][tid >> 5] = xmin; bred[1][tid >> 5] = ymin; bred[2][tid >> 5] = xmax; bred[3][tid >> 5] = ymax; bred[4][tid >> 5] = kmin; }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < LN_TPB / 32; ++k) {
+        xmin = fminf(xmin, bred[0][k]); ymin = fminf(ymin, bred[1][k]);
+        xmax = fmaxf(xmax, bred[2][k]); ymax = fmaxf(ymax, bred[3][k]); kmin = fminf(kmin, bred[4][k]);
+      }
+      int n_act = 0;
+      for (int t0 = 0; t0 < n_tiles_all; t0 += LN_TPB) {
+        const int t = t0 + tid;
+        bool live = false;
+        if (t < n_tiles_all) {
+          const TileBox b = a.boxes[j_begin / LP_TILE + t];
+          const float gx = fmaxf(0.f, fmaxf(b.xmin - xmax, xmin - b.xmax));
+          const float gy = fmaxf(0.f, fmaxf(b.ymin - ymax, ymin - b.ymax));
+          const float d2 = gx * gx + gy * gy;
+          const float k_eff = (KIND == LP_EPSGRAD) ? fminf(kmin, b.kmin) : kmin;
+          live = !(d2 * k_eff > LP_CULL);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, live);
+        if ((tid & 31) == 0) wcount[tid >> 5] = __popc(bal);
+        __syncthreads();
+        int before = n_act;
+        for (int w = 0; w < (tid >> 5); ++w) before += wcount[w];
+        if (live) act[before + __popc(bal & ((1u << (tid & 31)) - 1u))] = (unsigned short)t;
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < LN_TPB / 32; ++w) tot += wcount[w];
+        n_act += tot;
+        __syncthreads();
+      }
+      n_tiles = n_act;
+    } else {
+      for (int t = tid; t < n_tiles_all; t += LN_TPB) act[t] = (unsigned short)t;
+      __syncthreads();
+    }
+    auto issue = [&](int idx, int buf) {
       if (tid == 0) {
-        const int j0 = j_begin + t * LP_TILE;
+        const int j0 = j_begin + (int)act[idx] * LP_TILE;
         const int cnt = min(LP_TILE, j_end - j0);
         // bulk copies move multiples of 16 bytes: the float2 tile is rounded up to an even count (the caller
         // pads jaux to an even length)
@@ -100,11 +211,11 @@ __global__ void __launch_bounds__(LN_TPB, 4) largeN_pass_kernel(PassArgs a) {
         if (AUX) tma_load_1d(&rawaux[AUX ? buf : 0][0], a.jaux + j0, aux_bytes, &bars[buf]);
       }
     };
-    issue(0, 0);
+    if (n_tiles > 0) issue(0, 0);
     if (n_tiles > 1) issue(1, 1);
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t & 1;
-      const int jt0 = j_begin + t * LP_TILE;
+      const int jt0 = j_begin + (int)act[t] * LP_TILE;
       const int cnt = min(LP_TILE, j_end - jt0);
       mbar_wait(&bars[buf], phase[buf]);
       phase[buf] ^= 1u;
@@ -239,28 +350,46 @@ __global__ void __launch_bounds__(LN_TPB, 4) largeN_pass_kernel(PassArgs a) {
         atomicAdd(&a.out[2 * (size_t)ii[k] + 0], -o0[k]);
         atomicAdd(&a.out[2 * (size_t)ii[k] + 1], -o1[k]);
       } else {
-        a.out[ii[k]] = o0[k];       // single j-chunk: plain store
+        // positive doubles order like their bit patterns: minimum across j-chunks with an integer atomic
+        atomicMin(reinterpret_cast<unsigned long long*>(&a.out[ii[k]]), (unsigned long long)__double_as_longlong(o0[k]));
       }
     }
   }
 }
 
-static int g_pass_sm = 0;
+__global__ void fill_f64_kernel(double* p, size_t n, double v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+int largeN_tile_boxes(const float* xym, const float* jaux, int n_total, float* boxes, cudaStream_t st) {
+  if (!xym || !boxes || n_total <= 0) { set_error("nb_largeN_tile_boxes_f32: bad arguments"); return NB_ERR_ARG; }
+  const int n_tiles = (n_total + LP_TILE - 1) / LP_TILE;
+  largeN_tile_box_kernel<<<n_tiles, 256, 0, st>>>(reinterpret_cast<const float4*>(xym), reinterpret_cast<const float2*>(jaux),
+                                                  n_total, LP_TILE, reinterpret_cast<TileBox*>(boxes));
+  NB_CUDA_CHECK(cudaGetLastError());
+  return NB_OK;
+}
 
 int largeN_pass(int kind, const float* xym, const float* jaux, int n_total, int i0, int ni, const float* iparam,
-                float eps, double* out, cudaStream_t st) {
+                float eps, double* out, const float* boxes, cudaStream_t st) {
   if (!xym || !out || n_total <= 0 || ni <= 0 || i0 < 0 || i0 + ni > n_total || kind < 0 || kind > 3 ||
       (kind == LP_DENSITY && !iparam) || (kind == LP_EPSGRAD && !jaux)) {
     set_error("nb_largeN_pass_f32: bad arguments");
     return NB_ERR_ARG;
   }
-  if (g_pass_sm == 0) {
-    int dev = 0;
-    NB_CUDA_CHECK(cudaGetDevice(&dev));
-    NB_CUDA_CHECK(cudaDeviceGetAttribute(&g_pass_sm, cudaDevAttrMultiProcessorCount, dev));
+  int dev = 0, sm = 0;
+  NB_CUDA_CHECK(cudaGetDevice(&dev));
+  NB_CUDA_CHECK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+  LargeNChunks c = largeN_chunks(n_total, ni, LP_IPT, LP_TILE, sm * 4, false);
+  if ((c.jchunk + LP_TILE - 1) / LP_TILE > LP_MAX_TILES) {
+    c.jchunk = LP_MAX_TILES * LP_TILE;
+    c.n_jchunks = (n_total + c.jchunk - 1) / c.jchunk;
+    const int n_units = c.n_ichunks * c.n_jchunks;
+    c.grid = n_units < sm * 4 ? n_units : sm * 4;
   }
-  const LargeNChunks c = largeN_chunks(n_total, ni, LP_IPT, LP_TILE, g_pass_sm * 4, kind == LP_TAUMIN);
   PassArgs a;
+  a.boxes = reinterpret_cast<const TileBox*>(boxes);
   a.xym = reinterpret_cast<const float4*>(xym);
   a.jaux = reinterpret_cast<const float2*>(jaux);
   a.iparam = iparam;
@@ -269,6 +398,7 @@ int largeN_pass(int kind, const float* xym, const float* jaux, int n_total, int 
   a.out = out;
   a.n_ichunks = c.n_ichunks; a.n_jchunks = c.n_jchunks; a.jchunk = c.jchunk;
   if (kind != LP_TAUMIN) NB_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * 2 * (size_t)ni, st));
+  else fill_f64_kernel<<<(ni + 255) / 256, 256, 0, st>>>(out, (size_t)ni, 1.0e300);
   switch (kind) {
     case LP_DENSITY: largeN_pass_kernel<LP_DENSITY><<<c.grid, LN_TPB, 0, st>>>(a); break;
     case LP_EPSGRAD: largeN_pass_kernel<LP_EPSGRAD><<<c.grid, LN_TPB, 0, st>>>(a); break;

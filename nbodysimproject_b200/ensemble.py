@@ -102,8 +102,9 @@ class DeviceBucket:
         self.q = _to_dev(q, torch.float64, self.device).clone()
         self.v = _to_dev(v, torch.float64, self.device).clone()
         self.B, self.N = int(self.m.shape[0]), int(self.m.shape[1])
-        if not (2 <= self.N <= 8):
-            raise L.NBodyB200Error(f"ensemble kernels support N = 2..8 bodies per system, got {self.N}")
+        n_max = 8 if self.mode == L.MODE_HAMSOFT else 64
+        if not (2 <= self.N <= n_max):
+            raise L.NBodyB200Error(f"ensemble kernels support N = 2..{n_max} bodies per system in this mode, got {self.N}")
         self.eps = _to_dev(np.broadcast_to(np.asarray(eps, dtype=np.float64), (self.B,))
                            if not isinstance(eps, torch.Tensor) else eps, torch.float64, self.device)
         self.n_sub = torch.ones((self.B,), dtype=torch.int32, device=self.device)
@@ -132,12 +133,13 @@ class DeviceBucket:
         n = torch.clamp(torch.ceil(abs(float(dt)) / h), 1, int(split_n_max)).to(torch.int32)
         self.n_sub = n.contiguous()
 
-    def sort(self):
+    def sort(self, heavy_threshold: int = -1):
+        """n_sub-descending permutation; heavy_threshold -1 = the automatic, N-only rule (product setting)."""
         torch = self.torch
         self.perm = torch.empty((self.B,), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
             L.check(L.load().nb_sort_by_nsub(L.ptr(self.n_sub), self.B, self.N, L.ptr(self.perm), L.ptr(self._bins),
-                                             L.stream_ptr()), "nb_sort_by_nsub")
+                                             int(heavy_threshold), L.stream_ptr()), "nb_sort_by_nsub")
 
     def run(self, dt, n_steps, sample_interval=0, n_megno=0, raw_dr=None, raw_dv=None, flags=0, want_dyn=True,
             eps_pi=None, hs_params=None, work=None, t_main=None):

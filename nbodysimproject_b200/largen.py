@@ -51,6 +51,8 @@ class LargeNSimulation:
         self.vel = torch.as_tensor(v[self.i0:self.i0 + self.ni].astype(np.float32)).to(self.device).contiguous()
         self.acc = torch.zeros((self.ni, 2), dtype=torch.float32, device=self.device)
         self.sums = torch.zeros((2,), dtype=torch.float64, device=self.device)
+        self.acc_ws = torch.empty((self.ni, 2), dtype=torch.float64, device=self.device)   # fp64 accumulators of a call
+        self.variant = -1                                                                  # kernel variant (A-B tests)
         self._have_acc = False
         self.force_evals = 0
 
@@ -66,7 +68,8 @@ class LargeNSimulation:
         with torch.cuda.device(self.device):
             L.check(L.load().nb_largeN_accel_f32(L.ptr(self.xym), self.n, self.i0, self.ni, self.eps, self.G,
                                                  L.ptr(self.acc), L.ptr(self.sums) if with_sums else None,
-                                                 L.stream_ptr()), "nb_largeN_accel_f32")
+                                                 L.ptr(self.acc_ws), int(self.variant), L.stream_ptr()),
+                    "nb_largeN_accel_f32")
         self.force_evals += 1
         self._have_acc = True
         return self.acc

@@ -258,12 +258,20 @@ def analyze_simulations(sims, n_steps: int, dt: float, mode: str, via: str = "de
 
 
 def _analyze_minimal(m, q, v, eps, G, imode, n_steps, dt, top, group):
-    bk = E.DeviceBucket(m, q, v, eps, G, imode, group[0].device)
-    bk.prepare(L.PREP_SNAPSHOT_KICK, float(top[0]), float(group[0].cfg.initial_dt), dt, int(group[0].cfg.split_n_max))
-    vk = bk.v.cpu().numpy()
-    bk.sort()
-    dyn = bk.run(dt, n_steps, 0, 0, flags=L.RUN_ENERGY).cpu().numpy()
-    return dyn, None, bk.status.cpu().numpy(), vk
+    """'minimal' mode: energy drift only.  snapshot() kicks every sim with ITS OWN last |dt|
+    (integration_scheme_base.py:154-175), so sims last stepped with different dt are prepared per kick size, like the
+    core / full branch."""
+    B = m.shape[0]
+    dyn = np.empty((B, L.N_DYN)); status = np.zeros(B, dtype=np.int32); vk = np.empty_like(v)
+    for t in np.unique(top):
+        sel = np.where(top == t)[0]
+        bk = E.DeviceBucket(m[sel], q[sel], v[sel], eps[sel], G, imode, group[0].device)
+        bk.prepare(L.PREP_SNAPSHOT_KICK, float(t), float(group[0].cfg.initial_dt), dt, int(group[0].cfg.split_n_max))
+        vk[sel] = bk.v.cpu().numpy()
+        bk.sort()
+        dyn[sel] = bk.run(dt, n_steps, 0, 0, flags=L.RUN_ENERGY).cpu().numpy()
+        status[sel] = bk.status.cpu().numpy()
+    return dyn, None, status, vk
 
 
 def _analyze_adaptive(group, m, q, v, G, imode, n_steps, dt, mode, interval, n_megno, rr, rv):

@@ -72,13 +72,14 @@ def test_bad_arguments_return_error_codes_without_touching_the_gpu():
         lib.nb_ensemble_run_f64(N, N, N, N, 1.0, 4, 3, 0, 0, 0.01, 1, 0, 0, N, N, N, N, N, N, N, N, N, N),
         lib.nb_ensemble_run_f64(p, p, p, p, 1.0, 4, 3, 0, 0, 0.01, 1, 0, 5, N, N, N, N, N, N, N, N, N, N),   # megno without draws
         lib.nb_ensemble_run_adaptive_f64(N, N, N, N, N, 1.0, 4, 3, 0, 0.01, 1, N, 1e9, 5, N, N, N, N),
-        lib.nb_sort_by_nsub(N, 4, 3, N, N, N),
-        lib.nb_ensemble_set_heavy_nsub(64),
-        lib.nb_largeN_accel_f32(N, 10, 0, 10, 0.1, 1.0, N, N, N),
-        lib.nb_largeN_accel_f32(p, 10, 5, 10, 0.1, 1.0, p, N, N),                      # i-range outside n_total
-        lib.nb_largeN_pass_f32(7, p, N, 10, 0, 10, N, 0.0, p, N),                      # unknown kind
-        lib.nb_largeN_pass_f32(0, p, N, 10, 0, 10, N, 0.0, p, N),                      # DENSITY without h
-        lib.nb_largeN_set_variant(99),
+        lib.nb_sort_by_nsub(N, 4, 3, N, N, -1, N),
+        lib.nb_sort_by_nsub(p, 4, 3, p, p, 64, N),                                     # threshold out of range
+        lib.nb_largeN_accel_f32(N, 10, 0, 10, 0.1, 1.0, N, N, N, -1, N),
+        lib.nb_largeN_accel_f32(p, 10, 5, 10, 0.1, 1.0, p, N, p, -1, N),                # i-range outside n_total
+        lib.nb_largeN_accel_f32(p, 10, 0, 10, 0.1, 1.0, p, N, N, -1, N),                # no workspace
+        lib.nb_largeN_accel_f32(p, 10, 0, 10, 0.1, 1.0, p, N, p, 99, N),                # unknown variant
+        lib.nb_largeN_pass_f32(7, p, N, 10, 0, 10, N, 0.0, p, N, N),                      # unknown kind
+        lib.nb_largeN_pass_f32(0, p, N, 10, 0, 10, N, 0.0, p, N, N),                      # DENSITY without h
         lib.nb_mlp_classify_f32(p, p, p, 65, p, p, p, p, p, p, p, 0.0, 0.5, 4, p, N, N),   # F > 64
         lib.nb_generate_ensemble_f64(9, 3, 4, 1, 0, p, p, p, p, N),                     # unknown cohort
         lib.nb_generate_ensemble_f64(1, 4, 4, 1, 0, p, p, p, p, N),                     # hierarchical needs N = 3
@@ -87,6 +88,5 @@ def test_bad_arguments_return_error_codes_without_touching_the_gpu():
     ]
     assert all(rc < 0 for rc in cases), cases
     assert lib.nb_last_error().decode() != ""
-    assert lib.nb_ensemble_set_heavy_nsub(-1) == 0 and lib.nb_largeN_set_variant(-1) == 0
     # adaptive softening exists for verlet / yoshida4 only
     assert lib.nb_ensemble_run_adaptive_f64(p, p, p, p, p, 1.0, 4, 3, 2, 0.01, 1, N, 1e9, 5, N, N, N, N) == -3

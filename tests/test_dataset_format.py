@@ -54,3 +54,18 @@ def test_committed_sample_loads():
     from nbodysimproject_b200 import dataset as D
     X, y, fn = D.StabilityDataset.load(os.path.join(GOLDEN, "dataset_sample.csv"))
     assert X.shape[0] == y.shape[0] == 6 and X.shape[1] == len(fn)
+
+
+def test_classifier_feature_index_matches_the_written_table(tmp_path):
+    """The gather map of the inference kernel lists exactly the columns the loader returns, in the loader's order."""
+    from nbodysimproject_b200 import dataset as D
+    from nbodysimproject_b200.classifier import default_feature_index, COL_PATHOLOGICAL
+    dyn, static = _tensors()
+    for mode, n in (("full", 42), ("core", 17)):
+        df = D.table_from_tensors(dyn, static if mode == "full" else None, mode)
+        path = str(tmp_path / f"{mode}.csv")
+        names = D.save_feature_table(path, df)
+        X, y, fn = D.StabilityDataset.load(path)
+        idx_names, idx = default_feature_index(mode)
+        assert fn == names == idx_names and X.shape[1] == n == len(idx)
+        assert idx[-1] == COL_PATHOLOGICAL and names[-1] == "pathological_energy"

@@ -235,16 +235,14 @@ def test_heavy_substep_mapping_matches_thread_mapping(E, O):
         res = {}
         # force the fixed threshold 4 so that every N exercises its latency mapping (the automatic threshold keeps
         # e.g. all N = 3 systems on the thread mapping, where the fast mapping gains nothing)
-        L.check(L.load().nb_ensemble_set_heavy_nsub(4))
         for use_sort in (False, True):
             bk = E.DeviceBucket(m, q, v, 0.3, 1.0, mode)
             bk.prepare(L.PREP_REMOVE_COM | L.PREP_CTOR_KICK, 0.01, 0.01, 0.01)
             if use_sort:
-                bk.sort()
+                bk.sort(heavy_threshold=4)
             dyn = bk.run(0.01, 40, 2, 10, rr, rv, flags=L.RUN_ENERGY | L.RUN_WRITE_STATE)
             res[use_sort] = (bk.q.cpu().numpy(), bk.v.cpu().numpy(), dyn.cpu().numpy(), bk.n_sub.cpu().numpy(),
                              bk.status.cpu().numpy())
-        L.check(L.load().nb_ensemble_set_heavy_nsub(-1))
         nsub = res[True][3]
         assert (nsub > 4).sum() > 10 and (nsub <= 4).sum() >= 0
         assert np.all(res[True][4] == 0)
@@ -280,12 +278,10 @@ def test_heavy_threshold_depends_on_n_only_and_results_are_shard_invariant(E, O)
     v = rng.randn(B, N, 2) * 0.3
 
     def run(sl, thr=-1):
-        L.check(L.load().nb_ensemble_set_heavy_nsub(thr))
         bk = E.DeviceBucket(m[sl], q[sl], v[sl], 0.3, 1.0, "yoshida4")
         bk.prepare(L.PREP_REMOVE_COM | L.PREP_CTOR_KICK, 0.01, 0.01, 0.01)
-        bk.sort()
+        bk.sort(heavy_threshold=thr)
         dyn = bk.run(0.01, 30, 3, 0, flags=L.RUN_ENERGY | L.RUN_WRITE_STATE)
-        L.check(L.load().nb_ensemble_set_heavy_nsub(-1))
         return bk.q.cpu().numpy(), dyn.cpu().numpy(), int(bk._bins[64]), int(bk._bins[65]), bk.n_sub.cpu().numpy()
 
     full = run(slice(0, B))

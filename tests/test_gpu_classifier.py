@@ -23,12 +23,15 @@ def test_mlp_matches_torch_fp32(mode, B):
     dyn = rng.standard_normal((B, L.N_DYN)) * 3.0
     stat = rng.standard_normal((B, L.N_STATIC)) * 3.0
     dyn[::7, 5] = np.nan                                    # nan_to_num path
+    dyn[::11, 1] = 40.0                                     # pathological energy drift -> derived column = 1
     mean, scale = rng.standard_normal(F), rng.uniform(0.5, 2.0, F)
     clf = StabilityClassifier.from_state_dict(sd, mean=mean, scale=scale, threshold=0.37, feature_index=idx)
     d_dyn, d_stat = torch.as_tensor(dyn).cuda(), torch.as_tensor(stat).cuda()
     prob, label = clf.predict(d_dyn, d_stat if mode == "full" else None)
     # torch fp32 reference
-    X = np.concatenate([dyn[:, :], stat], axis=1)[:, [c if c < 64 else L.N_DYN + (c - 64) for c in idx]]
+    patho = (np.abs(dyn[:, L.DYN_COLUMNS.index("energy_drift")]) > 10.0).astype(float)
+    wide = np.concatenate([dyn, stat, patho[:, None]], axis=1)
+    X = wide[:, [c if c < 63 else (L.N_DYN + L.N_STATIC if c == 63 else L.N_DYN + (c - 64)) for c in idx]]
     X = np.nan_to_num(X, nan=0.0)
     Xs = torch.as_tensor(((X.astype(np.float32) - mean.astype(np.float32)) * (1.0 / scale).astype(np.float32)))
     with torch.no_grad():
@@ -62,3 +65,36 @@ def test_classifier_on_real_feature_tensors():
     p = prob.cpu().numpy()
     assert p.shape == (B,) and np.all(np.isfinite(p[np.isfinite(dyn.cpu().numpy()).all(1)]))
     assert set(np.unique(label.cpu().numpy())) <= {0, 1}
+
+
+def test_reference_trained_layout_round_trip(tmp_path):
+    """A model trained by the reference's train_mlp on a table written from the feature tensors has one input per column
+    StabilityDataset.load returns (42 in full mode: 16 dynamic + 25 static + pathological_energy).  Its state_dict must be
+    accepted with the DEFAULT feature index, and the kernel's gather must line up with the loader's matrix and the
+    scaler vectors column for column (the derived column was missing from the index)."""
+    import torch
+    from nbodysimproject_b200 import _lib as L, dataset as D
+    from nbodysimproject_b200.classifier import StabilityClassifier, default_feature_index
+    rng = np.random.default_rng(3)
+    B = 600
+    dyn = rng.standard_normal((B, L.N_DYN)) * 2.0
+    dyn[:, 0] = (rng.random(B) > 0.5).astype(float)
+    dyn[::9, 1] = 30.0
+    dyn[::13, 6] = np.nan
+    stat = rng.standard_normal((B, L.N_STATIC)) * 2.0
+    df = D.table_from_tensors(dyn, stat, "full")
+    path = str(tmp_path / "t.csv")
+    names = D.save_feature_table(path, df)
+    X, y, fn = D.StabilityDataset.load(path)
+    assert X.shape == (B, 42) and fn == names == default_feature_index("full")[0]
+    mean, scale = X.mean(0), X.std(0) + 0.5
+    torch.manual_seed(4)
+    fc1, fc2, fc3 = torch.nn.Linear(42, 128), torch.nn.Linear(128, 64), torch.nn.Linear(64, 1)
+    sd = {"fc1.weight": fc1.weight, "fc1.bias": fc1.bias, "fc2.weight": fc2.weight, "fc2.bias": fc2.bias,
+          "fc3.weight": fc3.weight, "fc3.bias": fc3.bias}
+    clf = StabilityClassifier.from_state_dict(sd, mean=mean, scale=scale)          # default index
+    prob, _ = clf.predict(torch.as_tensor(dyn).cuda(), torch.as_tensor(stat).cuda())
+    Xs = torch.as_tensor(((X.astype(np.float32) - mean.astype(np.float32)) * (1.0 / scale).astype(np.float32)))
+    with torch.no_grad():
+        ref = torch.sigmoid(fc3(torch.relu(fc2(torch.relu(fc1(Xs)))))).reshape(-1).numpy()
+    assert np.max(np.abs(prob.cpu().numpy() - ref)) < 5e-5

@@ -104,7 +104,7 @@ def test_c5_full_size_force_properties():
     rms = ref.pow(2).mean().sqrt()
     assert float((acc[idx] - ref).abs().max() / rms) < 2e-5
     # scalar fp32 kernel (v1) and packed f32x2 kernel (default) agree
-    L.check(L.load().nb_largeN_set_variant(1))
+    sim.variant = 1
     acc1 = sim.accelerations().double().clone()
-    L.check(L.load().nb_largeN_set_variant(-1))
+    sim.variant = -1
     assert float((acc1 - acc).abs().max() / acc.abs().max()) < 1e-5

@@ -42,7 +42,7 @@ def test_passes_vs_dense_numpy(n):
 
     def run(kind, iparam=None, eps=0.0):
         L.check(lib.nb_largeN_pass_f32(kind, L.ptr(sim.xym), L.ptr(jaux), n, 0, n, L.ptr(iparam), eps, L.ptr(out),
-                                       L.stream_ptr()))
+                                       None, L.stream_ptr()))
         return out.cpu().numpy().copy()
 
     # DENSITY: S0, S1

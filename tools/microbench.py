@@ -48,7 +48,7 @@ def ensemble(B=1 << 17, steps=200):
 
 
 def largen(n=1 << 18):
-    """Variant is latched from NB_LARGEN_VARIANT on first use: run once per variant in a fresh process."""
+    """All kernel variants of the large-N force (the variant is an argument of nb_largeN_accel_f32)."""
     import ctypes
     rng = np.random.RandomState(0)
     xym = np.zeros((n, 4), dtype=np.float32)
@@ -57,18 +57,17 @@ def largen(n=1 << 18):
     d = torch.as_tensor(xym).cuda()
     acc = torch.empty((n, 2), dtype=torch.float32, device="cuda")
     sums = torch.zeros(2, dtype=torch.float64, device="cuda")
+    ws = torch.empty((n, 2), dtype=torch.float64, device="cuda")
     lib = L.load()
     for variant in (1, 8, 9, 10):
-      L.check(lib.nb_largeN_set_variant(variant))
-      os.environ["NB_LARGEN_VARIANT"] = str(variant)
       for with_sums in (False, True):
           def run():
               L.check(lib.nb_largeN_accel_f32(L.ptr(d), n, 0, n, 1e-3, 1.0, L.ptr(acc),
-                                              L.ptr(sums) if with_sums else None, L.stream_ptr()))
+                                              L.ptr(sums) if with_sums else None, L.ptr(ws), variant, L.stream_ptr()))
           run()
           t = ev_time(run)
           pairs = float(n) * n
-          print(f"largeN n={n} variant={os.environ.get('NB_LARGEN_VARIANT')} sums={with_sums}: {pairs/t:.3e} pairs/s "
+          print(f"largeN n={n} variant={variant} sums={with_sums}: {pairs/t:.3e} pairs/s "
                 f"{pairs*14/t*1e-12:.2f} TFLOP/s(14/pair) t={t*1e3:.2f} ms", flush=True)
 
 
