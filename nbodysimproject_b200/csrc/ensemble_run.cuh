@@ -21,6 +21,13 @@
 #include "ensemble_group.cuh"
 #include "ensemble_pairlane.cuh"
 
+#ifndef NB_WH_MINB
+#define NB_WH_MINB 3          // whfast main kernel: resident CTAs per SM the register allocation must allow (N <= NB_WH_MINB_MAXN)
+#endif
+#ifndef NB_WH_MINB_MAXN
+#define NB_WH_MINB_MAXN 5
+#endif
+
 namespace nb {
 
 // ---------------------------------------------------------------------------------------------
@@ -250,7 +257,7 @@ __host__ __device__ constexpr bool use_pairlane() { return N >= 5 && MODE != NB_
 // Nothing in here takes the address of the state, so it stays in registers for the whole run.
 // ---------------------------------------------------------------------------------------------
 template <int N, int MODE, bool GUARD, bool EXACT>
-__global__ void __launch_bounds__(128) ensemble_main_kernel(RunArgs a, int write_state) {
+__global__ void __launch_bounds__(128, (MODE == NB_MODE_WHFAST && N <= NB_WH_MINB_MAXN) ? NB_WH_MINB : 1) ensemble_main_kernel(RunArgs a, int write_state) {
   const int bid = (int)blockIdx.x + a.block0;                          // logical CTA (the launch may be split head / rest)
   stamp_begin(a.tstamp);
   if (MODE != NB_MODE_WHFAST && bid < a.group_blocks) {                // latency-optimised mappings for the n_sub-heavy head

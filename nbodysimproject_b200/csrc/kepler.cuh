@@ -89,13 +89,21 @@ __device__ __forceinline__ int kepler_reference(double& rx, double& ry, double& 
   // chi_new == chi; an exact 2-cycle therefore runs to the 64-iteration cap -- 4 % of all planetary solves.)
   double x2 = __longlong_as_double(0x7ff8000000000000LL);
   sd c0, c1, c2, c3;
+  // Stumpff c2 / c3 of the previous iterate, and whether (c2, c3) below belong to the FINAL iterate: the reference
+  // re-evaluates its series at the final chi (kepler_solver.py:81-83); whenever the loop has just evaluated it at that
+  // very chi -- every exit except the 64-iteration cap -- the values are reused (same input, same bits; one of ~10
+  // series evaluations per solve saved)
+  double c2p = 0.0, c3p = 0.0;
+  bool have_c = false;
   int it = 0;
   double last_step = 0.0;
   const sd k1 = r0 * vr0 / sqrt_mu, k2 = sd(1.0) - alpha * r0, k3 = sqrt_mu * dt;     // loop invariants, same rounding
   for (; it < 64;) {
     ++it;
     const sd z = alpha * chi * chi;
+    c2p = c2.v; c3p = c3.v;
     cfunc_reference(z.v, c0, c1, c2, c3);
+    have_c = true;                               // (c2, c3) belong to the current chi
     const sd f = k1 * chi * chi * c1 + k2 * chi * chi * chi * c2 + r0 * chi - k3;
     const sd fp = k1 * chi * (sd(1.0) - alpha * chi * chi * c2) + k2 * chi * chi * c1 + r0;
     if (fp.v == 0.0) break;
@@ -109,20 +117,27 @@ __device__ __forceinline__ int kepler_reference(double& rx, double& ry, double& 
     // iterates alternate between chi_new and chi for the rest of the reference's 64 iterations; its final iterate is
     // the one with the parity of 64.  Detected after ~8 iterations instead of running all 64 in lock-step per warp.
     if (chi_new.v == x2) {
-      if (((64 - it) & 1) == 0) chi = chi_new;
+      if (((64 - it) & 1) == 0) {                // final iterate = chi_new == the iterate BEFORE chi: its series values
+        chi = chi_new;
+        c2 = sd(c2p); c3 = sd(c3p);
+        have_c = it >= 2;
+      }
       executed += it - 64;                       // counted work = iterations actually executed, not the reference's 64
       it = 64;
       break;
     }
     x2 = chi.v;
     chi = chi_new;
+    have_c = false;                              // the new chi has not been evaluated yet
   }
   // the reference's exit test is exact equality, so running into the 64-iteration cap while hovering within a
   // few ulps of the root is normal; only a cap hit with a still-moving iterate is reported (as 65)
   executed += it;
   if (it >= 64 && !(last_step <= 1e-9 * fabs(chi.v))) it = 65;
-  const sd z = alpha * chi * chi;
-  cfunc_reference(z.v, c0, c1, c2, c3);
+  if (!have_c) {
+    const sd z = alpha * chi * chi;
+    cfunc_reference(z.v, c0, c1, c2, c3);
+  }
   const sd f = sd(1.0) - chi * chi * c2 / r0;
   const sd g = dt - chi * chi * chi * c3 / sqrt_mu;
   const sd nx = f * r_x + g * v_x;

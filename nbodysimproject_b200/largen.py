@@ -20,7 +20,11 @@ from . import _lib as L
 
 class LargeNSimulation:
     def __init__(self, masses, positions, velocities=None, G: float = 1.0, softening: float = 1e-3,
-                 integrator_mode: str = "verlet", device=None, group=None, distributed: bool = True):
+                 integrator_mode: str = "verlet", device=None, group=None, distributed: bool = True,
+                 spatial_sort: bool = False):
+        """spatial_sort: store the particles along a Morton (Z-order) curve.  Results do not depend on the storage
+        order; `positions` / `velocities` / `accelerations_in_input_order` give the caller's order back.  The ham_soft
+        subclass switches it on: its eps* passes skip tiles whose particles are all farther than 9.35 h apart."""
         torch = L.require_cuda()
         import torch.distributed as dist
         self.torch = torch
@@ -44,6 +48,10 @@ class LargeNSimulation:
         self.eps = float(softening)
         # COM velocity removal like the facade (simulation.py:85-86)
         v = v - np.sum(m[:, None] * v, axis=0) / np.sum(m)
+        self.order = None                    # storage index -> input index
+        if spatial_sort and self.n > 1:
+            self.order = morton_order(q)
+            m, q, v = m[self.order], q[self.order], v[self.order]
         xym = np.zeros((self.n, 4), dtype=np.float32)
         xym[:, 0:2] = q
         xym[:, 2] = m
@@ -60,6 +68,31 @@ class LargeNSimulation:
     @property
     def local(self):
         return self.xym[self.i0:self.i0 + self.ni]
+
+    def _to_input_order(self, a):
+        """numpy array indexed by storage position (all N particles) -> the caller's particle order"""
+        if self.order is None:
+            return a
+        out = np.empty_like(a)
+        out[self.order] = a
+        return out
+
+    def _gather_local(self, t):
+        if self.dist is not None and self.world > 1:
+            out = self.torch.empty((self.n,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
+            self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+            return out
+        return t
+
+    @property
+    def positions(self):
+        """[N, 2] fp64 positions in the caller's order (all ranks hold all positions)."""
+        return self._to_input_order(self.xym[:, :2].double().cpu().numpy())
+
+    @property
+    def velocities(self):
+        """[N, 2] fp64 velocities in the caller's order (gathered over the ranks)."""
+        return self._to_input_order(self._gather_local(self.vel).double().cpu().numpy())
 
     def accelerations(self, with_sums: bool = False):
         torch = self.torch
@@ -152,7 +185,7 @@ class LargeNHamSoftSimulation(LargeNSimulation):
                  theta_cap: float = 0.1, theta_imp: float = 0.5, alpha: float = 0.1, eta: float = 1.35,
                  chi_pi: float = 0.2, j_max_cap: float = 0.02, initial_dt: float = 0.01, use_soft_barrier: bool = True,
                  disable_barrier: bool = False, split_n_max: int = 50, device=None, group=None,
-                 distributed: bool = True):
+                 distributed: bool = True, spatial_sort: bool = True, cull: bool = True):
         min_softening = max(0.0, float(min_softening))
         softening = float(softening)
         if softening < 0.0:
@@ -161,7 +194,8 @@ class LargeNHamSoftSimulation(LargeNSimulation):
             min_softening = 0.1 * softening                         # simulation.py:88-114
         s0 = max(softening, min_softening)
         super().__init__(masses, positions, velocities, G=G, softening=s0, integrator_mode="verlet", device=device,
-                         group=group, distributed=distributed)
+                         group=group, distributed=distributed, spatial_sort=spatial_sort)
+        self.cull = bool(cull)
         torch = self.torch
         self.mode = "ham_soft"
         self.s0 = s0
@@ -182,6 +216,11 @@ class LargeNHamSoftSimulation(LargeNSimulation):
         self.jaux = torch.zeros((n_pad, 2), dtype=torch.float32, device=self.device)
         self.out64 = torch.zeros((self.ni, 2), dtype=torch.float64, device=self.device)
         self.acc_sums = torch.zeros((2,), dtype=torch.float64, device=self.device)
+        n_tiles = (self.n + 511) // 512
+        self.boxes = torch.zeros((n_tiles, 8), dtype=torch.float32, device=self.device)   # NB_LN_BOX_FLOATS per NB_LN_TILE
+        self._pos_version = 0            # bumped by every drift: tile boxes and the legacy direction depend on q only
+        self._boxes_version = (-1, False)
+        self._unit_cache = None
         # ---- constructor calibration
         self._calibrate_from_initial_conditions()
         if not (math.isfinite(self.k_soft) and self.k_soft > 0.0):
@@ -209,13 +248,29 @@ class LargeNHamSoftSimulation(LargeNSimulation):
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
         return t
 
+    def _tile_boxes(self, with_jaux: bool):
+        """Bounding boxes (+ the smallest exponent scale of jaux) of the 512-particle tiles for the current positions."""
+        key = (self._pos_version, bool(with_jaux))
+        if with_jaux or self._boxes_version != key:
+            torch = self.torch
+            with torch.cuda.device(self.device):
+                L.check(L.load().nb_largeN_tile_boxes_f32(L.ptr(self.xym), L.ptr(self.jaux) if with_jaux else None, self.n,
+                                                          L.ptr(self.boxes), L.stream_ptr()), "nb_largeN_tile_boxes_f32")
+            self._boxes_version = key
+        return self.boxes
+
     def _pass(self, kind, iparam=None, eps=0.0):
         torch = self.torch
+        boxes = None
+        if self.cull and kind in (LN_DENSITY, LN_EPSGRAD):
+            boxes = self._tile_boxes(kind == LN_EPSGRAD)
         with torch.cuda.device(self.device):
             L.check(L.load().nb_largeN_pass_f32(kind, L.ptr(self.xym), L.ptr(self.jaux), self.n, self.i0, self.ni,
-                                                L.ptr(iparam), float(eps), L.ptr(self.out64), L.stream_ptr()),
-                    "nb_largeN_pass_f32")
+                                                L.ptr(iparam), float(eps), L.ptr(self.out64), L.ptr(boxes),
+                                                L.stream_ptr()), "nb_largeN_pass_f32")
         self.n_passes += 1
+        if boxes is None:
+            self.n_full_passes = getattr(self, "n_full_passes", 0) + 1
         return self.out64
 
     # ---- barrier (barrier.py:66-113) ----------------------------------------------------------------
@@ -306,7 +361,11 @@ class LargeNHamSoftSimulation(LargeNSimulation):
             self.dist.all_gather_into_tensor(self.jaux[:self.n], self.jaux[self.i0:self.i0 + self.ni], group=self.group)
         g = self._pass(LN_EPSGRAD).clone()
         g = torch.where(torch.isfinite(g), g, torch.zeros_like(g))
-        u = self._pass(LN_UNITGRAD)                 # legacy gradient = -c_pref * u with c_pref > 0
+        # legacy gradient = -c_pref * u with c_pref > 0; u depends on the positions only, and the S half-flow that ends a
+        # sub-step and the one that opens the next see the same positions: one long-range pass serves both
+        if self._unit_cache is None or self._unit_cache[0] != self._pos_version:
+            self._unit_cache = (self._pos_version, self._pass(LN_UNITGRAD).clone())
+        u = self._unit_cache[1]
         dot = float(self._allsum(-(g * u).sum()))
         if math.isfinite(dot) and dot < 0.0:
             g = -g
@@ -481,6 +540,7 @@ class LargeNHamSoftSimulation(LargeNSimulation):
         self.s_half(h)
         self.v_half_kick(h)
         self._kick_drift(0.0, h)
+        self._pos_version += 1
         self._gather()
         self.v_half_kick(h)
         self.s_half(h)
@@ -506,6 +566,25 @@ class LargeNHamSoftSimulation(LargeNSimulation):
             p = self.n_exp - 1
             H += (self.k_wall / p) * (max(0.0, a - self.eps) ** p + max(0.0, self.eps - b) ** p)
         return H
+
+
+def morton_order(q, bits: int = 16):
+    """Permutation that sorts 2-D points along a Z-order curve (interleaved bits of the quantised coordinates)."""
+    q = np.asarray(q, dtype=np.float64)
+    lo, hi = q.min(0), q.max(0)
+    span = np.maximum(hi - lo, 1e-300)
+    g = np.minimum(((q - lo) / span * (1 << bits)).astype(np.uint64), (1 << bits) - 1)
+
+    def spread(x):
+        x = x & np.uint64(0xFFFF)
+        x = (x | (x << np.uint64(8))) & np.uint64(0x00FF00FF)
+        x = (x | (x << np.uint64(4))) & np.uint64(0x0F0F0F0F)
+        x = (x | (x << np.uint64(2))) & np.uint64(0x33333333)
+        x = (x | (x << np.uint64(1))) & np.uint64(0x55555555)
+        return x
+
+    key = spread(g[:, 0]) | (spread(g[:, 1]) << np.uint64(1))
+    return np.argsort(key, kind="stable")
 
 
 def make_disc(n: int, seed: int = 0):

@@ -143,3 +143,46 @@ def test_extended_hamiltonian_is_conserved():
     assert abs(H1 - H0) < 2e-4 * abs(H0)
     assert np.all(np.abs(P1[:2] - P0[:2]) < 1e-5)
     assert sim.eps_min <= sim.eps <= sim.eps_max
+
+
+def test_locality_culling_drops_only_exact_zeros_and_storage_order_is_invisible():
+    """The DENSITY / EPSGRAD passes skip (i-block, j-tile) pairs whose bounding boxes are farther apart than 9.35 h
+    (ex2.approx.ftz is exactly zero there).  Culled and unculled passes agree to the order of the cross-chunk fp64
+    atomics (1e-14); a Morton-sorted simulation gives the caller's particle order back and tracks the unsorted one to
+    fp32 summation-order noise."""
+    import math
+    import torch
+    from nbodysimproject_b200 import largen as LN
+    n = 20000
+    m, q, v = LN.make_disc(n, seed=3)
+    soft = 2.0 / math.sqrt(n)
+    a = LN.LargeNHamSoftSimulation(m, q, v, softening=soft, initial_dt=1e-3)                         # sorted, culled
+    b = LN.LargeNHamSoftSimulation(m, q, v, softening=soft, initial_dt=1e-3, cull=False)             # sorted, every tile
+    c = LN.LargeNHamSoftSimulation(m, q, v, softening=soft, initial_dt=1e-3, spatial_sort=False, cull=False)
+    assert a.order is not None and c.order is None
+    assert np.allclose(a.positions, q, rtol=0, atol=1e-6) and np.allclose(c.positions, q, rtol=0, atol=1e-6)
+    # single passes: same h, same jaux -> same sums
+    h = torch.full((n,), 0.7 * soft, dtype=torch.float32, device="cuda")
+    da = a._pass(LN.LN_DENSITY, h).clone()
+    db = b._pass(LN.LN_DENSITY, h).clone()
+    assert float((da - db).abs().max()) <= 1e-14 * float(db.abs().max())
+    assert float(db.abs().max()) > 0
+    es_a, g_a = a.eps_star_and_grad()
+    es_b, g_b = b.eps_star_and_grad()
+    assert abs(es_a - es_b) <= 1e-13 * abs(es_b)
+    assert float((g_a - g_b).abs().max()) <= 1e-12 * float(g_b.abs().max())
+    # the culled simulation really skips work: boxes of distant tiles fail the test
+    bx = a._tile_boxes(False).cpu().numpy()
+    ext = max(bx[:, 2].max() - bx[:, 0].min(), bx[:, 3].max() - bx[:, 1].min())
+    assert np.median(np.maximum(bx[:, 2] - bx[:, 0], bx[:, 3] - bx[:, 1])) < 0.35 * ext      # tiles are compact
+    hsub = 1e-3 / a.frozen_n_sub
+    for sim in (a, b, c):
+        for _ in range(2):
+            sim.strang_step(hsub)
+    assert abs(a.eps - b.eps) <= 1e-12 * abs(b.eps) and abs(a.pi - b.pi) <= 1e-9 * max(abs(b.pi), 1e-9)
+    assert np.max(np.abs(a.positions - b.positions)) <= 1e-12
+    assert abs(a.eps - c.eps) <= 2e-5 * abs(c.eps)
+    assert np.max(np.abs(a.positions - c.positions)) <= 2e-6 * np.max(np.abs(c.positions))
+    assert np.max(np.abs(a.velocities - c.velocities)) <= 2e-4 * np.max(np.abs(c.velocities))
+    # one long-range UNITGRAD pass per sub-step (shared by the closing and the next opening S half-flow)
+    assert a._unit_cache is not None
