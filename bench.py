@@ -434,7 +434,7 @@ def ensemble_section(args, ctx):
     B_total = args.systems
     inp = make_inputs(B_total, seed=42 + rank)
     Ns = sorted(inp, reverse=True)   # launch the large-N buckets first: their sequential sub-step tails are the longest
-    host, devb = {}, {}
+    host, devb, devb2 = {}, {}, {}
     h2d = 0
     for N in Ns:
         d = inp[N]
@@ -448,13 +448,23 @@ def ensemble_section(args, ctx):
         hb["nsub"] = torch.empty((B,), dtype=torch.int32).pin_memory()
         hb["status"] = torch.empty((B,), dtype=torch.int32).pin_memory()
         host[N] = hb
-        bk = E.DeviceBucket(hb["m"], hb["q"], hb["v"], hb["eps"], 1.0, MODE, dev)
-        bk.v0 = bk.v.clone()
-        bk.q0 = bk.q.clone()
-        bk.rdr = hb["raw_dr"].to(dev)
-        bk.rdv = hb["raw_dv"].to(dev)
-        bk.stream = torch.cuda.Stream(device=dev)
-        devb[N] = bk
+        sets = []
+        for _ in range(1):          # one buffer / stream set (two sets interleaved worse: the step time became order-sensitive)
+            bk = E.DeviceBucket(hb["m"], hb["q"], hb["v"], hb["eps"], 1.0, MODE, dev)
+            if sets:
+                bk.v0, bk.q0, bk.rdr, bk.rdv = sets[0].v0, sets[0].q0, sets[0].rdr, sets[0].rdv
+            else:
+                bk.v0 = bk.v.clone()
+                bk.q0 = bk.q.clone()
+                bk.rdr = hb["raw_dr"].to(dev)
+                bk.rdv = hb["raw_dv"].to(dev)
+            # highest priority, like the slot streams of the host entry point: nb_ensemble_run_f64 then demotes only the
+            # BULK of each main kernel to an internal normal-priority stream, so every latency-bound piece (the
+            # sub-step-heavy heads, the MEGNO kernels with their own tails, energy / finalize) is dispatched first
+            bk.stream = torch.cuda.Stream(device=dev, priority=-1)
+            sets.append(bk)
+        devb2[N] = sets
+        devb[N] = sets[0]
     del inp
     prep_flags = L.PREP_REMOVE_COM | L.PREP_CTOR_KICK | L.PREP_SNAPSHOT_KICK
     interval = max(1, N_STEPS // 100)
@@ -465,34 +475,45 @@ def ensemble_section(args, ctx):
     stamps = {N: torch.tensor([[I64MAX, 0]] * (args.steps + 1), dtype=torch.int64, device=dev) for N in Ns}
     timed_step = [0]
 
+    step_no = [0]
+    # launch order of the buckets: the large-N buckets first (their sequential sub-step tails are the longest)
+    issue_order = [int(x) for x in args.order.split(",")] if args.order else list(Ns)
+
     def step_device(record=False, first=False, last=False):
         """One step = one full pass of the analysis over every bucket.  Consecutive steps are independent batches and are
         enqueued back to back on the bucket streams WITHOUT a device-wide join in between (each bucket's stream keeps its
-        own steps in order), so the sub-step-heavy tail of one step overlaps the bulk of the next, as in any pipelined
-        deployment; the timed region starts with a fork from the timing stream and ends with a join into it."""
+        own steps in order), so the sub-step-heavy tail of one bucket overlaps the next step of the others, as in any
+        pipelined deployment; the timed region starts with a fork from the timing stream and ends with a join into it.
+        (Alternating two buffer / stream sets, as the e2e leg does through the host entry point's slots, was tried and
+        made the device-resident step time launch-order sensitive, 54-90 ms; one set is stable at ~55 ms.)"""
         nonlocal launches_per_step
         cur = torch.cuda.current_stream()
         n = 0
+        par = 0
+        step_no[0] += 1
         # the construction-time kernels of every bucket first (0.3 % of the step), then the runs: nb_ensemble_run_f64
         # launches each bucket's sub-step-heavy head at high priority, so no head waits behind another bucket's bulk
-        for N in Ns:
-            bk = devb[N]
+        for N in issue_order:
+            bk = devb2[N][par]
             if first:
-                bk.stream.wait_stream(cur)
+                for b2 in devb2[N]:
+                    b2.stream.wait_stream(cur)
             with torch.cuda.stream(bk.stream):
                 bk.q.copy_(bk.q0)
                 bk.v.copy_(bk.v0)
                 bk.prepare(prep_flags, 0.01, 0.01, DT, 50, want_static=True)     # 1 kernel
                 bk.sort(args.heavy_threshold)                                    # 3 kernels
-        for N in Ns:
-            bk = devb[N]
+        for N in issue_order:
+            bk = devb2[N][par]
             with torch.cuda.stream(bk.stream):
                 ts = stamps[N][timed_step[0]] if record else None
                 bk.dyn = bk.run(DT, N_STEPS, interval, N_MEGNO, bk.rdr, bk.rdv, flags=L.RUN_ENERGY, t_main=ts)  # 2+2+1+1 kernels
                 n += 10
+            devb[N] = bk                  # the bucket of the most recent step (cross-checks below)
         if last:
             for N in Ns:
-                cur.wait_stream(devb[N].stream)
+                for b2 in devb2[N]:
+                    cur.wait_stream(b2.stream)
         launches_per_step = n
         if record:
             timed_step[0] += 1
@@ -623,6 +644,7 @@ def ensemble_section(args, ctx):
     # free the C3 buffers before the secondary sections
     for N in Ns:
         devb[N] = None
+        devb2[N] = None
         host[N] = None
     torch.cuda.empty_cache()
 
@@ -1174,6 +1196,7 @@ def main():
     ap.add_argument("--heavy-threshold", type=int, default=-1, dest="heavy_threshold",
                     help="tuning sweeps only: fixed n_sub threshold of the latency mappings on the device-resident path "
                          "(-1 = the automatic N-only rule, the product setting)")
+    ap.add_argument("--order", default="", help="tuning only: launch order of the N buckets on the device path, e.g. 8,7,6,5,4,3")
     ap.add_argument("--horizon", type=int, default=0,
                     help="integrator steps per system for --workload c4 / c1 (default 1000; C4 as worded: 1000000)")
     args = ap.parse_args()
