@@ -4,8 +4,26 @@
 #include <stdint.h>
 #include <math.h>
 #include "../../include/nbody_b200.h"
+#ifndef __CUDA_ARCH__
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX v3: ranges cost ~nothing unless a profiler is attached
+#endif
 
 namespace nb {
+
+// NVTX range around the host-side launch sequence of one phase (prepare / main / MEGNO / finalize / large-N passes),
+// so that an nsys / ncu timeline shows the reference's call structure
+struct NvtxRange {
+  explicit NvtxRange(const char* name) {
+#ifndef __CUDA_ARCH__
+    nvtxRangePushA(name);
+#endif
+  }
+  ~NvtxRange() {
+#ifndef __CUDA_ARCH__
+    nvtxRangePop();
+#endif
+  }
+};
 
 void set_error(const char* msg);
 int cuda_fail(cudaError_t e, const char* where);

@@ -151,6 +151,7 @@ int ensemble_run_classic(const RunArgs& a_in, int N, int mode, cudaStream_t st) 
   const bool split = a.perm && a.n_heavy && a.B >= NB_SPLIT_MIN_B && a.n_steps > 0 &&
                      (mode == NB_MODE_VERLET || mode == NB_MODE_YOSHIDA4);
   int rc;
+  NvtxRange r_all("nb_ensemble_run: E0 + main");
   if (!split) {
     if (energy) energy_kernel<<<blocks, threads, 0, st>>>(a.m, a.q, a.v, a.eps, a.G, a.B, N, a.dyn, 0);
     rc = phase(0, write, a, st);
@@ -191,6 +192,7 @@ int ensemble_run_classic(const RunArgs& a_in, int N, int mode, cudaStream_t st) 
     NB_CUDA_CHECK(cudaEventRecord(sp->ev[k][2], side));            // join
     NB_CUDA_CHECK(cudaStreamWaitEvent(st, sp->ev[k][2], 0));
   }
+  NvtxRange r_tail("nb_ensemble_run: E1 + MEGNO + finalize");
   if (energy) energy_kernel<<<blocks, threads, 0, st>>>(a.m, a.q, a.v, a.eps, a.G, a.B, N, a.dyn, 1);
   if (megno) {
     rc = phase(1, (a.flags & NB_RUN_WRITE_STATE) ? 1 : 0, a, st);
@@ -463,6 +465,7 @@ __global__ void sort_scatter_kernel(const int32_t* __restrict__ n_sub, int B, in
 // launchers
 // ---------------------------------------------------------------------------------------------
 int ensemble_prepare(const PrepArgs& a, int N, cudaStream_t st) {
+  NvtxRange r("nb_ensemble_prepare");
   const int threads = 128, blocks = (a.B + threads - 1) / threads;
   switch (N) {
     case 2: ensemble_prepare_kernel<2><<<blocks, threads, 0, st>>>(a); break;
@@ -513,6 +516,7 @@ int variational_batched(const double* q, const double* m, const double* s2, cons
 }
 
 int sort_by_nsub(const int32_t* n_sub, int B, int N, int32_t* perm, int32_t* ws, int heavy_threshold, cudaStream_t st) {
+  NvtxRange r("nb_sort_by_nsub");
   if (heavy_threshold < -1 || heavy_threshold > 63) { set_error("nb_sort_by_nsub: heavy_threshold must be -1 (automatic) or 0..63"); return NB_ERR_ARG; }
   NB_CUDA_CHECK(cudaMemsetAsync(ws, 0, 66 * sizeof(int32_t), st));
   const int threads = 256;

@@ -1205,6 +1205,7 @@ int hamsoft_run(const double* m, double* q, double* v, double G, int B, int N, u
                 int sample_interval, int n_megno, const int32_t* n_sub, const int32_t* perm, const double* raw_dr,
                 const double* raw_dv, double* eps_pi, const double* hs, double* dyn, int32_t* status, double* work,
                 unsigned long long* tstamp, cudaStream_t st) {
+  NvtxRange r("nb_ensemble_run: ham_soft");
   HsArgs a{m, q, v, G, B, flags, dt, n_steps, sample_interval, n_megno, n_sub, perm, raw_dr, raw_dv, eps_pi, hs, dyn,
            status, work, tstamp};
   NB_HS_DISPATCH(N, (hamsoft_run_kernel<NN><<<hs_run_blocks<NN>(a.B), 128, 0, st>>>(a)));

@@ -193,6 +193,7 @@ static int analyze_host_ex(const double* m, const double* q, double* v, const do
   if (n_megno > 0 && !dev_tangent && (!raw_dr || !raw_dv)) { set_error("nb_ensemble_analyze_host: n_megno > 0 needs raw_dr/raw_dv (or NB_HOST_DEVICE_TANGENT)"); return NB_ERR_ARG; }
   if (adaptive && (hamsoft || mode == NB_MODE_WHFAST || !o.soft_par)) { set_error("nb_ensemble_analyze_host: NB_HOST_ADAPTIVE needs verlet / yoshida4 and opts->soft_par"); return NB_ERR_UNSUPPORTED; }
   if (B == 0) return NB_OK;
+  NvtxRange r_host("nb_ensemble_analyze_host");
   std::lock_guard<std::mutex> lock(g_ws_mu);
   DeviceGuard guard(device);
   if (!guard.ok) { set_error("nb_ensemble_analyze_host: cudaSetDevice failed"); return NB_ERR_CUDA; }

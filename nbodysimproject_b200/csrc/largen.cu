@@ -378,6 +378,7 @@ int largeN_accel(const float* xym, int n_total, int i0, int ni, float eps, float
     set_error("nb_largeN_accel_f32: bad arguments (workspace = ni x 2 doubles of device memory is required; variant -1..10)");
     return NB_ERR_ARG;
   }
+  NvtxRange r("nb_largeN_accel");
   // stateless: the fp64 accumulators live in the CALLER's workspace, so calls on different streams / devices / threads
   // never share anything (round 1 kept one process-global buffer here)
   int dev = 0, sm_count = 0;

@@ -378,6 +378,8 @@ int largeN_pass(int kind, const float* xym, const float* jaux, int n_total, int 
     set_error("nb_largeN_pass_f32: bad arguments");
     return NB_ERR_ARG;
   }
+  static const char* const names[4] = {"nb_largeN_pass: DENSITY", "nb_largeN_pass: EPSGRAD", "nb_largeN_pass: UNITGRAD", "nb_largeN_pass: TAUMIN"};
+  NvtxRange r(names[kind]);
   int dev = 0, sm = 0;
   NB_CUDA_CHECK(cudaGetDevice(&dev));
   NB_CUDA_CHECK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));

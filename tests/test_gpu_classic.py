@@ -72,9 +72,13 @@ def test_coincident_bodies_unsoftened(E):
 
 
 @pytest.mark.parametrize("horizon,tol", [(1, 1e-13), (10, 1e-13), (100, 1e-12), (1000, 1e-9)])
-def test_classic_trajectories_vs_golden(E, horizon, tol):
+@pytest.mark.parametrize("fname", ["trajectories.npz", "trajectories_regular.npz"])
+def test_classic_trajectories_vs_golden(E, horizon, tol, fname):
+    """trajectories.npz: the named systems incl. chaotic ones (tolerance widened by the reference's own sensitivity);
+    trajectories_regular.npz: regular N = 5..8 systems (sensitivity ~1e-14), i.e. the FIXED tolerance at every N."""
     import nbodysimproject_b200._lib as L
-    g = load_golden("trajectories.npz")
+    g = load_golden(fname)
+    regular = "regular" in fname
     for key in g["names"]:
         key = str(key)
         mode = key.split("_")[1]
@@ -86,7 +90,10 @@ def test_classic_trajectories_vs_golden(E, horizon, tol):
         assert int(bk.n_sub[0]) == int(g[key + "n_sub"])
         bk.run(0.01, horizon, flags=L.RUN_WRITE_STATE, want_dyn=False)
         # tolerance "before chaotic divergence": see tests/test_oracle_golden.py
-        tol = max(tol, 30.0 * float(g[key + f"sens{horizon}"]))
+        if regular:
+            assert float(g[key + f"sens{horizon}"]) < 1e-12          # the golden system really is regular
+        else:
+            tol = max(tol, 30.0 * float(g[key + f"sens{horizon}"]))
         assert relerr(bk.q.cpu().numpy()[0], g[key + f"q{horizon}"]) < tol, key
         assert relerr(bk.v.cpu().numpy()[0], g[key + f"v{horizon}"]) < tol * 10, key
         assert int(bk.status[0]) == 0
@@ -134,11 +141,16 @@ def test_whfast_exact_kepler_circular_orbit(E):
 _LOOSE = {"MEGNO": 1e-6, "lyapunov_time": 1e-6}
 
 
-@pytest.mark.parametrize("mode", ["verlet", "yoshida4"])
+@pytest.mark.parametrize("mode", ["verlet", "yoshida4", "regular_verlet", "regular_yoshida4"])
 @pytest.mark.parametrize("via", ["device", "host"])
 def test_feature_rows_vs_golden(E, mode, via):
+    """features_<mode>.npz: the named systems (per-column tolerance widened by the reference's own sensitivity, which
+    leaves some cells of the chaotic rand6 / rand8 rows vacuous); features_regular_<mode>.npz: regular N = 5..8 systems
+    whose every column is compared at the fixed floor (the sensitivities are ~1e-14)."""
     import nbodysimproject_b200._lib as L
     g = load_golden(f"features_{mode}.npz")
+    regular = mode.startswith("regular_")
+    mode = mode.split("_")[-1]
     n_steps, dt = int(g["n_steps"]), float(g["dt"])
     cols = [str(c) for c in g["columns"]]
     for name in g["names"]:
@@ -167,6 +179,9 @@ def test_feature_rows_vs_golden(E, mode, via):
                 # routine (chaotic amplification, recorded in the golden file as sens__<col>), floored at the
                 # rounding level of the quantity
                 sens = float(g[f"{name}__sens__{c}"]) if f"{name}__sens__{c}" in g.files else 0.0
+                if regular:
+                    assert sens < 1e-12, (name, c, sens)
+                    sens = 0.0
                 floor = {"energy_drift": 2e-13, "angular_momentum_drift": 2e-13, "com_drift_mean": 1e-12,
                          "com_drift_max": 1e-12}.get(c, 1e-9 * max(abs(ref), 1e-12) + 1e-14)
                 assert abs(got - ref) <= floor + 100.0 * sens, (name, c, got, ref, sens)

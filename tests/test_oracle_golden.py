@@ -32,8 +32,9 @@ def test_kepler_bug_compatible():
 
 
 @pytest.mark.parametrize("horizon,tol", [(1, 1e-14), (10, 1e-13), (100, 1e-12), (1000, 1e-9)])
-def test_classic_trajectories(horizon, tol):
-    g = load_golden("trajectories.npz")
+@pytest.mark.parametrize("fname", ["trajectories.npz", "trajectories_regular.npz"])
+def test_classic_trajectories(horizon, tol, fname):
+    g = load_golden(fname)
     for key in g["names"]:
         key = str(key)
         mode = key.split("_")[1]
@@ -77,9 +78,10 @@ def test_whfast_trajectories():
 _LOOSE = {"MEGNO": 1e-6, "lyapunov_time": 1e-6, "energy_drift": 1e-5, "angular_momentum_drift": 1e-2}
 
 
-@pytest.mark.parametrize("mode", ["verlet", "yoshida4"])
+@pytest.mark.parametrize("mode", ["verlet", "yoshida4", "regular_verlet", "regular_yoshida4"])
 def test_feature_rows(mode):
     g = load_golden(f"features_{mode}.npz")
+    mode = mode.split("_")[-1]
     n_steps, dt = int(g["n_steps"]), float(g["dt"])
     cols = [str(c) for c in g["columns"]]
     for name in g["names"]:
