@@ -45,6 +45,7 @@ __device__ __forceinline__ double hs_ipow(double x, int e) {   // x ** e for sma
 // barrier.py:66-113
 __device__ __forceinline__ double hs_barrier_force(double eps, const HsPar& P) {
   if (P.policy != 0) return 0.0;
+  if (eps >= P.eps_min && eps <= P.eps_max) return 0.0;          // inside the admissible interval: both terms vanish
   if (!(is_finite(P.k_wall) && P.k_wall > 0.0)) return 0.0;
   const int n = max(2, P.n_exp);
   const double la = fmax(0.0, P.eps_min - eps), rb = fmax(0.0, eps - P.eps_max);
@@ -162,6 +163,11 @@ __device__ __forceinline__ double hs_eps_target(const double* qx, const double* 
 #define HS_NACC 22
 #define NB_INV_PI 0.31830988618379067154
 
+// exp / log out of line: inlined at every call site (N (N-1) in the Jacobi sweep alone) they made the straight-line code
+// of a sub-step ~80 KB per warp and the kernel stalled on instruction fetch (ncu r2: no_instruction 2.8 warps per issue)
+__device__ __noinline__ double hs_exp(double x) { return exp(x); }
+__device__ __noinline__ double hs_log(double x) { return log(x); }
+
 // a / b for a divisor that is finite, positive and far from the denormal range (smoothing lengths, masses, alpha ...):
 // MUFU.RCP64H seed, two Newton steps, one residual correction = 8 FP64-pipe instructions and no slow-path call.
 // The compiler's generic division is ~15 instructions PLUS a ~60-instruction subroutine whenever the dividend is zero
@@ -259,7 +265,7 @@ __device__ __forceinline__ int hs_solve_regs(const double (&r2)[N * (N - 1) / 2 
         if (j == i) continue;
         const int a = i < j ? i : j, b = i < j ? j : i;
         const double arg = r2[a * N - a * (a + 1) / 2 + (b - a - 1)] * nih2;
-        if (arg > -746.0) S += m[j] * (c * exp(arg));
+        if (arg > -746.0) S += m[j] * (c * hs_exp(arg));
       }
       const double Si = fmax(S, 1.0e-30);
       double v = eta * sqrt(hs_div(m[i], Si));
@@ -291,11 +297,11 @@ __device__ __forceinline__ double hs_softmin(const double (&h)[N], const HsPar& 
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const double d = t[i] - tmax;                // <= 0; the largest term is exp(0) = 1 exactly
-    s += (d == 0.0) ? 1.0 : ((d > -746.0) ? exp(d) : 0.0);
+    s += (d == 0.0) ? 1.0 : ((d > -746.0) ? hs_exp(d) : 0.0);
   }
   double es;
   if (s <= 0.0 || !is_finite(s)) es = P.s0;
-  else es = -alpha * (tmax + log(s));
+  else es = -alpha * (tmax + hs_log(s));
   if (P.policy == 0) {
     double lo = P.eps_min, hi = P.eps_max;
     if (hi < lo) { const double t2 = lo; lo = hi; hi = t2; }
@@ -354,7 +360,7 @@ __device__ __forceinline__ double hs_eps_target_coop(HsSh<N>& sh, double eps_cur
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       const double arg = r2[j] * nih2;
-      if (j != i && arg > -746.0) S += sh.m[j] * (c * exp(arg));
+      if (j != i && arg > -746.0) S += sh.m[j] * (c * hs_exp(arg));
     }
     const double Si = fmax(S, 1.0e-30);
     double v = P.eta * sqrt(hs_div(mi, Si));
@@ -398,7 +404,7 @@ __device__ __forceinline__ void hs_fallback_grp(HsSh<N>& sh, int lane, bool comm
   const double ti = -sh.h[i] * sh.inv_alpha;
   const double tmax = grp_max<LPS>(ti);
   const double di = ti - tmax;
-  const double ei = (di == 0.0) ? 1.0 : ((di > -746.0) ? exp(di) : 0.0);
+  const double ei = (di == 0.0) ? 1.0 : ((di > -746.0) ? hs_exp(di) : 0.0);
   __syncwarp();
   if (mine) sh.bx[i] = ei;
   __syncwarp();
@@ -420,7 +426,7 @@ __device__ __forceinline__ void hs_fallback_grp(HsSh<N>& sh, int lane, bool comm
     const double rr = dx * dx + dy * dy;
     const double arg = -rr * ih2;
     if (arg > -746.0) {
-      W[j] = c * exp(arg);
+      W[j] = c * hs_exp(arg);
       S += sh.m[j] * W[j];
       Sd += sh.m[j] * (W[j] * (2.0 * ihj * (rr * ih2 - 1.0)));      // dW/dh = W (-2/h + 2 r^2/h^3)
     }
@@ -449,7 +455,7 @@ __device__ __forceinline__ void hs_fallback_grp(HsSh<N>& sh, int lane, bool comm
     const double rx = sh.x[a] - xi, ry = sh.y[a] - yi;
     const double arg = -(rx * rx + ry * ry) * ia2;
     if (arg > -746.0) {
-      const double Wa = (ia2 * NB_INV_PI) * exp(arg);
+      const double Wa = (ia2 * NB_INV_PI) * hs_exp(arg);
       const double coef = -2.0 * Wa * ia2;
       gx -= sa * mi * (coef * rx);
       gy -= sa * mi * (coef * ry);
@@ -508,12 +514,16 @@ __device__ __forceinline__ double hs_eps_star_and_grad(HsSh<N>& sh, double eps_c
     double r2[NP > 0 ? NP : 1];
     {
       double px[N], py[N];
+      // this lane's perturbed coordinate (body c >> 1, axis c & 1): one finite-difference step, then a select per body
+      const int pb = pert ? (c >> 1) : 0;
+      const bool on_y = (c & 1) != 0;
+      const double base_v = on_y ? sh.y[pb] : sh.x[pb];
+      const double pert_v = base_v + sgn * hs_fd_step(base_v);
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         px[i] = sh.x[i];
         py[i] = sh.y[i];
-        if (pert && c == 2 * i) px[i] = px[i] + sgn * hs_fd_step(px[i]);
-        if (pert && c == 2 * i + 1) py[i] = py[i] + sgn * hs_fd_step(py[i]);
+        if (pert && i == pb) { if (on_y) py[i] = pert_v; else px[i] = pert_v; }
       }
       int p = 0;
 #pragma unroll
