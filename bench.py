@@ -316,7 +316,7 @@ def impl_reference(args):
     if args.workload == "largen":
         return impl_reference_largen(args)
     cores = os.cpu_count() or 1
-    n_jobs = cores * 24                       # >= 24 systems per core and step: the per-process tail stays < 5 %
+    n_jobs = cores * 48                       # 48 systems per core and step: the per-process tail stays small
     pool = CpuPool(cores)
     times, done = [], 0
     for it in range(args.warmup + args.steps):
@@ -343,7 +343,8 @@ def impl_reference(args):
         "cpu_baseline": {"value": value, "unit": "system-steps/s", "cores": cores, "kind": kind,
                          "sample": f"{n_jobs} systems x {STEPS_PER_SYSTEM} steps per bench step, "
                                    + ("the reference's BatchStabilityAnalyzer.analyze_batch" if kind == "reference"
-                                      else "NumPy oracle (oracle/nbody_oracle.py; ~2x faster per core than the reference, "
+                                      else "NumPy oracle (oracle/nbody_oracle.py; measured 3.0x faster per core than the reference's "
+                                           "own analyze_batch in the build container, 22.1e3 vs 7.4e3 system-steps/s on 8 cores, "
                                            "DESIGN.md section 5)")
                                    + f" in {cores} worker processes created before the timed steps"},
         "e2e": {"value": value, "unit": "system-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -622,9 +623,12 @@ def ensemble_section(args, ctx):
         roof = {"bound": "fp64", "kernel": "ensemble_main_kernel<N=3..8, yoshida4> (6 concurrent launches per step)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "frac_nominal": ach / NOMINAL_FP64, "peak_nominal": NOMINAL_FP64,
-                "traffic": _traffic("ensemble_main_six_launches_bytes_per_2p20_systems"),
-                "traffic_note": "dram bytes over the six launches of one step at 2^20 systems/GPU from the committed ncu "
-                                "capture (profiles/r2_traffic.json); the state is read once and lives in registers",
+                "traffic": (lambda t: None if t is None else t * (B_total / float(1 << 20)))(
+                    _traffic("ensemble_main_six_launches_bytes_per_2p20_systems")),
+                "traffic_note": "dram__bytes_read + dram__bytes_write over the main-phase launches of one step from the "
+                                "committed ncu capture of this command at 2^20 systems/GPU (profiles/r2_traffic.json, "
+                                "tools/ncu_traffic.py), scaled by the batch size; the state is read once and lives in "
+                                "registers (algorithmic bytes: ~0.45 KB in + 0.18 KB out per system = 0.66 GB/step)",
                 "flops_per_step": tot_fl, "ms": win * 1e3,
                 "timing": "%globaltimer stamps published by the main kernels themselves (first CTA start, last warp end; "
                           "nb_ensemble_run_counted_f64 t_main) inside the timed steps; span from the earliest start of the "
@@ -666,7 +670,8 @@ def ensemble_section(args, ctx):
         kind = cpu_kind()
         cpu = {"value": rate, "unit": "system-steps/s", "cores": cores, "kind": kind,
                "sample": f"{n_jobs} systems x {STEPS_PER_SYSTEM} steps of the same generator (workload-weighted N mix), "
-                         + ("the reference's BatchStabilityAnalyzer" if kind == "reference" else "NumPy oracle")
+                         + ("the reference's BatchStabilityAnalyzer" if kind == "reference" else
+                            "NumPy oracle (3.0x faster per core than the reference itself, measured in the build container)")
                          + f" in {cores} processes, {dt_cpu:.1f} s"}
     if rank != 0:
         return None

@@ -162,6 +162,12 @@ class NBodySimulation:
                  adaptive_timestep: bool = None, adaptive_softening: bool = None, skip_init_corrector: bool = False,
                  skip_cm_recenter: bool = False, integrator_mode: str | None = None, device=None):
         self.cfg = config.copy() if config else SimConfig()
+        # reference test hooks that the GPU kernels do not implement (simulation.py:80-83, 159-162 float32 state arrays;
+        # hamsoft_eps_model.py:82-89; hamsoft_stepper.py:119-124, 270-284): reported, never silently ignored, never raised
+        for name in ("fast_float32", "use_legacy_eps_star", "fixed_eps_star", "freeze_s_subsystem", "_validate_S_only"):
+            if bool(getattr(self.cfg, name, False)):
+                print(f"[nbodysimproject_b200] SimConfig.{name} is not supported by the fp64 GPU kernels: "
+                      f"running the production path (NB_ERR_UNSUPPORTED at the C ABI)")
         self.device = device
         self.kepler_mode = "reference"       # or "exact" 
         if adaptive_timestep is not None:
