@@ -205,8 +205,9 @@ class LargeNHamSoftSimulation(LargeNSimulation):
         self.theta_cap, self.theta_imp, self.alpha_cfg, self.eta = float(theta_cap), float(theta_imp), alpha, float(eta)
         self.chi_pi, self.j_max_cap = float(chi_pi), float(j_max_cap)
         self.soft_policy = bool(use_soft_barrier) and not bool(disable_barrier)
-        if not self.soft_policy and not disable_barrier:
-            raise L.NBodyB200Error("ham_soft barrier policy 'reflection' is not built")
+        # hamiltonian_softening_integrator.py:96-108: "reflection" unless the soft barrier is on; disable_barrier switches
+        # the folds off as well (hamsoft_barrier_controller.py:46-47)
+        self.reflect_policy = (not bool(use_soft_barrier)) and not bool(disable_barrier)
         self.split_n_max = int(split_n_max)
         self.alpha_run = None
         self.n_passes = 0
@@ -272,6 +273,22 @@ class LargeNHamSoftSimulation(LargeNSimulation):
         if boxes is None:
             self.n_full_passes = getattr(self, "n_full_passes", 0) + 1
         return self.out64
+
+    # ---- reflection policy: fold epsilon into [eps_min, eps_max], flipping pi (hamsoft_barrier_controller.py:27-69,
+    #      hamsoft_utils.py:105-184 reflect_if_needed) -- eps, pi are replicated host scalars
+    def _fold(self):
+        if not self.reflect_policy:
+            return
+        a, b = float(self.eps_min), float(self.eps_max)
+        R = b - a
+        if not math.isfinite(R) or R <= 0.0:
+            self.eps, self.pi = a, -float(self.pi)
+            return
+        y = (float(self.eps) - a) % (2.0 * R)           # Python float modulo: sign of the divisor
+        if y <= R:
+            self.eps = a + y
+        else:
+            self.eps, self.pi = b - (y - R), -float(self.pi)
 
     # ---- barrier (barrier.py:66-113) ----------------------------------------------------------------
     def _fbar(self, eps):
@@ -487,6 +504,7 @@ class LargeNHamSoftSimulation(LargeNSimulation):
     def s_half(self, h):
         torch = self.torch
         dt = 0.5 * float(h)
+        self._fold()                                            # hamsoft_stepper.py:107-113
         eps0, pi0 = float(self.eps), float(self.pi)
         es, grad = self.eps_star_and_grad()
         k, mu = self.k_soft, self.mu_soft
@@ -522,6 +540,7 @@ class LargeNHamSoftSimulation(LargeNSimulation):
         self.vel += (Ja * grad / self.m64[:, None]).float()
         self.eps = float(eps_rot)
         self.pi = float(eta_t + kick2)
+        self._fold()                                            # hamsoft_stepper.py:72-80
         self.taps = dict(eps_star=es, J=J, J_applied=Ja, theta=th, sweeps=self.last_sweeps)
 
     def v_half_kick(self, h):
@@ -537,6 +556,7 @@ class LargeNHamSoftSimulation(LargeNSimulation):
         self.pi = float(self.pi) - (dU + dB) * hh
 
     def strang_step(self, h):
+        self._fold()                                            # hamsoft_stepper.py:261-264
         self.s_half(h)
         self.v_half_kick(h)
         self._kick_drift(0.0, h)
@@ -544,6 +564,7 @@ class LargeNHamSoftSimulation(LargeNSimulation):
         self._gather()
         self.v_half_kick(h)
         self.s_half(h)
+        self._fold()                                            # hamsoft_stepper.py:300-303
 
     def step(self, dt):
         """hamiltonian_softening_integrator.py:496-557."""

@@ -186,3 +186,33 @@ def test_locality_culling_drops_only_exact_zeros_and_storage_order_is_invisible(
     assert np.max(np.abs(a.velocities - c.velocities)) <= 2e-4 * np.max(np.abs(c.velocities))
     # one long-range UNITGRAD pass per sub-step (shared by the closing and the next opening S half-flow)
     assert a._unit_cache is not None
+
+
+def test_reflection_policy_folds_epsilon_like_the_oracle():
+    """Barrier policy 'reflection' (use_soft_barrier = False): epsilon is folded into [eps_min, eps_max] and pi flipped
+    (hamsoft_barrier_controller.py:27-69, hamsoft_utils.py:159-184) at the four places the stepper does it.  A narrow
+    admissible interval makes epsilon hit both walls within a few sub-steps."""
+    from nbodysimproject_b200.largen import LargeNHamSoftSimulation
+    from oracle.largen_hamsoft_oracle import LargeNHamSoftOracle
+    m, q, v = _system(200, 5)
+    gpu = LargeNHamSoftSimulation(m, q, v, softening=0.02, use_soft_barrier=False, spatial_sort=False)
+    xym = gpu.xym.cpu().numpy().astype(np.float64)
+    v32 = gpu.vel.cpu().numpy().astype(np.float64)
+    ora = LargeNHamSoftOracle(xym[:, 2], xym[:, :2], v32, softening=0.02, skip_cm_recenter=True, use_soft_barrier=False)
+    assert gpu.reflect_policy and ora.reflect_policy and not gpu.soft_policy
+    for sim in (gpu, ora):                       # squeeze the interval around the start value
+        sim.eps_max = float(sim.eps) * 1.002
+        sim.eps_min = float(sim.eps) * 0.9995
+    h = 0.01 / ora.frozen_n_sub
+    flips = 0
+    for _ in range(6):
+        p_before = ora.pi
+        gpu.strang_step(h)
+        ora.strang_step(h)
+        assert gpu.eps_min <= gpu.eps <= gpu.eps_max
+        assert abs(gpu.eps - ora.eps) < 2e-5 * abs(ora.eps)
+        assert abs(gpu.pi - ora.pi) < 5e-3 * max(abs(ora.pi), 1e-6)
+        flips += int(np.sign(ora.pi) != np.sign(p_before))
+    qg = gpu.xym[:, :2].cpu().numpy().astype(np.float64)
+    assert np.max(np.abs(qg - ora.q)) < 5e-6 * np.max(np.abs(ora.q))
+    assert flips >= 1                            # the walls were really hit
