@@ -233,7 +233,6 @@ int nb_ensemble_run_counted_f64(const double* m, double* q, double* v, const dou
                                 const double* raw_dv, double* eps_pi, const double* hs_params, double* dyn_features,
                                 int32_t* status, double* work, uint64_t* t_main, void* stream) {
   if (!m || !q || !v || B < 0 || N < NB_MIN_N || N > NB_MAX_N_MID || n_steps < 0 || n_megno < 0) { set_error("nb_ensemble_run_f64: bad arguments"); return NB_ERR_ARG; }
-  if (N > NB_MAX_N && mode == NB_MODE_HAMSOFT) { set_error("nb_ensemble_run_f64: the ham_soft kernels cover N <= 8 bodies"); return NB_ERR_UNSUPPORTED; }
   if (n_megno > 0 && (!raw_dr || !raw_dv)) { set_error("nb_ensemble_run_f64: n_megno > 0 needs raw_dr/raw_dv"); return NB_ERR_ARG; }
   if (B == 0) return NB_OK;
   if (mode == NB_MODE_HAMSOFT) {
@@ -257,14 +256,14 @@ int nb_ensemble_run_f64(const double* m, double* q, double* v, const double* eps
 
 int nb_hamsoft_setup_f64(const double* m, const double* q, double G, int B, int N, unsigned flags, double dt,
                          double* hs_params, double* eps_pi, int32_t* n_sub, void* stream) {
-  if (!m || !q || !hs_params || !eps_pi || B < 0 || N < NB_MIN_N || N > NB_MAX_N || ((flags & 2u) && !n_sub)) { set_error("nb_hamsoft_setup_f64: bad arguments"); return NB_ERR_ARG; }
+  if (!m || !q || !hs_params || !eps_pi || B < 0 || N < NB_MIN_N || N > NB_MAX_N_MID || ((flags & 2u) && !n_sub)) { set_error("nb_hamsoft_setup_f64: bad arguments"); return NB_ERR_ARG; }
   if (B == 0) return NB_OK;
   return hamsoft_setup(m, q, G, B, N, flags, dt, hs_params, eps_pi, n_sub, (cudaStream_t)stream);
 }
 
 int nb_hamsoft_probe_f64(const double* m, const double* q, const double* v, double G, int B, int N,
                          const double* eps_pi, const double* hs_params, double* out, void* stream) {
-  if (!m || !q || !v || !hs_params || !eps_pi || !out || B < 0 || N < NB_MIN_N || N > NB_MAX_N) { set_error("nb_hamsoft_probe_f64: bad arguments"); return NB_ERR_ARG; }
+  if (!m || !q || !v || !hs_params || !eps_pi || !out || B < 0 || N < NB_MIN_N || N > NB_MAX_N_MID) { set_error("nb_hamsoft_probe_f64: bad arguments"); return NB_ERR_ARG; }
   if (B == 0) return NB_OK;
   return hamsoft_probe(m, q, v, G, B, N, eps_pi, hs_params, out, (cudaStream_t)stream);
 }

@@ -658,11 +658,6 @@ __device__ __noinline__ double hs_eps_target_sh(const HsSh<N>* sh, double eps_cu
 // ---------------------------------------------------------------------------------------------
 // run kernel: one group of LPS lanes per system
 // ---------------------------------------------------------------------------------------------
-struct HsArgs {
-  const double* m; double* q; double* v; double G; int B; unsigned flags; double dt; int n_steps; int sample_interval;
-  int n_megno; const int32_t* n_sub; const int32_t* perm; const double* raw_dr; const double* raw_dv; double* eps_pi;
-  const double* hs; double* dyn; int32_t* status; double* work; unsigned long long* tstamp;
-};
 
 template <int N>
 static inline int hs_run_blocks(int B) {
@@ -794,33 +789,7 @@ __global__ void __launch_bounds__(128, (N <= 3 ? 6 : (N <= 4 ? 5 : (N <= 6 ? 3 :
 #pragma unroll
           for (int i = 0; i < N; ++i) var += (Li[i] - mean) * (Li[i] - mean);
           var /= N;
-          const double com = sqrt(cx * cx + cy * cy);
-          if (A[HA_HAVE_FIRST] == 0.0) { A[HA_LFIRST] = Lt; A[HA_HAVE_FIRST] = 1.0; }
-          const double Lfirst = A[HA_LFIRST];
-          double c;
-          if (Lfirst != 0.0 && Lt != 0.0) c = (Lt * Lfirst) / (fabs(Lt) * fabs(Lfirst));
-          else { c = 0.0; A[HA_COS_NAN] = 1.0; }
-          A[HA_COM_SUM] += com; A[HA_COM_MAX] = fmax(A[HA_COM_MAX], com);
-          A[HA_VAR_SUM] += var; A[HA_VAR_MAX] = fmax(A[HA_VAR_MAX], var);
-          A[HA_COS_SUM] += c; A[HA_COS_MIN] = fmin(A[HA_COS_MIN], c);
-          const double mu = sh.P.mu;
-          {
-            const double xj = eps * pi / mu;
-            const double n = (A[HA_WJ_N] += 1.0);
-            const double d = xj - A[HA_WJ_MEAN];
-            A[HA_WJ_MEAN] += d / n;
-            A[HA_WJ_M2] += d * (xj - A[HA_WJ_MEAN]);
-          }
-          if (mu * eps != 0.0 || pi != 0.0) {
-            const double xt = atan2(pi, mu * eps);
-            const double n = (A[HA_WT_N] += 1.0);
-            const double d = xt - A[HA_WT_MEAN];
-            A[HA_WT_MEAN] += d / n;
-            A[HA_WT_M2] += d * (xt - A[HA_WT_MEAN]);
-          } else {
-            A[HA_TH_NAN] = 1.0;
-          }
-          A[HA_NSAMP] += 1.0;
+          hs_sample_scalars(A, sqrt(cx * cx + cy * cy), var, Lt, eps, pi, sh.P.mu);
         }
       }
     } else {
@@ -891,34 +860,7 @@ __global__ void __launch_bounds__(128, (N <= 3 ? 6 : (N <= 4 ? 5 : (N <= 6 ? 3 :
     a.eps_pi[2 * (size_t)sys] = eps;
     a.eps_pi[2 * (size_t)sys + 1] = pi;
   }
-  if (a.dyn) {
-    double* f = a.dyn + (size_t)sys * NB_N_DYN;
-    const double* A = sh.acc;
-    auto drift_of = [&](double a0, double a1) {
-      if (is_finite(a0) && fabs(a0) > 0.0 && is_finite(a1)) return fabs((a1 - a0) / a0);
-      if (is_finite(a0) && is_finite(a1)) return fabs(a1 - a0);
-      return inf;
-    };
-    const int n_samp = (int)A[HA_NSAMP];
-    const double E0 = A[HA_E0], L0 = A[HA_L0], E1 = A[HA_E1], L1 = A[HA_L1];
-    const bool th_nan = A[HA_TH_NAN] != 0.0, cos_nan = A[HA_COS_NAN] != 0.0;
-    const double ed = want_energy ? drift_of(E0, E1) : nan, ld = want_energy ? drift_of(L0, L1) : nan;
-    const double inv = n_samp > 0 ? 1.0 / (double)n_samp : nan;
-    const double com_mean = n_samp > 0 ? A[HA_COM_SUM] * inv : nan;
-    f[NB_F_ENERGY_DRIFT] = ed; f[NB_F_ANGMOM_DRIFT] = ld;
-    f[NB_F_COM_MEAN] = com_mean; f[NB_F_COM_MAX] = n_samp > 0 ? A[HA_COM_MAX] : nan;
-    f[NB_F_JEPS_MEAN] = n_samp > 0 ? A[HA_WJ_MEAN] : nan;
-    f[NB_F_JEPS_STD] = n_samp > 0 ? sqrt(A[HA_WJ_M2] / A[HA_WJ_N]) : nan;
-    f[NB_F_THETA_MEAN] = (n_samp > 0 && !th_nan) ? A[HA_WT_MEAN] : nan;
-    f[NB_F_THETA_STD] = (n_samp > 0 && !th_nan) ? sqrt(A[HA_WT_M2] / A[HA_WT_N]) : nan;
-    f[NB_F_COS_MEAN] = (n_samp > 0 && !cos_nan) ? A[HA_COS_SUM] * inv : nan;
-    f[NB_F_COS_MIN] = (n_samp > 0 && !cos_nan) ? A[HA_COS_MIN] : nan;
-    f[NB_F_VARL_MEAN] = n_samp > 0 ? A[HA_VAR_SUM] * inv : nan; f[NB_F_VARL_MAX] = n_samp > 0 ? A[HA_VAR_MAX] : nan;
-    f[NB_F_TIDAL_MEAN] = n_samp > 0 ? 0.0 : nan; f[NB_F_TIDAL_MAX] = n_samp > 0 ? 0.0 : nan;
-    f[NB_F_MEGNO] = megno; f[NB_F_LYAP_TIME] = lyap;
-    f[NB_F_IS_STABLE] = ((ed < 0.01) && (ld < 0.01) && (com_mean < 1.0) && (megno < 10.0)) ? 1.0 : 0.0;
-    f[NB_F_E0] = E0; f[NB_F_E1] = E1; f[NB_F_L0] = L0; f[NB_F_L1] = L1; f[NB_F_T_END] = t_end;
-  }
+  if (a.dyn) hs_write_dyn(a.dyn + (size_t)sys * NB_N_DYN, sh.acc, want_energy, megno, lyap, t_end);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1088,6 +1030,7 @@ int hamsoft_run(const double* m, double* q, double* v, double G, int B, int N, u
   NvtxRange r("nb_ensemble_run: ham_soft");
   HsArgs a{m, q, v, G, B, flags, dt, n_steps, sample_interval, n_megno, n_sub, perm, raw_dr, raw_dv, eps_pi, hs, dyn,
            status, work, tstamp};
+  if (N > NB_MAX_N && N <= NB_MAX_N_MID) return hamsoft_mid_run(a, N, st);    // 9..64 bodies: one CTA per system
   NB_HS_DISPATCH(N, (hamsoft_run_kernel<NN><<<hs_run_blocks<NN>(a.B), 128, 0, st>>>(a)));
   NB_CUDA_CHECK(cudaGetLastError());
   return NB_OK;
@@ -1095,6 +1038,7 @@ int hamsoft_run(const double* m, double* q, double* v, double G, int B, int N, u
 
 int hamsoft_setup(const double* m, const double* q, double G, int B, int N, unsigned flags, double dt, double* hs,
                   double* eps_pi, int32_t* n_sub, cudaStream_t st) {
+  if (N > NB_MAX_N && N <= NB_MAX_N_MID) return hamsoft_mid_setup(m, q, G, B, N, flags, dt, hs, eps_pi, n_sub, st);
   const int blocks = (B + 63) / 64;
   NB_HS_DISPATCH(N, (hamsoft_setup_kernel<NN><<<blocks, 64, 0, st>>>(m, q, G, B, flags, dt, hs, eps_pi, n_sub)));
   NB_CUDA_CHECK(cudaGetLastError());
@@ -1103,6 +1047,7 @@ int hamsoft_setup(const double* m, const double* q, double G, int B, int N, unsi
 
 int hamsoft_probe(const double* m, const double* q, const double* v, double G, int B, int N, const double* eps_pi,
                   const double* hs, double* out, cudaStream_t st) {
+  if (N > NB_MAX_N && N <= NB_MAX_N_MID) return hamsoft_mid_probe(m, q, v, G, B, N, eps_pi, hs, out, st);
   const int blocks = (B + 3) / 4;
   NB_HS_DISPATCH(N, (hamsoft_probe_kernel<NN><<<blocks, 128, 0, st>>>(m, q, v, G, B, eps_pi, hs, out)));
   NB_CUDA_CHECK(cudaGetLastError());

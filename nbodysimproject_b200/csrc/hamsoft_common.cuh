@@ -135,4 +135,80 @@ __device__ __forceinline__ void hs_spring_setup(HsSpring& R, const HsPar& P, dou
   R.inv_den = R.den_ok ? 1.0 / den : 0.0;
 }
 
+// launch arguments of the run kernels (hamsoft.cu: N <= 8; hamsoft_mid.cu: 9..64 bodies)
+struct HsArgs {
+  const double* m; double* q; double* v; double G; int B; unsigned flags; double dt; int n_steps; int sample_interval;
+  int n_megno; const int32_t* n_sub; const int32_t* perm; const double* raw_dr; const double* raw_dv; double* eps_pi;
+  const double* hs; double* dyn; int32_t* status; double* work; unsigned long long* tstamp;
+};
+
+// one step_metrics sample (diagnostics.py:241-285) from the scalars of the system: |COM|, var(L_i), L_total, and the
+// Welford accumulators of J_eps = eps pi / mu and theta = atan2(pi, mu eps)
+__device__ __forceinline__ void hs_sample_scalars(double* A, double com, double var, double Lt, double eps, double pi,
+                                                  double mu) {
+  if (A[HA_HAVE_FIRST] == 0.0) { A[HA_LFIRST] = Lt; A[HA_HAVE_FIRST] = 1.0; }
+  const double Lfirst = A[HA_LFIRST];
+  double c;
+  if (Lfirst != 0.0 && Lt != 0.0) c = (Lt * Lfirst) / (fabs(Lt) * fabs(Lfirst));
+  else { c = 0.0; A[HA_COS_NAN] = 1.0; }
+  A[HA_COM_SUM] += com; A[HA_COM_MAX] = fmax(A[HA_COM_MAX], com);
+  A[HA_VAR_SUM] += var; A[HA_VAR_MAX] = fmax(A[HA_VAR_MAX], var);
+  A[HA_COS_SUM] += c; A[HA_COS_MIN] = fmin(A[HA_COS_MIN], c);
+  {
+    const double xj = eps * pi / mu;
+    const double n = (A[HA_WJ_N] += 1.0);
+    const double d = xj - A[HA_WJ_MEAN];
+    A[HA_WJ_MEAN] += d / n;
+    A[HA_WJ_M2] += d * (xj - A[HA_WJ_MEAN]);
+  }
+  if (mu * eps != 0.0 || pi != 0.0) {
+    const double xt = atan2(pi, mu * eps);
+    const double n = (A[HA_WT_N] += 1.0);
+    const double d = xt - A[HA_WT_MEAN];
+    A[HA_WT_MEAN] += d / n;
+    A[HA_WT_M2] += d * (xt - A[HA_WT_MEAN]);
+  } else {
+    A[HA_TH_NAN] = 1.0;
+  }
+  A[HA_NSAMP] += 1.0;
+}
+
+// the dynamic feature row of one system from its accumulators (stability_analyzer.py:69-259)
+__device__ __forceinline__ void hs_write_dyn(double* f, const double* A, bool want_energy, double megno, double lyap,
+                                             double t_end) {
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  auto drift_of = [&](double a0, double a1) {
+    if (is_finite(a0) && fabs(a0) > 0.0 && is_finite(a1)) return fabs((a1 - a0) / a0);
+    if (is_finite(a0) && is_finite(a1)) return fabs(a1 - a0);
+    return inf;
+  };
+  const int n_samp = (int)A[HA_NSAMP];
+  const double E0 = A[HA_E0], L0 = A[HA_L0], E1 = A[HA_E1], L1 = A[HA_L1];
+  const bool th_nan = A[HA_TH_NAN] != 0.0, cos_nan = A[HA_COS_NAN] != 0.0;
+  const double ed = want_energy ? drift_of(E0, E1) : nan, ld = want_energy ? drift_of(L0, L1) : nan;
+  const double inv = n_samp > 0 ? 1.0 / (double)n_samp : nan;
+  const double com_mean = n_samp > 0 ? A[HA_COM_SUM] * inv : nan;
+  f[NB_F_ENERGY_DRIFT] = ed; f[NB_F_ANGMOM_DRIFT] = ld;
+  f[NB_F_COM_MEAN] = com_mean; f[NB_F_COM_MAX] = n_samp > 0 ? A[HA_COM_MAX] : nan;
+  f[NB_F_JEPS_MEAN] = n_samp > 0 ? A[HA_WJ_MEAN] : nan;
+  f[NB_F_JEPS_STD] = n_samp > 0 ? sqrt(A[HA_WJ_M2] / A[HA_WJ_N]) : nan;
+  f[NB_F_THETA_MEAN] = (n_samp > 0 && !th_nan) ? A[HA_WT_MEAN] : nan;
+  f[NB_F_THETA_STD] = (n_samp > 0 && !th_nan) ? sqrt(A[HA_WT_M2] / A[HA_WT_N]) : nan;
+  f[NB_F_COS_MEAN] = (n_samp > 0 && !cos_nan) ? A[HA_COS_SUM] * inv : nan;
+  f[NB_F_COS_MIN] = (n_samp > 0 && !cos_nan) ? A[HA_COS_MIN] : nan;
+  f[NB_F_VARL_MEAN] = n_samp > 0 ? A[HA_VAR_SUM] * inv : nan; f[NB_F_VARL_MAX] = n_samp > 0 ? A[HA_VAR_MAX] : nan;
+  f[NB_F_TIDAL_MEAN] = n_samp > 0 ? 0.0 : nan; f[NB_F_TIDAL_MAX] = n_samp > 0 ? 0.0 : nan;
+  f[NB_F_MEGNO] = megno; f[NB_F_LYAP_TIME] = lyap;
+  f[NB_F_IS_STABLE] = ((ed < 0.01) && (ld < 0.01) && (com_mean < 1.0) && (megno < 10.0)) ? 1.0 : 0.0;
+  f[NB_F_E0] = E0; f[NB_F_E1] = E1; f[NB_F_L0] = L0; f[NB_F_L1] = L1; f[NB_F_T_END] = t_end;
+}
+
+// 9..64 bodies, one CTA per system (hamsoft_mid.cu)
+int hamsoft_mid_run(const HsArgs& a, int N, cudaStream_t st);
+int hamsoft_mid_setup(const double* m, const double* q, double G, int B, int N, unsigned flags, double dt, double* hs,
+                      double* eps_pi, int32_t* n_sub, cudaStream_t st);
+int hamsoft_mid_probe(const double* m, const double* q, const double* v, double G, int B, int N, const double* eps_pi,
+                      const double* hs, double* out, cudaStream_t st);
+
 }  // namespace nb

@@ -102,9 +102,8 @@ class DeviceBucket:
         self.q = _to_dev(q, torch.float64, self.device).clone()
         self.v = _to_dev(v, torch.float64, self.device).clone()
         self.B, self.N = int(self.m.shape[0]), int(self.m.shape[1])
-        n_max = 8 if self.mode == L.MODE_HAMSOFT else 64
-        if not (2 <= self.N <= n_max):
-            raise L.NBodyB200Error(f"ensemble kernels support N = 2..{n_max} bodies per system in this mode, got {self.N}")
+        if not (2 <= self.N <= 64):
+            raise L.NBodyB200Error(f"ensemble kernels support N = 2..64 bodies per system, got {self.N}")
         self.eps = _to_dev(np.broadcast_to(np.asarray(eps, dtype=np.float64), (self.B,))
                            if not isinstance(eps, torch.Tensor) else eps, torch.float64, self.device)
         self.n_sub = torch.ones((self.B,), dtype=torch.int32, device=self.device)

@@ -87,8 +87,8 @@ def test_hamsoft_through_host_entry_matches_device_path():
     sequence the golden tests pin (tests/test_gpu_hamsoft.py), so the numbers are identical."""
     from nbodysimproject_b200 import ensemble as E, hamsoft as H, _lib as L
     from nbodysimproject_b200.simulation import SimConfig
-    for N in (3, 5):
-        B = 257
+    for N in (3, 5, 10):              # 10: one CTA per system (csrc/hamsoft_mid.cu)
+        B = 257 if N <= 8 else 33
         m, q, v, eps, rr, rv = _bucket(B, N, seed=21)
         soft = np.full(B, 0.05)
         r = E.analyze_host(m, q, v.copy(), soft, 1.0, "ham_soft", 40, 0.01, 10, rr, rv, L.PREP_REMOVE_COM, n_chunks=3,
