@@ -164,6 +164,12 @@ def flops_main(N, n_sub_sum, n_steps):
     return float(n_sub_sum) * n_steps * (3 * 14.0 * N * (N - 1) + 36.0 * N)
 
 
+def flops_megno(N, B, n_sub_sum, n_megno):
+    """SURVEY.md section 8d, "system-step, yoshida4 + MEGNO" = 3 x 14 N(N-1) + 19 N(N-1) + 44 N: a MEGNO step is a
+    macro step (n_sub sub-steps) plus one tangent-map evaluation (19 flop / ordered pair + 8 N for the tangent update)."""
+    return flops_main(N, n_sub_sum, n_megno) + float(B) * n_megno * (19.0 * N * (N - 1) + 8.0 * N)
+
+
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the reference's own Python path when a checkout is importable (baseline/_ref/minbody or $NBODY_REFERENCE;
 # the reference is pure Python, is not pip-installable and does not travel to the GPU box, so normally it is not),
@@ -450,7 +456,7 @@ def ensemble_section(args, ctx):
         hb["status"] = torch.empty((B,), dtype=torch.int32).pin_memory()
         host[N] = hb
         sets = []
-        for _ in range(1):          # one buffer / stream set (two sets interleaved worse: the step time became order-sensitive)
+        for _ in range(max(1, args.sets)):   # buffer / stream sets: consecutive steps alternate between them
             bk = E.DeviceBucket(hb["m"], hb["q"], hb["v"], hb["eps"], 1.0, MODE, dev)
             if sets:
                 bk.v0, bk.q0, bk.rdr, bk.rdv = sets[0].v0, sets[0].q0, sets[0].rdr, sets[0].rdv
@@ -477,6 +483,7 @@ def ensemble_section(args, ctx):
     timed_step = [0]
 
     step_no = [0]
+    inflight = []
     # launch order of the buckets: the large-N buckets first (their sequential sub-step tails are the longest)
     issue_order = [int(x) for x in args.order.split(",")] if args.order else list(Ns)
 
@@ -490,7 +497,7 @@ def ensemble_section(args, ctx):
         nonlocal launches_per_step
         cur = torch.cuda.current_stream()
         n = 0
-        par = 0
+        par = step_no[0] % max(1, args.sets)
         step_no[0] += 1
         # the construction-time kernels of every bucket first (0.3 % of the step), then the runs: nb_ensemble_run_f64
         # launches each bucket's sub-step-heavy head at high priority, so no head waits behind another bucket's bulk
@@ -511,6 +518,19 @@ def ensemble_section(args, ctx):
                 bk.dyn = bk.run(DT, N_STEPS, interval, N_MEGNO, bk.rdr, bk.rdv, flags=L.RUN_ENERGY, t_main=ts)  # 2+2+1+1 kernels
                 n += 10
             devb[N] = bk                  # the bucket of the most recent step (cross-checks below)
+        if args.sets > 1:
+            # a streaming caller keeps a bounded number of steps in flight: step k is enqueued, then the host waits for
+            # step k - (sets - 1) (event waits on the bucket streams, no device-wide join) -- exactly what the e2e leg does
+            # through nb_host_sync
+            evs = []
+            for N in issue_order:
+                ev = torch.cuda.Event()
+                ev.record(devb2[N][par].stream)
+                evs.append(ev)
+            inflight.append(evs)
+            while len(inflight) > args.sets - 1:
+                for ev in inflight.pop(0):
+                    ev.synchronize()
         if last:
             for N in Ns:
                 for b2 in devb2[N]:
@@ -605,12 +625,13 @@ def ensemble_section(args, ctx):
     roof = None
     if rank == 0:
         peak = L.peak_flops(0, local)
-        tot_fl, per = 0.0, []
+        tot_fl, meg_fl, per = 0.0, 0.0, []
         for N in Ns:
             bk = devb[N]
             nsub_sum = int(bk.n_sub.sum().item())       # n_sub of the last timed step (deterministic in the inputs)
             bk.flops = flops_main(N, nsub_sum, N_STEPS)
             tot_fl += bk.flops
+            meg_fl += flops_megno(N, bk.B, nsub_sum, N_MEGNO)
             ts = stamps[N][:args.steps].cpu().numpy()
             bk.ts = ts
             per.append(dict(N=N, B=bk.B, mean_n_sub=nsub_sum / bk.B, max_n_sub=int(bk.n_sub.max().item()),
@@ -619,24 +640,35 @@ def ensemble_section(args, ctx):
         # earliest start of the first step to the latest end of the last one, divided by the number of steps
         span = max(devb[N].ts[:, 1].max() for N in Ns) - min(devb[N].ts[:, 0].min() for N in Ns)
         win = float(span) * 1e-9 / args.steps
-        ach = tot_fl / win * 1e-12
-        roof = {"bound": "fp64", "kernel": "ensemble_main_kernel<N=3..8, yoshida4> (6 concurrent launches per step)",
+        # the span also contains the MEGNO kernels (and prepare / sort / energy / finalize) of every timed step but the
+        # last, whose MEGNO phase starts after the last main-phase stamp: their algorithmic flops belong to the same
+        # window (SURVEY.md 8d states the C3 unit as "system-step, yoshida4 + MEGNO")
+        meg_in = meg_fl * (args.steps - 1) / float(args.steps)
+        ach_main = tot_fl / win * 1e-12
+        ach = (tot_fl + meg_in) / win * 1e-12
+        roof = {"bound": "fp64", "kernel": "ensemble_main_kernel + ensemble_megno_kernel <N=3..8, yoshida4> "
+                                           "(6 + 6 concurrent launches per step)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "frac_nominal": ach / NOMINAL_FP64, "peak_nominal": NOMINAL_FP64,
+                "main_phase_only": {"achieved": ach_main, "frac": ach_main / peak, "flops_per_step": tot_fl,
+                                    "note": "r1 / early-r2 accounting: main-phase flops over the same window (which "
+                                            "also holds the MEGNO kernels' time)"},
+                "flops_megno_phase_per_step": meg_fl,
                 "traffic": (lambda t: None if t is None else t * (B_total / float(1 << 20)))(
                     _traffic("ensemble_main_six_launches_bytes_per_2p20_systems")),
                 "traffic_note": "dram__bytes_read + dram__bytes_write over the main-phase launches of one step from the "
                                 "committed ncu capture of this command at 2^20 systems/GPU (profiles/r2_traffic.json, "
                                 "tools/ncu_traffic.py), scaled by the batch size; the state is read once and lives in "
                                 "registers (algorithmic bytes: ~0.45 KB in + 0.18 KB out per system = 0.66 GB/step)",
-                "flops_per_step": tot_fl, "ms": win * 1e3,
+                "flops_per_step": tot_fl + meg_in, "ms": win * 1e3,
                 "timing": "%globaltimer stamps published by the main kernels themselves (first CTA start, last warp end; "
                           "nb_ensemble_run_counted_f64 t_main) inside the timed steps; span from the earliest start of the "
                           "first timed step to the latest end of the last one over all six buckets, divided by the steps "
                           "(consecutive steps are pipelined, so per-step windows overlap)",
                 "peak_source": "nb_peak_flops(0): register-resident DFMA micro-benchmark, same GPU, same run "
                                "(MEASURED_PEAKS.json has no FP64 figure; nominal 64 DFMA/clk/SM x 148 x 1.965 GHz = 37.2)",
-                "flop_model": "SURVEY.md 8d: per sub-step 3 x 14 N(N-1) + 36 N",
+                "flop_model": "SURVEY.md 8d: per sub-step 3 x 14 N(N-1) + 36 N; per MEGNO step additionally 19 N(N-1) + 8 N "
+                              "for the tangent map",
                 "share_of_step": win / (t_dev / args.steps), "per_bucket": per}
 
     # ---- N > 1: cross-rank correctness (the reference's contract: per-system results independent of batching,
@@ -1201,6 +1233,8 @@ def main():
     ap.add_argument("--heavy-threshold", type=int, default=-1, dest="heavy_threshold",
                     help="tuning sweeps only: fixed n_sub threshold of the latency mappings on the device-resident path "
                          "(-1 = the automatic N-only rule, the product setting)")
+    ap.add_argument("--sets", type=int, default=1,
+                    help="device path: buffer / stream sets that consecutive steps alternate between (steps in flight)")
     ap.add_argument("--order", default="", help="tuning only: launch order of the N buckets on the device path, e.g. 8,7,6,5,4,3")
     ap.add_argument("--horizon", type=int, default=0,
                     help="integrator steps per system for --workload c4 / c1 (default 1000; C4 as worded: 1000000)")

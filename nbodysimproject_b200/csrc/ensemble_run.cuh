@@ -28,6 +28,7 @@
 #define NB_WH_MINB_MAXN 5
 #endif
 
+
 namespace nb {
 
 // ---------------------------------------------------------------------------------------------
@@ -192,19 +193,28 @@ __device__ __forceinline__ int substep(SysState<N>& s, const double* m, double G
     pair_pass<N, TANGENT, GUARD>(s, drx, dry, dax, day);
     kick<N>(s, 0.5 * ha);
   } else {  // NB_MODE_WHFAST: Kepler(h/2) . full-force kick(h) . Kepler(h/2)   whfast_scheme.py:71-93
-    kep = kepler_drift<N, EXACT>(s, m, G, 0.5 * h, iters);
-    if (EXACT) {
-      // physically correct Wisdom-Holman: kick with the INTERACTION acceleration only (the star-planet Kepler
-      // terms are already in the drift); the reference kicks with the full force (whfast_scheme.py:85-88)
-      double ix[N], iy[N];
-      wh_interaction_accel<N>(s, m, G, ix, iy);
+    // two trips of one loop, so that the Kepler solver -- by far the largest piece of code -- is instantiated once per
+    // kernel (+5 % on the C4 cohort: instruction fetch).  Tried and dropped (r2, measured): solving the planets of a
+    // system W = 2 / 3 at a time in lock-step so that their dependency chains interleave -- bit-identical, but 1.6x
+    // (N = 3) to 5x (N = 4, 5) SLOWER: every lane then runs to the slower planet's iteration count, and a converged
+    // lane divides 0 by f', which is the generic division's slow path.
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      kep = max(kep, kepler_drift<N, EXACT>(s, m, G, 0.5 * h, iters));
+      if (half == 0) {
+        if (EXACT) {
+          // physically correct Wisdom-Holman: kick with the INTERACTION acceleration only (the star-planet Kepler
+          // terms are already in the drift); the reference kicks with the full force (whfast_scheme.py:85-88)
+          double ix[N], iy[N];
+          wh_interaction_accel<N>(s, m, G, ix, iy);
 #pragma unroll
-      for (int i = 0; i < N; ++i) { s.ax[i] = ix[i]; s.ay[i] = iy[i]; }
-    } else {
-      pair_pass<N, false, GUARD>(s, nullptr, nullptr, nullptr, nullptr);
+          for (int i = 0; i < N; ++i) { s.ax[i] = ix[i]; s.ay[i] = iy[i]; }
+        } else {
+          pair_pass<N, false, GUARD>(s, nullptr, nullptr, nullptr, nullptr);
+        }
+        kick<N>(s, h);
+      }
     }
-    kick<N>(s, h);
-    kep = max(kep, kepler_drift<N, EXACT>(s, m, G, 0.5 * h, iters));
     if (TANGENT) pair_pass<N, true, GUARD>(s, drx, dry, dax, day);
   }
   return kep;
