@@ -29,6 +29,11 @@
 #endif
 
 
+#ifndef NB_Y4_ROLL_MINN
+#define NB_Y4_ROLL_MINN 6     // yoshida4 main kernel: body counts from which the three stages run as a rolled loop (one
+                              // instance of the unrolled pair loop: C3 step 54.7 -> 53.9 ms; rolling N <= 5 as well: 54.1)
+#endif
+
 namespace nb {
 
 // ---------------------------------------------------------------------------------------------
@@ -183,15 +188,26 @@ __device__ __forceinline__ int substep(SysState<N>& s, const double* m, double G
     // roundings by <= 1 ulp of the kick; 4N FP64 operations fewer per sub-step)
     const double hab = 0.5 * ha + 0.5 * hb;
     kick<N>(s, 0.5 * ha);
-    drift<N>(s, ha);
-    pair_pass<N, false, GUARD>(s, nullptr, nullptr, nullptr, nullptr);
-    kick<N>(s, hab);
-    drift<N>(s, hb);
-    pair_pass<N, false, GUARD>(s, nullptr, nullptr, nullptr, nullptr);
-    kick<N>(s, hab);
-    drift<N>(s, ha);
-    pair_pass<N, TANGENT, GUARD>(s, drx, dry, dax, day);
-    kick<N>(s, 0.5 * ha);
+    if (!TANGENT && N >= NB_Y4_ROLL_MINN) {
+      // the three stages as trips of one loop: one instance of the unrolled pair loop per kernel instead of three
+      // (same operations in the same order: bit-identical)
+#pragma unroll 1
+      for (int st = 0; st < 3; ++st) {
+        drift<N>(s, st == 1 ? hb : ha);
+        pair_pass<N, false, GUARD>(s, nullptr, nullptr, nullptr, nullptr);
+        kick<N>(s, st == 2 ? 0.5 * ha : hab);
+      }
+    } else {
+      drift<N>(s, ha);
+      pair_pass<N, false, GUARD>(s, nullptr, nullptr, nullptr, nullptr);
+      kick<N>(s, hab);
+      drift<N>(s, hb);
+      pair_pass<N, false, GUARD>(s, nullptr, nullptr, nullptr, nullptr);
+      kick<N>(s, hab);
+      drift<N>(s, ha);
+      pair_pass<N, TANGENT, GUARD>(s, drx, dry, dax, day);
+      kick<N>(s, 0.5 * ha);
+    }
   } else {  // NB_MODE_WHFAST: Kepler(h/2) . full-force kick(h) . Kepler(h/2)   whfast_scheme.py:71-93
     // two trips of one loop, so that the Kepler solver -- by far the largest piece of code -- is instantiated once per
     // kernel (+5 % on the C4 cohort: instruction fetch).  Tried and dropped (r2, measured): solving the planets of a

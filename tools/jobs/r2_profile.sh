@@ -3,6 +3,7 @@
 # gpurun copies back at most 64 MiB: every .ncu-rep is summarised on the box (tools/ncu_key.py, tools/ncu_lines.py) and
 # only the two smallest reports travel.
 O=gpurun_out
+python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_c4_horizon.py::test_million_steps_on_65536_systems 2>&1 | tail -2
 ( time python bench.py > $O/r2_bench_n1.json 2> $O/r2_bench_n1.err ) 2> $O/r2_bench_n1.time; tail -3 $O/r2_bench_n1.time | head -1
 ( time python bench.py --impl reference --steps 5 --warmup 1 > $O/r2_bench_ref.json 2>/dev/null ) 2> $O/r2_bench_ref.time
 python bench.py --workload c1 > $O/r2_bench_c1.json 2>/dev/null
