@@ -98,46 +98,54 @@ __device__ __forceinline__ int kepler_reference(double& rx, double& ry, double& 
   int it = 0;
   double last_step = 0.0;
   const sd k1 = r0 * vr0 / sqrt_mu, k2 = sd(1.0) - alpha * r0, k3 = sqrt_mu * dt;     // loop invariants, same rounding
-  for (; it < 64;) {
-    ++it;
+  // ONE loop holds the only instance of the Stumpff series: the Newton trips, plus -- when the series values at hand do
+  // not belong to the final iterate -- one closing trip (`fin`) that evaluates them there (kepler_solver.py:81-83)
+  bool fin = false;
+  for (;;) {
     const sd z = alpha * chi * chi;
-    c2p = c2.v; c3p = c3.v;
+    if (!fin) { ++it; c2p = c2.v; c3p = c3.v; }
     cfunc_reference(z.v, c0, c1, c2, c3);
+    if (fin) break;
     have_c = true;                               // (c2, c3) belong to the current chi
+    bool stop = false;
     const sd f = k1 * chi * chi * c1 + k2 * chi * chi * chi * c2 + r0 * chi - k3;
     const sd fp = k1 * chi * (sd(1.0) - alpha * chi * chi * c2) + k2 * chi * chi * c1 + r0;
-    if (fp.v == 0.0) break;
-    const sd chi_new = chi - f / fp;
-    last_step = fabs(chi_new.v - chi.v);
-    if (chi_new.v == chi.v) {
-      chi = chi_new;
-      break;
-    }
-    // Exact-cycle shortcut (bit-identical result): the Newton map is a pure function of chi, so chi_new == x2 means the
-    // iterates alternate between chi_new and chi for the rest of the reference's 64 iterations; its final iterate is
-    // the one with the parity of 64.  Detected after ~8 iterations instead of running all 64 in lock-step per warp.
-    if (chi_new.v == x2) {
-      if (((64 - it) & 1) == 0) {                // final iterate = chi_new == the iterate BEFORE chi: its series values
+    if (fp.v == 0.0) {
+      stop = true;
+    } else {
+      const sd chi_new = chi - f / fp;
+      last_step = fabs(chi_new.v - chi.v);
+      if (chi_new.v == chi.v) {
         chi = chi_new;
-        c2 = sd(c2p); c3 = sd(c3p);
-        have_c = it >= 2;
+        stop = true;
+      } else if (chi_new.v == x2) {
+        // Exact-cycle shortcut (bit-identical result): the Newton map is a pure function of chi, so chi_new == x2 means
+        // the iterates alternate between chi_new and chi for the rest of the reference's 64 iterations; its final
+        // iterate is the one with the parity of 64.  Detected after ~8 iterations instead of running all 64 in lock-step
+        // per warp.
+        if (((64 - it) & 1) == 0) {              // final iterate = chi_new == the iterate BEFORE chi: its series values
+          chi = chi_new;
+          c2 = sd(c2p); c3 = sd(c3p);
+          have_c = it >= 2;
+        }
+        executed += it - 64;                     // counted work = iterations actually executed, not the reference's 64
+        it = 64;
+        stop = true;
+      } else {
+        x2 = chi.v;
+        chi = chi_new;
+        have_c = false;                          // the new chi has not been evaluated yet
       }
-      executed += it - 64;                       // counted work = iterations actually executed, not the reference's 64
-      it = 64;
-      break;
     }
-    x2 = chi.v;
-    chi = chi_new;
-    have_c = false;                              // the new chi has not been evaluated yet
+    if (stop || it >= 64) {
+      if (have_c) break;
+      fin = true;
+    }
   }
   // the reference's exit test is exact equality, so running into the 64-iteration cap while hovering within a
   // few ulps of the root is normal; only a cap hit with a still-moving iterate is reported (as 65)
   executed += it;
   if (it >= 64 && !(last_step <= 1e-9 * fabs(chi.v))) it = 65;
-  if (!have_c) {
-    const sd z = alpha * chi * chi;
-    cfunc_reference(z.v, c0, c1, c2, c3);
-  }
   const sd f = sd(1.0) - chi * chi * c2 / r0;
   const sd g = dt - chi * chi * chi * c3 / sqrt_mu;
   const sd nx = f * r_x + g * v_x;

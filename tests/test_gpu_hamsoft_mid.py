@@ -85,6 +85,46 @@ def test_mid_hamsoft_constructor_probe_and_steps_vs_oracle(N, seed, scale, soft,
     assert int(b.bk.status[0]) & 1 == 0
 
 
+@pytest.mark.parametrize("use_soft,disabled", [(False, False), (True, True)])
+def test_mid_hamsoft_barrier_policies_vs_oracle(use_soft, disabled):
+    """Reflection fold (epsilon folded into a squeezed [eps_min, eps_max], pi flipped) and disabled barrier at N = 9
+    (hamsoft_utils.py:150-176, hamsoft_stepper.py:72-80, 107-113, 261-303); the oracle's policies are pinned to the live
+    reference by tests/test_oracle_golden.py::test_hamsoft_barrier_policies_vs_golden."""
+    from nbodysimproject_b200 import hamsoft as H
+    from nbodysimproject_b200.hamsoft import P
+    from nbodysimproject_b200.simulation import SimConfig
+    from oracle.hamsoft_oracle import HamSoftOracleSim
+    N, dt, soft, K, steps = 9, 1e-4, 0.05, 2, 4
+    m, q, v = _cluster(N, 9, 0.3)
+    o = HamSoftOracleSim(m, q, v, softening=soft, skip_cm_recenter=True, initial_dt=dt, use_soft_barrier=use_soft,
+                         disable_barrier=disabled)
+    cfg = SimConfig()
+    cfg.use_soft_barrier, cfg.disable_barrier = use_soft, disabled
+    hs, s0 = H.default_params(cfg, soft, 0.1 * soft)
+    assert hs[0, P["policy"]] == (2.0 if disabled else 1.0)
+    b = H.HamSoftBucket(m[None], q[None], v[None], hs, np.array([[s0[0], 0.0]]), 1.0)
+    b.setup(calibrate=True, freeze_dt=dt)
+    assert np.allclose(_ctor_row(b), _oracle_row(o), rtol=1e-12, atol=0)
+    if not disabled:
+        # squeeze the interval around the start value so that the spring flow crosses both walls within a few sub-steps
+        lo, hi = o.eps * (1.0 - 2e-4), o.eps * (1.0 + 2e-4)
+        o.eps_min, o.eps_max = lo, hi
+        b.hs[0, P["eps_min"]] = lo
+        b.hs[0, P["eps_max"]] = hi
+    o.frozen_n_sub = K
+    o.macro_dt_frozen = dt
+    b.n_sub[:] = K
+    for _ in range(steps):
+        o.step(dt)
+    b.run(dt, steps)
+    ep = b.eps_pi.cpu().numpy()[0]
+    assert relerr(b.bk.q.cpu().numpy()[0], o.q) < 1e-8
+    assert abs(ep[0] - o.eps) <= 1e-7 * abs(o.eps), (ep, o.eps, o.pi)
+    assert abs(ep[1] - o.pi) <= 1e-5 * max(abs(o.pi), 1e-6), (ep, o.eps, o.pi)
+    if not disabled:
+        assert lo <= ep[0] <= hi
+
+
 def test_mid_hamsoft_64_bodies_constructor_eps_star_and_invariants():
     """N = 64 (257 evaluations per S half-flow): constructor and eps* against the oracle (the oracle's 257-solve gradient
     takes a minute, so the stepping check is the flow's own invariants: linear momentum is conserved by the pairwise
