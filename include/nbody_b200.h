@@ -36,7 +36,8 @@ extern "C" {
 #define NB_MIN_N 2
 #define NB_MAX_N 8             /* register-resident ensemble kernels are templated on N = 2..8 (all modes) */
 #define NB_MAX_N_MID 64        /* 9..64 bodies: one CTA per system (verlet / yoshida4 / whfast / ham_soft incl. setup and
-                                  probe, pair + variational calls, prepare, host entry); classic adaptive softening: N <= 8 */
+                                  probe, pair + variational calls, prepare, host entry); classic adaptive softening: one
+                                  thread per system */
 
 /* integrator_mode (sim_config.py:19-24) */
 #define NB_MODE_VERLET 0

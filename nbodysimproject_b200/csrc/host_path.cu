@@ -188,7 +188,6 @@ static int analyze_host_ex(const double* m, const double* q, double* v, const do
   const bool keep_v = (o.flags & NB_HOST_KEEP_V) != 0;
   if (slot < 0 || slot >= NB_HOST_SLOTS) { set_error("nb_ensemble_analyze_host: slot out of range"); return NB_ERR_ARG; }
   if (!m || !q || !v || !eps || !dyn_features || B < 0 || N < NB_MIN_N || N > NB_MAX_N_MID || n_steps < 0 || n_megno < 0) { set_error("nb_ensemble_analyze_host: bad arguments"); return NB_ERR_ARG; }
-  if (N > NB_MAX_N && opts_in && (opts_in->flags & NB_HOST_ADAPTIVE)) { set_error("nb_ensemble_analyze_host: adaptive softening covers N <= 8 bodies"); return NB_ERR_UNSUPPORTED; }
   if (mode != NB_MODE_VERLET && mode != NB_MODE_YOSHIDA4 && mode != NB_MODE_WHFAST && !hamsoft) { set_error("nb_ensemble_analyze_host: unknown integrator mode"); return NB_ERR_ARG; }
   if (n_megno > 0 && !dev_tangent && (!raw_dr || !raw_dv)) { set_error("nb_ensemble_analyze_host: n_megno > 0 needs raw_dr/raw_dv (or NB_HOST_DEVICE_TANGENT)"); return NB_ERR_ARG; }
   if (adaptive && (hamsoft || mode == NB_MODE_WHFAST || !o.soft_par)) { set_error("nb_ensemble_analyze_host: NB_HOST_ADAPTIVE needs verlet / yoshida4 and opts->soft_par"); return NB_ERR_UNSUPPORTED; }

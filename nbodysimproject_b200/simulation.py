@@ -216,15 +216,13 @@ class NBodySimulation:
         self._in_integration = False
         self._acc_cached = False
         self._status = 0
-        # Body counts: 2..8 register-resident kernels, 9..64 one CTA per system (every integrator mode; classic adaptive
-        # softening stays N <= 8).  The reference never raises (simulation.py:76-78): what the fp64 kernels do not cover
-        # is reported and the simulation is disabled (n_bodies = 0), like any other unusable input; LargeNSimulation is
-        # the fp32 large-N path.
-        n_cap = 8 if (self._adaptive_softening and self._integrator_mode != "ham_soft") else 64
+        # Body counts: 2..8 register-resident kernels, 9..64 one CTA (classic adaptive softening: one thread) per system,
+        # every integrator mode.  The reference never raises (simulation.py:76-78): beyond 64 bodies the simulation is
+        # reported and disabled (n_bodies = 0), like any other unusable input; LargeNSimulation is the fp32 large-N path.
+        n_cap = 64
         if self.n_bodies > n_cap:
             print(f"[nbodysimproject_b200] {self.n_bodies} bodies in mode '{self._integrator_mode}': the fp64 kernels cover "
-                  f"up to {n_cap} (64; classic adaptive softening: 8); simulation disabled -- use LargeNSimulation "
-                  f"for large N")
+                  f"up to {n_cap}; simulation disabled -- use LargeNSimulation for large N")
             self._disable_simulation()
             return
         remove_com = not skip_cm_recenter

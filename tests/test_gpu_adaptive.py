@@ -74,6 +74,46 @@ def test_step_many_equals_repeated_steps_and_batch_vs_oracle():
     assert a.manager.history == b2.manager.history
 
 
+@pytest.mark.parametrize("N,mode", [(12, "yoshida4"), (20, "verlet")])
+def test_mid_n_adaptive_softening_vs_oracle(N, mode):
+    """9 .. 64 bodies (run-time body count, one thread per system; csrc/ensemble_adaptive.cu): stepping through the C ABI
+    and through the facade against the oracle, as for N <= 8 above; the reference accepts any body count
+    (simulation.py:39-162)."""
+    import nbodysimproject_b200 as nb
+    from nbodysimproject_b200 import ensemble as E
+    from oracle import nbody_oracle as O
+    rng = np.random.RandomState(N)
+    B = 3
+    m = rng.uniform(0.3, 2.0, (B, N))
+    q = rng.randn(B, N, 2) * 2.0
+    v = rng.randn(B, N, 2) * 0.3
+    v -= (m[:, :, None] * v).sum(1, keepdims=True) / m.sum(1)[:, None, None]
+    soft = 0.08
+    href = np.array([O.classic_h_sub_ref(q[b], m[b], 1.0, 0.01, 50) for b in range(B)])
+    qf, vf, hist, dE, st = E.advance_bucket_adaptive(m, q, v, soft, soft, 0.1 * soft, 1.0, href, 1.0, mode, 0.01, 20)
+    assert np.all(st == 0) and hist.shape == (B, 20)
+    for b in range(B):
+        o = O.OracleSim(m[b], q[b], v[b], softening=soft, integrator_mode=mode, adaptive_softening=True,
+                        skip_cm_recenter=True)
+        eps = []
+        for _ in range(20):
+            o.step(0.01)
+            eps.append(o.s)
+        assert np.allclose(hist[b], eps, rtol=1e-9)
+        assert relerr(qf[b], o.q) < 1e-9
+        assert dE[b] == pytest.approx(o.softening_energy_delta, rel=1e-8, abs=1e-11)
+    sim = nb.NBodySimulation(masses=m[0], positions=q[0], velocities=v[0], softening=soft, integrator_mode=mode,
+                             adaptive_softening=True)
+    o = O.OracleSim(m[0], q[0], v[0], softening=soft, integrator_mode=mode, adaptive_softening=True)
+    assert sim.n_bodies == N
+    for _ in range(10):
+        sim.step(0.01)
+        o.step(0.01)
+    assert relerr(sim.pos, o.q) < 1e-9
+    assert sim.manager.s == pytest.approx(o.s, rel=1e-9)
+    assert sim.softening_energy_delta == pytest.approx(o.softening_energy_delta, rel=1e-8, abs=1e-11)
+
+
 def test_stability_analysis_of_adaptive_sims_vs_golden():
     """StabilityAnalyzer('full') on adaptive-softening sims against the live reference's rows
     (oracle/make_golden_adaptive.py features): tolerance 1e-8 + 100 x the reference's own sensitivity per column."""

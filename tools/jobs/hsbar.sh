@@ -1,0 +1,11 @@
+#!/bin/bash
+python -m pytest tests/test_gpu_hamsoft.py tests/test_gpu_adaptive.py tests/test_gpu_midn.py tests/test_gpu_host_path.py -x -q 2>&1 | tail -3
+for v in tools/variants/lib_nobar.so nbodysimproject_b200/libnbody_b200.so tools/variants/lib_nobar.so nbodysimproject_b200/libnbody_b200.so; do
+  echo "== $v"
+  python tools/lib_override.py $v --workload c1 --no-cpu 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('c1 value %.4e  e2e %.4e  ms %.1f' % (d['value'], d['e2e']['value'], d['ms_per_step']))
+"
+done
+for v in tools/variants/lib_nobar.so nbodysimproject_b200/libnbody_b200.so; do echo "== $v"; python tools/hs_variant.py $v 65536 100 2>&1 | tail -5; done
