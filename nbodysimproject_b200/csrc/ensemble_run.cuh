@@ -22,7 +22,10 @@
 #include "ensemble_pairlane.cuh"
 
 #ifndef NB_WH_MINB
-#define NB_WH_MINB 3          // whfast main kernel: resident CTAs per SM the register allocation must allow (N <= NB_WH_MINB_MAXN)
+#define NB_WH_MINB 5          // whfast main kernel: resident CTAs per SM the register allocation must allow (N <= NB_WH_MINB_MAXN).
+                              // 96 registers + 300-500 B of spills instead of 154-166 registers and none: a kernel alone is 0-6 %
+                              // slower, the three concurrent C4 buckets 13 % faster (1.12e9 -> 1.27e9; 3: 1.12, 4: 1.22,
+                              // 5 / 6 / 8: 1.27) -- the strictly rounded Newton chain is latency-bound (top stall `wait`)
 #endif
 #ifndef NB_WH_MINB_MAXN
 #define NB_WH_MINB_MAXN 5
