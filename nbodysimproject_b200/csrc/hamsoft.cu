@@ -689,8 +689,11 @@ __device__ __forceinline__ void hs_load_system(HsSh<N>& sh, const double* m, con
   }
 }
 
+// Resident CTAs per SM: the kernel is latency-bound (top stalls `wait`, `no_instruction`), so occupancy is worth more than
+// spill-free code from N = 5 up: 4 (N = 5, 6) and 3 (N = 7, 8) CTAs/SM with 80-230 B of spills instead of 3 / 2 without:
+// +12 % at N = 6, +30 % at N = 8; for N <= 4 more than 6 / 5 CTAs/SM gains nothing (N = 3: -4 % on the C1 batch).
 template <int N>
-__global__ void __launch_bounds__(128, (N <= 3 ? 6 : (N <= 4 ? 5 : (N <= 6 ? 3 : 2)))) hamsoft_run_kernel(HsArgs a) {
+__global__ void __launch_bounds__(128, (N <= 3 ? 6 : (N <= 4 ? 5 : (N <= 6 ? 4 : 3)))) hamsoft_run_kernel(HsArgs a) {
   constexpr int LPS = HsLanes<N>::LPS, SPW = 32 / LPS;   // lanes per system, systems per warp
   __shared__ HsSh<N> shs[4 * SPW];
   const int lane_full = threadIdx.x & 31;

@@ -1,5 +1,5 @@
 #!/bin/bash
-for v in nbodysimproject_b200/libnbody_b200.so tools/variants/lib_inl.so; do
+for v in nbodysimproject_b200/libnbody_b200.so tools/variants/lib_occ.so; do
   echo "== $v"
   python tools/lib_override.py $v --workload c1 --no-cpu 2>/dev/null | python -c "
 import json,sys
