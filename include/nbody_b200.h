@@ -87,8 +87,14 @@ enum {
   NB_HS_K_SOFT = 0, NB_HS_MU_SOFT, NB_HS_EPS_MIN, NB_HS_EPS_MAX, NB_HS_ALPHA_RUN, NB_HS_K_WALL,
   NB_HS_BARRIER_N, NB_HS_ETA, NB_HS_J_MAX_CAP, NB_HS_LAMBDA, NB_HS_POLICY /*0 soft barrier, 1 reflection (fold), 2 none*/,
   NB_HS_THETA_IMP, NB_HS_THETA_CAP, NB_HS_CHI_PI, NB_HS_OMEGA_SPR0, NB_HS_S0,
+  NB_HS_FLAGS /*bit mask NB_HS_FLAG_*, stored as a double*/,
   NB_HS_NPARAM
 };
+/* reference test hooks: SimConfig.freeze_s_subsystem (hamsoft_stepper.py:119-124, 592-600: no S half-flow, no pi half
+ * kick -- epsilon and pi stay frozen) and cfg._validate_S_only (hamsoft_stepper.py:270-284,
+ * hamiltonian_softening_integrator.py:804-835: a macro step is ONE sub-step S S between the folds, no V, no T) */
+#define NB_HS_FLAG_FREEZE_S 1
+#define NB_HS_FLAG_S_ONLY 2
 
 const char* nb_last_error(void);
 int nb_version(void);

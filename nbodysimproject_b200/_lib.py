@@ -37,7 +37,8 @@ STATIC_COLUMNS = [
 ]
 N_STATIC = len(STATIC_COLUMNS)
 HS_PARAMS = ["k_soft", "mu_soft", "eps_min", "eps_max", "alpha_run", "k_wall", "barrier_n", "eta",
-             "j_max_cap", "lambda", "policy", "theta_imp", "theta_cap", "chi_pi", "omega_spr0", "s0"]
+             "j_max_cap", "lambda", "policy", "theta_imp", "theta_cap", "chi_pi", "omega_spr0", "s0", "flags"]
+HS_FLAG_FREEZE_S, HS_FLAG_S_ONLY = 1, 2
 N_HS = len(HS_PARAMS)
 
 EXPORTS = [

@@ -538,14 +538,17 @@ __device__ __forceinline__ void hs_s_half(HsSh<N>& sh, double& eps, double& pi, 
   const double dp_inf = sqrt(dmax2);
   const double thr = P.jcap * p_scale;
   const double Ja = (dp_inf > thr && dp_inf > 0.0) ? J * (thr / dp_inf) : J;
-  if (act && mine && Ja != 0.0) {               // p += J grad eps*; v = p / m
+  // SimConfig.freeze_s_subsystem (hamsoft_stepper.py:119-124): the half-flow ends after the fold; predicated, not
+  // branched, because two systems may share the warp and the code above shuffles
+  const bool frozen = (P.flags & NB_HS_FLAG_FREEZE_S) != 0;
+  if (act && mine && Ja != 0.0 && !frozen) {    // p += J grad eps*; v = p / m
     const double im = hs_rcp(mi);
     sh.vx[i] = (mi * vx + Ja * gx) * im;
     sh.vy[i] = (mi * vy + Ja * gy) * im;
   }
   double pi_out = eta_t + kick2;
   hs_fold(eps_rot, pi_out, P);                   // hamsoft_stepper.py:72-80
-  if (act) { eps = eps_rot; pi = pi_out; }
+  if (act) { eps = frozen ? eps0 : eps_rot; pi = frozen ? pi0 : pi_out; }
 }
 
 // V half-kick: hamsoft_stepper.py:543-663 + pi_half_kick hamsoft_flows.py:1102-1132; body i on lane i.  The pair factor
@@ -586,7 +589,7 @@ __device__ __forceinline__ void hs_v_half(HsSh<N>& sh, double eps, double& pi, d
   const double s3t = grp_sum<LPS>(mine ? s3 : 0.0);
   const double dU = (eps == 0.0 || G == 0.0) ? 0.0 : G * eps * s3t;
   const double dB = (P.policy == 0) ? -hs_barrier_force(eps, P) : 0.0;
-  if (act) pi = pi - (dU + dB) * hh;
+  if (act && !(P.flags & NB_HS_FLAG_FREEZE_S)) pi = pi - (dU + dB) * hh;    // hamsoft_stepper.py:592-600
 }
 
 template <int N>
@@ -610,9 +613,10 @@ __device__ __forceinline__ void hs_strang(HsSh<N>& sh, double& eps, double& pi, 
   for (int half = 0; half < 2; ++half) {
     hs_s_half<N>(sh, eps, pi, h, lane, act, sweeps);
     if (half == 0) {
-      hs_v_half<N>(sh, eps, pi, G, h, lane, act);
-      hs_t_drift<N>(sh, h, lane, act);
-      hs_v_half<N>(sh, eps, pi, G, h, lane, act);
+      const bool vt = act && !(P.flags & NB_HS_FLAG_S_ONLY);       // cfg._validate_S_only: S S (hamsoft_stepper.py:270-284)
+      hs_v_half<N>(sh, eps, pi, G, h, lane, vt);
+      hs_t_drift<N>(sh, h, lane, vt);
+      hs_v_half<N>(sh, eps, pi, G, h, lane, vt);
     }
   }
   if (act) hs_fold(eps, pi, P);                  // hamsoft_stepper.py:300-303
@@ -711,7 +715,9 @@ __global__ void __launch_bounds__(128, (N <= 3 ? 6 : (N <= 4 ? 5 : (N <= 6 ? 4 :
   double eps = a.eps_pi[2 * (size_t)sys];
   double pi = a.eps_pi[2 * (size_t)sys + 1];
   const double G = a.G;
-  const int n_sub = max(1, a.n_sub ? a.n_sub[sys] : 1);
+  // cfg._validate_S_only: one sub-step per macro step whatever the frozen schedule (hamiltonian_softening_integrator.py:804-835)
+  const bool s_only = ((int)a.hs[(size_t)sys * NB_HS_NPARAM + NB_HS_FLAGS] & NB_HS_FLAG_S_ONLY) != 0;
+  const int n_sub = s_only ? 1 : max(1, a.n_sub ? a.n_sub[sys] : 1);
   const int n_sub_warp = SPW > 1 ? __reduce_max_sync(0xffffffffu, n_sub) : n_sub;
   const double h = a.dt / (double)n_sub;
   const double dt = a.dt;

@@ -10,7 +10,7 @@ namespace nb {
 
 struct HsPar {
   double k, mu, eps_min, eps_max, alpha, k_wall, eta, jcap, lam, theta_imp, theta_cap, chi_pi, omega0, s0;
-  int n_exp, policy;
+  int n_exp, policy, flags;
 };
 
 __device__ __forceinline__ HsPar hs_load(const double* p) {
@@ -19,7 +19,7 @@ __device__ __forceinline__ HsPar hs_load(const double* p) {
   h.alpha = p[NB_HS_ALPHA_RUN]; h.k_wall = p[NB_HS_K_WALL]; h.n_exp = (int)p[NB_HS_BARRIER_N]; h.eta = p[NB_HS_ETA];
   h.jcap = p[NB_HS_J_MAX_CAP]; h.lam = p[NB_HS_LAMBDA]; h.policy = (int)p[NB_HS_POLICY];
   h.theta_imp = p[NB_HS_THETA_IMP]; h.theta_cap = p[NB_HS_THETA_CAP]; h.chi_pi = p[NB_HS_CHI_PI];
-  h.omega0 = p[NB_HS_OMEGA_SPR0]; h.s0 = p[NB_HS_S0];
+  h.omega0 = p[NB_HS_OMEGA_SPR0]; h.s0 = p[NB_HS_S0]; h.flags = (int)p[NB_HS_FLAGS];
   return h;
 }
 

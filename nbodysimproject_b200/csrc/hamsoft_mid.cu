@@ -310,6 +310,11 @@ __device__ __forceinline__ void hm_s_half(HmSh& sh, int n, double& eps, double& 
   const double dt = 0.5 * h;
   double eps0 = eps, pi0 = pi;
   hs_fold(eps0, pi0, P);                         // hamsoft_stepper.py:107-113
+  if (P.flags & NB_HS_FLAG_FREEZE_S) {           // SimConfig.freeze_s_subsystem (hamsoft_stepper.py:119-124); CTA-uniform
+    eps = eps0;
+    pi = pi0;
+    return;
+  }
   bool fb;
   const double es = hm_eps_star_and_grad(sh, n, eps0, fb, sweeps);
   const HsSpring& R = sh.spr;
@@ -384,7 +389,7 @@ __device__ __forceinline__ void hm_v_half(HmSh& sh, int n, double eps, double& p
   const double s3t = hm_sum(sh, mine ? s3 : 0.0);
   const double dU = (eps == 0.0 || G == 0.0) ? 0.0 : G * eps * s3t;
   const double dB = (P.policy == 0) ? -hs_barrier_force(eps, P) : 0.0;
-  pi = pi - (dU + dB) * hh;
+  if (!(P.flags & NB_HS_FLAG_FREEZE_S)) pi = pi - (dU + dB) * hh;            // hamsoft_stepper.py:592-600
 }
 
 __device__ __forceinline__ void hm_t_drift(HmSh& sh, int n, double h) {
@@ -403,7 +408,7 @@ __device__ __forceinline__ void hm_strang(HmSh& sh, int n, double& eps, double& 
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     hm_s_half(sh, n, eps, pi, h, sweeps);
-    if (half == 0) {
+    if (half == 0 && !(P.flags & NB_HS_FLAG_S_ONLY)) {             // cfg._validate_S_only: S S (hamsoft_stepper.py:270-284)
       hm_v_half(sh, n, eps, pi, G, h);
       hm_t_drift(sh, n, h);
       hm_v_half(sh, n, eps, pi, G, h);
@@ -472,7 +477,8 @@ __global__ void __launch_bounds__(HM_THREADS) hamsoft_mid_run_kernel(HsArgs a, i
   double eps = a.eps_pi[2 * (size_t)sys];
   double pi = a.eps_pi[2 * (size_t)sys + 1];
   const double G = a.G;
-  const int n_sub = max(1, a.n_sub ? a.n_sub[sys] : 1);
+  const bool s_only = ((int)a.hs[(size_t)sys * NB_HS_NPARAM + NB_HS_FLAGS] & NB_HS_FLAG_S_ONLY) != 0;
+  const int n_sub = s_only ? 1 : max(1, a.n_sub ? a.n_sub[sys] : 1);   // hamiltonian_softening_integrator.py:804-835
   const double h = a.dt / (double)n_sub;
   const double dt = a.dt;
   __syncthreads();

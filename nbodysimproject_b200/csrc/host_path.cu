@@ -79,6 +79,7 @@ __global__ void hs_defaults_kernel(const double* __restrict__ soft, int B, doubl
   p[NB_HS_ALPHA_RUN] = 0.1; p[NB_HS_K_WALL] = 1.0e9; p[NB_HS_BARRIER_N] = 5.0; p[NB_HS_ETA] = 1.35;
   p[NB_HS_J_MAX_CAP] = 0.02; p[NB_HS_LAMBDA] = 0.3; p[NB_HS_POLICY] = 0.0; p[NB_HS_THETA_IMP] = 0.5;
   p[NB_HS_THETA_CAP] = 0.1; p[NB_HS_CHI_PI] = 0.2; p[NB_HS_OMEGA_SPR0] = 0.0; p[NB_HS_S0] = s0;
+  p[NB_HS_FLAGS] = 0.0;
   if (fill_eps_pi) { eps_pi[2 * (size_t)i] = fmax(s0, mn); eps_pi[2 * (size_t)i + 1] = 0.0; }
 }
 

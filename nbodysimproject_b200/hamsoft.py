@@ -42,6 +42,9 @@ def default_params(cfg, softening, min_softening, B=1):
     hs[:, P["chi_pi"]] = float(getattr(cfg, "chi_pi", 0.2))
     hs[:, P["omega_spr0"]] = 0.0
     hs[:, P["s0"]] = s0
+    # reference test hooks (hamsoft_stepper.py:119-124, 270-284, 592-600)
+    hs[:, P["flags"]] = ((L.HS_FLAG_FREEZE_S if bool(getattr(cfg, "freeze_s_subsystem", False)) else 0)
+                         | (L.HS_FLAG_S_ONLY if bool(getattr(cfg, "_validate_S_only", False)) else 0))
     return hs, s0
 
 

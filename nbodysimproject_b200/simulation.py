@@ -163,8 +163,9 @@ class NBodySimulation:
                  skip_cm_recenter: bool = False, integrator_mode: str | None = None, device=None):
         self.cfg = config.copy() if config else SimConfig()
         # reference test hooks that the GPU kernels do not implement (simulation.py:80-83, 159-162 float32 state arrays;
-        # hamsoft_eps_model.py:82-89; hamsoft_stepper.py:119-124, 270-284): reported, never silently ignored, never raised
-        for name in ("fast_float32", "use_legacy_eps_star", "fixed_eps_star", "freeze_s_subsystem", "_validate_S_only"):
+        # hamsoft_eps_model.py:82-89): reported, never silently ignored, never raised.  freeze_s_subsystem and
+        # _validate_S_only (hamsoft_stepper.py:119-124, 270-284) ARE implemented: flags of the ham_soft parameter row
+        for name in ("fast_float32", "use_legacy_eps_star", "fixed_eps_star"):
             if bool(getattr(self.cfg, name, False)):
                 print(f"[nbodysimproject_b200] SimConfig.{name} is not supported by the fp64 GPU kernels: "
                       f"running the production path (NB_ERR_UNSUPPORTED at the C ABI)")

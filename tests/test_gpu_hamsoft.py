@@ -232,3 +232,37 @@ def test_validate_ham_soft_scenarios_vs_reference():
             sim_eq.step_many(dt, n_steps)
             assert rel(sim_eq._pi, e[3]) < (1e-7 if tame else 1e-3), (key, sim_eq._pi, e[3])
             assert rel(sim_eq._epsilon, e[2]) < (1e-7 if tame else 1e-3)
+
+
+def test_hamsoft_config_hooks_vs_reference():
+    """SimConfig.freeze_s_subsystem (hamsoft_stepper.py:119-124, 592-600: epsilon, pi frozen, plain kick-drift-kick at the
+    frozen epsilon) and cfg._validate_S_only (:270-284: a step is S S, positions stay put) through the facade, against
+    outputs of the live reference (oracle/make_golden_hamsoft_hooks.py)."""
+    import nbodysimproject_b200 as nb
+    g = load_golden("hamsoft_hooks.npz")
+    dt = float(g["dt"])
+    for key in g["names"]:
+        key = str(key)
+        hook = str(g[key + "hook"])
+        cfg = nb.SimConfig()
+        setattr(cfg, hook, True)
+        sim = nb.NBodySimulation(config=cfg, masses=g[key + "m"], positions=g[key + "q_in"], velocities=g[key + "v_in"],
+                                 softening=float(g[key + "soft"]), integrator_mode="ham_soft")
+        ctor = g[key + "ctor"]
+        assert abs(sim._epsilon - ctor[0]) <= 1e-12 * abs(ctor[0]) and sim._integrator._frozen_n_sub == int(ctor[7])
+        done = 0
+        for mark in g[key + "marks"]:
+            mark = int(mark)
+            for _ in range(mark - done):
+                sim.step(dt)
+            done = mark
+            ref = g[key + f"ep{mark}"]
+            tol = 1e-9 if hook == "freeze_s_subsystem" else 1e-7     # S S: the finite-difference gradient drives v
+            assert relerr(sim.pos, g[key + f"q{mark}"]) < tol, (key, mark)
+            assert relerr(sim.vel, g[key + f"v{mark}"]) < 10 * tol, (key, mark, relerr(sim.vel, g[key + f"v{mark}"]))
+            assert abs(sim._epsilon - ref[0]) <= 1e-8 * abs(ref[0]), (key, mark, sim._epsilon, ref)
+            assert abs(sim._pi - ref[1]) <= 1e-6 * max(abs(ref[1]), 1e-9), (key, mark, sim._pi, ref)
+        if hook == "freeze_s_subsystem":
+            assert sim._epsilon == ctor[0] and sim._pi == 0.0
+        else:
+            assert np.array_equal(np.asarray(sim.pos), g[key + "q_in"])

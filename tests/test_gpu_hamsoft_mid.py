@@ -125,6 +125,38 @@ def test_mid_hamsoft_barrier_policies_vs_oracle(use_soft, disabled):
         assert lo <= ep[0] <= hi
 
 
+@pytest.mark.parametrize("hook", ["freeze_s_subsystem", "validate_s_only"])
+def test_mid_hamsoft_config_hooks_vs_oracle(hook):
+    """The two reference test hooks at N = 9 (flags of the parameter row; the oracle's hooks are pinned bit for bit to the
+    live reference by tests/test_oracle_golden.py::test_hamsoft_hooks_vs_golden)."""
+    from nbodysimproject_b200 import hamsoft as H, _lib as L
+    from nbodysimproject_b200.hamsoft import P
+    from nbodysimproject_b200.simulation import SimConfig
+    from oracle.hamsoft_oracle import HamSoftOracleSim
+    N, dt, soft, steps = 9, 1e-4, 0.05, 3
+    m, q, v = _cluster(N, 9, 0.3)
+    o = HamSoftOracleSim(m, q, v, softening=soft, skip_cm_recenter=True, initial_dt=dt, **{hook: True})
+    cfg = SimConfig()
+    setattr(cfg, "freeze_s_subsystem" if hook == "freeze_s_subsystem" else "_validate_S_only", True)
+    hs, s0 = H.default_params(cfg, soft, 0.1 * soft)
+    assert hs[0, P["flags"]] == (L.HS_FLAG_FREEZE_S if hook == "freeze_s_subsystem" else L.HS_FLAG_S_ONLY)
+    b = H.HamSoftBucket(m[None], q[None], v[None], hs, np.array([[s0[0], 0.0]]), 1.0)
+    b.setup(calibrate=True, freeze_dt=dt)
+    assert np.allclose(_ctor_row(b), _oracle_row(o), rtol=1e-12, atol=0)
+    if hook == "freeze_s_subsystem":
+        o.frozen_n_sub = 2
+        o.macro_dt_frozen = dt
+        b.n_sub[:] = 2
+    for _ in range(steps):
+        o.step(dt)
+    b.run(dt, steps)
+    ep = b.eps_pi.cpu().numpy()[0]
+    assert relerr(b.bk.q.cpu().numpy()[0], o.q) < 1e-9
+    assert relerr(b.bk.v.cpu().numpy()[0], o.v) < 1e-7
+    assert abs(ep[0] - o.eps) <= 1e-8 * abs(o.eps), (ep, o.eps)
+    assert abs(ep[1] - o.pi) <= 1e-6 * max(abs(o.pi), 1e-9), (ep, o.pi)
+
+
 def test_mid_hamsoft_64_bodies_constructor_eps_star_and_invariants():
     """N = 64 (257 evaluations per S half-flow): constructor and eps* against the oracle (the oracle's 257-solve gradient
     takes a minute, so the stepping check is the flow's own invariants: linear momentum is conserved by the pairwise

@@ -348,3 +348,28 @@ def test_adaptive_analysis_oracle_vs_golden():
         for c in cols:
             ref, sens = float(g[key + "f__" + c]), float(g[key + "sens__" + c])
             assert abs(row[c] - ref) <= 1e-9 * max(abs(ref), 1e-12) + 100 * sens, (key, c, row[c], ref)
+
+
+def test_hamsoft_hooks_vs_golden():
+    """SimConfig.freeze_s_subsystem and cfg._validate_S_only (oracle/make_golden_hamsoft_hooks.py, live reference)."""
+    from oracle.hamsoft_oracle import HamSoftOracleSim
+    g = load_golden("hamsoft_hooks.npz")
+    dt = float(g["dt"])
+    for key in g["names"]:
+        key = str(key)
+        hook = str(g[key + "hook"])
+        o = HamSoftOracleSim(g[key + "m"], g[key + "q_in"], g[key + "v_in"], softening=float(g[key + "soft"]),
+                             freeze_s_subsystem=(hook == "freeze_s_subsystem"), validate_s_only=(hook == "_validate_S_only"))
+        ctor = g[key + "ctor"]
+        mine = np.array([o.eps, o.pi, o.eps_min, o.eps_max, o.alpha_run, o.k_soft, o.mu_soft, float(o.frozen_n_sub),
+                         o.omega_spr0])
+        assert np.array_equal(mine, ctor), (key, mine, ctor)
+        done = 0
+        for mark in g[key + "marks"]:
+            mark = int(mark)
+            for _ in range(mark - done):
+                o.step(dt)
+            done = mark
+            assert np.array_equal(o.q, g[key + f"q{mark}"]), (key, mark)
+            assert np.array_equal(o.v, g[key + f"v{mark}"]), (key, mark)
+            assert np.array_equal(np.array([o.eps, o.pi, o.mu_soft]), g[key + f"ep{mark}"]), (key, mark)
